@@ -1,0 +1,79 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/* with the REAL reference CPU path (oracle/_ref/oracle_ref_avx2 = the reference's own
+RealSR::process_cpu + vendored ncnn b4ba207, AVX2 kernels, see oracle/build_ref.py).  Run in the build container
+(needs /root/reference for build_ref.py and images/0.png); the fixtures are committed because the GPU box has
+no /root/reference.  TEST INFRASTRUCTURE ONLY.
+
+Each case = <name>.in.npy (u8 HWC), <name>.out.npy (u8 HWC, 4x) and an entry in manifest.json."""
+import json, os, subprocess, sys, tempfile
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = os.path.join(ROOT, "oracle", "_ref", "oracle_ref_avx2")
+
+
+def noise(h, w, seed):
+    return np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+
+def natural(h, w, seed):
+    """box-blurred noise (SURVEY 8d 'natural' variant): smooth content, full u8 range"""
+    r = np.random.default_rng(seed).integers(0, 256, (h + 8, w + 8, 3)).astype(np.float64)
+    c = np.cumsum(np.cumsum(np.pad(r, ((1, 0), (1, 0), (0, 0))), 0), 1)
+    k = 7
+    b = (c[k:, k:] - c[:-k, k:] - c[k:, :-k] + c[:-k, :-k]) / (k * k)
+    b = b[:h, :w]
+    b = (b - b.min()) / (b.max() - b.min()) * 255.0
+    return np.clip(np.rint(b), 0, 255).astype(np.uint8)
+
+
+def run_ref(img, model, tilesize, tta, threads=8):
+    h, w, c = img.shape
+    with tempfile.TemporaryDirectory() as td:
+        fi, fo = os.path.join(td, "i.raw"), os.path.join(td, "o.raw")
+        img.tofile(fi)
+        mdir = os.path.join(ROOT, "models", model)
+        r = subprocess.run([REF, os.path.join(mdir, "x4.param"), os.path.join(mdir, "x4.bin"), fi, str(w), str(h),
+                            str(c), fo, str(tilesize), str(int(tta)), str(threads)], capture_output=True, text=True)
+        if r.returncode:
+            raise SystemExit(r.stderr)
+        info = json.loads(r.stdout.strip().splitlines()[-1])
+        return np.fromfile(fo, dtype=np.uint8).reshape(h * 4, w * 4, c), info
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    cases = [
+        # name, image, model, tilesize, tta
+        ("noise_40x36_jpeg_t200", noise(36, 40, 1001), "models-DF2K_JPEG", 200, 0),
+        ("natural_48x40_df2k_t32", natural(40, 48, 1002), "models-DF2K", 32, 0),
+        ("noise_50x33_df2k_t32", noise(33, 50, 1003), "models-DF2K", 32, 0),
+        ("natural_28x20_df2k_tta", natural(20, 28, 1004), "models-DF2K", 200, 1),
+        ("noise_37x23_jpeg_tta_t32", noise(23, 37, 1005), "models-DF2K_JPEG", 32, 1),
+        ("cfg1_noise_256_jpeg_t200", noise(256, 256, 1000), "models-DF2K_JPEG", 200, 0),
+        ("cfg1_noise_256_jpeg_t256", noise(256, 256, 1000), "models-DF2K_JPEG", 256, 0),
+    ]
+    try:
+        from PIL import Image
+        im = np.asarray(Image.open("/root/reference/images/0.png").convert("RGB"))
+        cases.append(("readme0_crop64_df2k_t200", np.ascontiguousarray(im[70:134, 60:124]), "models-DF2K", 200, 0))
+        cases.append(("readme0_crop96x80_df2k_t64", np.ascontiguousarray(im[40:120, 30:126]), "models-DF2K", 64, 0))
+    except Exception as e:  # PIL or the image absent
+        print("skipping README image cases:", e)
+    manifest = {"generator": "oracle/gen_golden.py", "reference_binary": "oracle/_ref/oracle_ref_avx2 (ncnn b4ba207, AVX2+FMA, OpenMP)",
+                "prepadding": 10, "cases": []}
+    flags = [l for l in open("/proc/cpuinfo") if l.startswith("model name")][:1]
+    manifest["host_cpu"] = flags[0].split(":", 1)[1].strip() if flags else "?"
+    for name, img, model, ts, tta in cases:
+        out, info = run_ref(img, model, ts, tta)
+        np.save(os.path.join(GOLD, name + ".in.npy"), img)
+        np.save(os.path.join(GOLD, name + ".out.npy"), out)
+        manifest["cases"].append({"name": name, "model": model, "tilesize": ts, "tta": tta, "h": img.shape[0],
+                                  "w": img.shape[1], "ref_seconds": info["seconds"]})
+        print(name, info["seconds"], "s")
+    json.dump(manifest, open(os.path.join(GOLD, "manifest.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

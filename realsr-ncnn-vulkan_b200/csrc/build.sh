@@ -1,0 +1,18 @@
+#!/bin/bash
+# Builds librealsr_b200.so in-tree for sm_100a (the .so is git-ignored but travels to the GPU box with gpurun).
+set -e
+cd "$(dirname "$0")"
+OUT=../librealsr_b200.so
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden,-Wall -ccbin /usr/bin/g++"
+mkdir -p build
+pids=()
+for f in conv_tc.cu misc_kernels.cu engine.cu; do
+  $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f -o build/${f%.cu}.o &
+  pids+=($!)
+done
+/usr/bin/g++ -O2 -std=c++17 -fPIC -fvisibility=hidden -Wall -c model.cpp -o build/model.o &
+pids+=($!)
+for p in "${pids[@]}"; do wait $p; done
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT build/conv_tc.o build/misc_kernels.o build/engine.o build/model.o -ccbin /usr/bin/g++
+echo "built $(realpath $OUT)"

@@ -1,0 +1,606 @@
+// engine.cu -- the tile engine behind the C ABI (include/realsr_b200.h): B200-native replacement of
+// RealSR::load / RealSR::process (/root/reference/src/realsr.cpp:38-143, :145-523).
+//
+// What the reference does per image (realsr.cpp:170-516): loop over tiles, one blocking Vulkan submit per tile,
+// ~1000 dispatches per tile through a graph interpreter.  Here: the graph is lowered once to a static schedule of
+// 1 + 15*nb + 5 fused kernels; tiles of equal padded shape are batched into ONE launch per layer (tile geometry is
+// unchanged -- it is part of the numerical contract), everything is queued on one stream per call without host
+// synchronisation, and the source / result images stay resident in HBM for the whole call.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/realsr_b200.h"
+#include "kernels.h"
+#include "model.h"
+
+using namespace rsr;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf d16[2], t32, r32, f32, u1, v1, u2, v2, tta, tiles, img_in, img_out;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
+};
+
+struct DeviceModel {
+    std::vector<__half*> wpk;   // per conv (index 0 unused)
+    std::vector<float*> bias;   // per conv, padded to cout_pad
+    std::vector<int> cout_pad;
+    float* w0 = nullptr;        // Conv_0 fp32 weights [64][27]
+    void* blob = nullptr;       // one allocation holding everything
+};
+
+}  // namespace
+
+struct rsr_handle {
+    int gpuid = 0, tta = 0;
+    int scale = 4, tilesize = 200, prepadding = 10;
+    bool loaded = false;
+    Model model;
+    DeviceModel dm;
+    std::mutex mu;
+    std::vector<Workspace*> pool;
+    std::string err;
+    // options
+    long long max_batch = 0;  // 0 = auto
+    int desc_mode = 0;  // measured on B200: SWIZZLE_128B is a function of the absolute smem address => base_offset 0 for row-shifted starts
+    int time_convs = 0;
+    // stats
+    long long launches = 0;
+    double last_ms = 0, last_conv_ms = 0;
+    long long last_padded = 0;
+};
+
+namespace {
+
+int set_err(rsr_handle* h, int code, const std::string& msg)
+{
+    std::lock_guard<std::mutex> g(h->mu);
+    h->err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                                        \
+    do {                                                                                                                \
+        cudaError_t e_ = (call);                                                                                        \
+        if (e_ != cudaSuccess) {                                                                                        \
+            char b_[512];                                                                                               \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);        \
+            return set_err(h, e_ == cudaErrorMemoryAllocation ? RSR_ERR_ALLOC : RSR_ERR_CUDA, b_);                      \
+        }                                                                                                               \
+    } while (0)
+
+int ensure(rsr_handle* h, DevBuf& b, size_t bytes)
+{
+    if (b.cap >= bytes) return 0;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = bytes + bytes / 8 + 4096;  // grow-only with slack; TMA needs 16-B alignment (cudaMalloc gives 256)
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+int make_map(rsr_handle* h, CUtensorMap* m, const void* base, int C, int W, int H, int B)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)CONV_P, (cuuint32_t)(CONV_BH + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[160];
+        snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d) for C=%d W=%d H=%d B=%d", (int)r, C, W, H, B);
+        return set_err(h, RSR_ERR_CUDA, b);
+    }
+    return 0;
+}
+
+Workspace* acquire_ws(rsr_handle* h)
+{
+    {
+        std::lock_guard<std::mutex> g(h->mu);
+        if (!h->pool.empty()) {
+            Workspace* w = h->pool.back();
+            h->pool.pop_back();
+            return w;
+        }
+    }
+    Workspace* w = new Workspace();
+    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&w->ev0) != cudaSuccess ||
+        cudaEventCreate(&w->ev1) != cudaSuccess) {
+        delete w;
+        return nullptr;
+    }
+    return w;
+}
+
+void release_ws(rsr_handle* h, Workspace* w)
+{
+    std::lock_guard<std::mutex> g(h->mu);
+    h->pool.push_back(w);
+}
+
+void free_ws(Workspace* w)
+{
+    DevBuf* bufs[] = {&w->d16[0], &w->d16[1], &w->t32, &w->r32, &w->f32, &w->u1, &w->v1, &w->u2, &w->v2, &w->tta, &w->tiles, &w->img_in, &w->img_out};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    for (auto& e : w->conv_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (w->ev0) cudaEventDestroy(w->ev0);
+    if (w->ev1) cudaEventDestroy(w->ev1);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    delete w;
+}
+
+struct BatchCtx {
+    rsr_handle* h;
+    Workspace* ws;
+    long long launches = 0;
+    size_t nconv_ev = 0;
+};
+
+int conv(BatchCtx& c, const CUtensorMap* map, ConvArgs a, int conv_idx)
+{
+    rsr_handle* h = c.h;
+    const DeviceModel& dm = h->dm;
+    a.wpk = dm.wpk[conv_idx];
+    a.bias = dm.bias[conv_idx];
+    a.cin = h->model.convs[conv_idx].cin;
+    a.desc_mode = h->desc_mode;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->time_convs) {
+        if (c.nconv_ev >= c.ws->conv_events.size()) {
+            cudaEvent_t x, y;
+            CK(cudaEventCreate(&x));
+            CK(cudaEventCreate(&y));
+            c.ws->conv_events.push_back({x, y});
+        }
+        e0 = c.ws->conv_events[c.nconv_ev].first;
+        e1 = c.ws->conv_events[c.nconv_ev].second;
+        c.nconv_ev++;
+        CK(cudaEventRecord(e0, c.ws->stream));
+    }
+    CK(launch_conv3x3_tc(map, a, dm.cout_pad[conv_idx], c.ws->stream));
+    if (e1) CK(cudaEventRecord(e1, c.ws->stream));
+    c.launches++;
+    return 0;
+}
+
+// Runs the whole network on one batch of same-shape padded tiles (H x W network-input pixels each).
+int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, uint8_t* d_out, const std::vector<TileDesc>& tiles, int H, int W,
+              bool tta_out)
+{
+    rsr_handle* h = c.h;
+    Workspace* ws = c.ws;
+    const Model& m = h->model;
+    const int B = (int)tiles.size();
+    const size_t npx = (size_t)B * H * W;
+    int r;
+    if ((r = ensure(h, ws->d16[0], npx * 192 * 2))) return r;
+    if ((r = ensure(h, ws->d16[1], npx * 192 * 2))) return r;
+    if ((r = ensure(h, ws->t32, npx * 64 * 4))) return r;
+    if ((r = ensure(h, ws->r32, npx * 64 * 4))) return r;
+    if ((r = ensure(h, ws->f32, npx * 64 * 4))) return r;
+    if ((r = ensure(h, ws->u1, npx * 4 * 64 * 2))) return r;
+    if ((r = ensure(h, ws->v1, npx * 4 * 64 * 2))) return r;
+    if ((r = ensure(h, ws->u2, npx * 16 * 64 * 2))) return r;
+    if ((r = ensure(h, ws->v2, npx * 16 * 64 * 2))) return r;
+    if ((r = ensure(h, ws->tiles, sizeof(TileDesc) * (size_t)B))) return r;
+    cudaStream_t st = ws->stream;
+    // tile descriptors: pageable -> device through the stream (small); safe because `tiles` outlives the sync below
+    CK(cudaMemcpyAsync(ws->tiles.p, tiles.data(), sizeof(TileDesc) * (size_t)B, cudaMemcpyHostToDevice, st));
+    const TileDesc* d_tiles = (const TileDesc*)ws->tiles.p;
+
+    __half* D[2] = {(__half*)ws->d16[0].p, (__half*)ws->d16[1].p};
+    CUtensorMap mapD[2], mapU1, mapV1, mapU2, mapV2;
+    if ((r = make_map(h, &mapD[0], D[0], 192, W, H, B))) return r;
+    if ((r = make_map(h, &mapD[1], D[1], 192, W, H, B))) return r;
+    if ((r = make_map(h, &mapU1, ws->u1.p, 64, 2 * W, 2 * H, B))) return r;
+    if ((r = make_map(h, &mapV1, ws->v1.p, 64, 2 * W, 2 * H, B))) return r;
+    if ((r = make_map(h, &mapU2, ws->u2.p, 64, 4 * W, 4 * H, B))) return r;
+    if ((r = make_map(h, &mapV2, ws->v2.p, 64, 4 * W, 4 * H, B))) return r;
+
+    // Conv_0 + preproc
+    {
+        FirstArgs f{};
+        f.img = d_img; f.img_w = img_w; f.img_h = img_h; f.tiles = d_tiles;
+        f.w = h->dm.w0; f.bias = h->dm.bias[0];
+        f.H = H; f.W = W; f.B = B;
+        f.d16 = D[0]; f.t32 = (float*)ws->t32.p; f.r32 = (float*)ws->r32.p; f.f32 = (float*)ws->f32.p;
+        CK(launch_conv_first(f, st));
+        c.launches++;
+    }
+    ConvArgs base{};
+    base.H = H; base.W = W; base.B = B;
+    base.t32 = (float*)ws->t32.p; base.r32 = (float*)ws->r32.p; base.f32 = (const float*)ws->f32.p;
+    base.tiles = d_tiles;
+    int cur = 0;
+    for (int rrdb = 0; rrdb < m.num_rrdb; rrdb++)
+        for (int rdb = 0; rdb < 3; rdb++) {
+            for (int k = 0; k < 4; k++) {  // x_{k+1} = lrelu(conv([x0..xk])) -> channel slice 64+32k of the same buffer
+                ConvArgs a = base;
+                a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_rdb(rrdb, rdb, k)].slope;
+                a.out16 = D[cur]; a.out_cs = 192; a.out_co = 64 + 32 * k;
+                if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, k)))) return r;
+            }
+            ConvArgs a = base;  // x5 -> residual(s) -> x0 of the next RDB in the other buffer
+            a.mode = CONV_RDB_OUT; a.rrdb_end = (rdb == 2);
+            a.out16 = D[cur ^ 1]; a.out_cs = 192; a.out_co = 0;
+            if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, 4)))) return r;
+            cur ^= 1;
+        }
+    {   // trunk conv + fea (BinaryOp ADD), result in channels 0..63 of the other dense buffer
+        ConvArgs a = base;
+        a.mode = CONV_TRUNK; a.out16 = D[cur ^ 1]; a.out_cs = 192; a.out_co = 0;
+        if ((r = conv(c, &mapD[cur], a, m.idx_trunk()))) return r;
+        cur ^= 1;
+    }
+    // nearest x2 -> conv+lrelu, twice (x4.param:996-999). The first source has 192 channels per pixel (reads 0..63).
+    CK(launch_upsample2x(D[cur], 192, (__half*)ws->u1.p, B, H, W, st));
+    c.launches++;
+    {
+        ConvArgs a = base;
+        a.H = 2 * H; a.W = 2 * W;
+        a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_up1()].slope;
+        a.out16 = (__half*)ws->v1.p; a.out_cs = 64; a.out_co = 0;
+        if ((r = conv(c, &mapU1, a, m.idx_up1()))) return r;
+    }
+    CK(launch_upsample2x((const __half*)ws->v1.p, 64, (__half*)ws->u2.p, B, 2 * H, 2 * W, st));
+    c.launches++;
+    {
+        ConvArgs a = base;
+        a.H = 4 * H; a.W = 4 * W;
+        a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_up2()].slope;
+        a.out16 = (__half*)ws->v2.p; a.out_cs = 64; a.out_co = 0;
+        if ((r = conv(c, &mapU2, a, m.idx_up2()))) return r;
+        a.slope = m.convs[m.idx_hr()].slope;
+        a.out16 = (__half*)ws->u2.p;  // u2 is dead after up2: reuse it for the HR conv output
+        if ((r = conv(c, &mapV2, a, m.idx_hr()))) return r;
+    }
+    {   // last conv (64->3, N padded to 16) + postproc / TTA store
+        ConvArgs a = base;
+        a.H = 4 * H; a.W = 4 * W;
+        a.mode = tta_out ? CONV_LAST_F32 : CONV_LAST_U8;
+        a.img_out = d_out; a.img_w = img_w * 4; a.img_h = img_h * 4;
+        a.prepad_s = h->prepadding * 4;
+        a.tta_out = (float*)ws->tta.p;
+        if ((r = conv(c, &mapU2, a, m.idx_last()))) return r;
+    }
+    return 0;
+}
+
+int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, int hh, uint8_t* d_out, long long* padded_out, long long* launches_out)
+{
+    const int T = h->tilesize, P = h->prepadding;
+    const int xtiles = (w + T - 1) / T, ytiles = (hh + T - 1) / T;
+    // tile grid: reference src/realsr.cpp:170-171,:176-187,:235-241 (GPU) == :537-553 (CPU)
+    std::map<std::pair<int, int>, std::vector<TileDesc>> groups;
+    for (int yi = 0; yi < ytiles; yi++)
+        for (int xi = 0; xi < xtiles; xi++) {
+            const int tw = std::min((xi + 1) * T, w) - xi * T, th = std::min((yi + 1) * T, hh) - yi * T;
+            TileDesc t{};
+            t.in_x0 = xi * T - P; t.in_y0 = yi * T - P;
+            t.out_x0 = xi * T * 4; t.out_y0 = yi * T * 4;
+            t.crop_w = tw * 4; t.crop_h = th * 4;
+            t.variant = 0; t.base_h = th + 2 * P; t.base_w = tw + 2 * P; t.tta_slot = 0;
+            groups[{t.base_h, t.base_w}].push_back(t);
+        }
+    BatchCtx c{h, ws};
+    long long padded = 0;
+    int r;
+    for (auto& g : groups) {
+        const int H = g.first.first, W = g.first.second;
+        std::vector<TileDesc>& tl = g.second;
+        // workspace per padded pixel: 2x192 fp16 + 3x64 fp32 + (u1,v1) 4x64x2 fp16 + (u2,v2) 16x64x2 fp16 [+ TTA 16 float4 x2]
+        const double bytes_per_tile = (double)H * W * (768.0 + 768.0 + 1024.0 + 4096.0 + (h->tta ? 512.0 : 0.0));
+        long long mb = h->max_batch > 0 ? h->max_batch : (long long)(12e9 / bytes_per_tile);
+        mb = std::max(1LL, std::min(mb, 64LL));
+        if (!h->tta) {
+            for (size_t i = 0; i < tl.size(); i += (size_t)mb) {
+                std::vector<TileDesc> batch(tl.begin() + i, tl.begin() + std::min(tl.size(), i + (size_t)mb));
+                if ((r = run_batch(c, d_in, w, hh, d_out, batch, H, W, false))) return r;
+                padded += (long long)batch.size() * H * W;
+                CK(cudaStreamSynchronize(ws->stream));  // `batch` (tile descriptors) must outlive the async copy
+            }
+        } else {
+            // 8 dihedral variants per tile (src/realsr.cpp:242-318): 0..3 keep the shape, 4..7 run transposed
+            const long long G = std::max(1LL, mb / 4);
+            for (size_t i = 0; i < tl.size(); i += (size_t)G) {
+                const size_t n = std::min(tl.size(), i + (size_t)G) - i;
+                const size_t slot_stride = (size_t)16 * H * W;  // float4 per slot
+                if ((r = ensure(h, ws->tta, n * 8 * slot_stride * sizeof(float4)))) return r;
+                std::vector<TileDesc> all(n * 8);
+                for (size_t gi = 0; gi < n; gi++)
+                    for (int v = 0; v < 8; v++) {
+                        TileDesc t = tl[i + gi];
+                        t.variant = v;
+                        t.tta_slot = (int)(gi * 8 + v);
+                        all[gi * 8 + v] = t;
+                    }
+                for (int half = 0; half < 2; half++) {
+                    std::vector<TileDesc> batch;
+                    for (size_t gi = 0; gi < n; gi++)
+                        for (int v = half * 4; v < half * 4 + 4; v++) batch.push_back(all[gi * 8 + v]);
+                    if ((r = run_batch(c, d_in, w, hh, d_out, batch, half ? W : H, half ? H : W, true))) return r;
+                    CK(cudaStreamSynchronize(ws->stream));
+                }
+                // gather needs the 8 descs of every tile in slot order on the device
+                if ((r = ensure(h, ws->tiles, sizeof(TileDesc) * all.size()))) return r;
+                CK(cudaMemcpyAsync(ws->tiles.p, all.data(), sizeof(TileDesc) * all.size(), cudaMemcpyHostToDevice, ws->stream));
+                TtaGatherArgs ga{};
+                ga.tta_out = (const float*)ws->tta.p; ga.tiles = (const TileDesc*)ws->tiles.p; ga.ngroups = (int)n;
+                ga.slot_stride = slot_stride; ga.img_out = d_out; ga.img_w = w * 4; ga.img_h = hh * 4; ga.prepad_s = P * 4;
+                int mw = 0, mh = 0;
+                for (size_t gi = 0; gi < n; gi++) { mw = std::max(mw, tl[i + gi].crop_w); mh = std::max(mh, tl[i + gi].crop_h); }
+                CK(launch_tta_gather(ga, mw, mh, ws->stream));
+                c.launches++;
+                CK(cudaStreamSynchronize(ws->stream));
+                padded += (long long)n * 8 * H * W;
+            }
+        }
+    }
+    *padded_out = padded;
+    *launches_out = c.launches;
+    if (h->time_convs) {
+        double ms = 0;
+        for (size_t i = 0; i < c.nconv_ev; i++) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ws->conv_events[i].first, ws->conv_events[i].second);
+            ms += t;
+        }
+        std::lock_guard<std::mutex> g(h->mu);
+        h->last_conv_ms = ms;
+    }
+    return 0;
+}
+
+int check_args(rsr_handle* h, const void* in, int w, int hh, int c, const void* out)
+{
+    if (!h) return RSR_ERR_GENERIC;
+    if (!h->loaded) return set_err(h, RSR_ERR_GENERIC, "rsr_process: no model loaded");
+    if (!in || !out || w <= 0 || hh <= 0) return set_err(h, RSR_ERR_GENERIC, "rsr_process: bad image arguments");
+    if (c != 3) return set_err(h, RSR_ERR_GENERIC, "rsr_process: only 3-channel RGB images are supported (alpha path not implemented)");
+    return 0;
+}
+
+}  // namespace
+
+// ================================================= C ABI ===========================================================
+extern "C" {
+
+rsr_handle* rsr_create(int gpuid, int tta_mode, int num_threads)
+{
+    (void)num_threads;
+    rsr_handle* h = new (std::nothrow) rsr_handle();
+    if (!h) return nullptr;
+    h->gpuid = gpuid;
+    h->tta = tta_mode ? 1 : 0;
+    return h;
+}
+
+void rsr_destroy(rsr_handle* h)
+{
+    if (!h) return;
+    if (h->gpuid >= 0) cudaSetDevice(h->gpuid);
+    for (Workspace* w : h->pool) free_ws(w);
+    if (h->dm.blob) cudaFree(h->dm.blob);
+    delete h;
+}
+
+int rsr_load(rsr_handle* h, const char* parampath, const char* modelpath)
+{
+    if (!h || !parampath || !modelpath) return RSR_ERR_GENERIC;
+    if (h->gpuid < 0) return set_err(h, RSR_ERR_NO_DEVICE, "gpuid -1 (ncnn CPU path) is not provided by librealsr_b200; use a CUDA device ordinal");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || h->gpuid >= ndev)
+        return set_err(h, RSR_ERR_NO_DEVICE, "invalid gpu device " + std::to_string(h->gpuid) + " (" + std::to_string(ndev) + " CUDA devices visible)");
+    CK(cudaSetDevice(h->gpuid));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->gpuid));
+    if (prop.major != 10) return set_err(h, RSR_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100 (this library is B200-only)");
+    Model m;
+    int r = load_model(parampath, modelpath, m);
+    if (r) return set_err(h, RSR_ERR_MODEL, m.error);
+    // pack + upload: one blob, 1024-B aligned sub-allocations (bulk copies need 16 B; keep slabs nicely aligned)
+    const int nconv = (int)m.convs.size();
+    std::vector<std::vector<uint16_t>> packed(nconv);
+    std::vector<size_t> off_w(nconv, 0), off_b(nconv, 0);
+    DeviceModel dm;
+    dm.cout_pad.assign(nconv, 0);
+    size_t total = 0;
+    auto bump = [&](size_t bytes) { size_t o = total; total += (bytes + 1023) & ~(size_t)1023; return o; };
+    const size_t off_w0 = bump(64 * 27 * 4);
+    for (int i = 0; i < nconv; i++) {
+        const ConvLayer& c = m.convs[i];
+        dm.cout_pad[i] = c.cout <= 16 ? 16 : (c.cout <= 32 ? 32 : 64);
+        if (i > 0) {
+            if (c.cout > 64 || (c.cin % 16)) return set_err(h, RSR_ERR_MODEL, "unsupported conv shape in " + c.name);
+            pack_conv_weights(c, dm.cout_pad[i], packed[i]);
+            off_w[i] = bump(packed[i].size() * 2);
+        }
+        off_b[i] = bump(64 * 4);
+    }
+    if (h->dm.blob) { cudaFree(h->dm.blob); h->dm = DeviceModel(); }
+    CK(cudaMalloc(&dm.blob, total));
+    std::vector<uint8_t> host(total, 0);
+    memcpy(host.data() + off_w0, m.convs[0].weight.data(), 64 * 27 * 4);
+    for (int i = 0; i < nconv; i++) {
+        if (i > 0) memcpy(host.data() + off_w[i], packed[i].data(), packed[i].size() * 2);
+        memcpy(host.data() + off_b[i], m.convs[i].bias.data(), m.convs[i].cout * 4);
+    }
+    CK(cudaMemcpy(dm.blob, host.data(), total, cudaMemcpyHostToDevice));
+    dm.w0 = (float*)((uint8_t*)dm.blob + off_w0);
+    dm.wpk.assign(nconv, nullptr);
+    dm.bias.assign(nconv, nullptr);
+    for (int i = 0; i < nconv; i++) {
+        if (i > 0) dm.wpk[i] = (__half*)((uint8_t*)dm.blob + off_w[i]);
+        dm.bias[i] = (float*)((uint8_t*)dm.blob + off_b[i]);
+    }
+    h->model = std::move(m);
+    h->dm = dm;
+    h->loaded = true;
+    return 0;
+}
+
+int rsr_set(rsr_handle* h, int scale, int tilesize, int prepadding)
+{
+    if (!h) return RSR_ERR_GENERIC;
+    if (scale != 4) return set_err(h, RSR_ERR_GENERIC, "invalid scale argument (only 4 is supported, like the reference)");
+    if (tilesize < 32) return set_err(h, RSR_ERR_GENERIC, "invalid tilesize argument (must be >= 32)");
+    if (prepadding < 0 || prepadding > 64) return set_err(h, RSR_ERR_GENERIC, "invalid prepadding");
+    h->scale = scale;
+    h->tilesize = tilesize;
+    h->prepadding = prepadding;
+    return 0;
+}
+
+static int process_impl(rsr_handle* h, const uint8_t* in, int w, int hh, int c, uint8_t* out, bool host_buffers)
+{
+    int r = check_args(h, in, w, hh, c, out);
+    if (r) return r;
+    CK(cudaSetDevice(h->gpuid));
+    Workspace* ws = acquire_ws(h);
+    if (!ws) return set_err(h, RSR_ERR_CUDA, "cannot create stream/events");
+    const size_t in_bytes = (size_t)w * hh * 3, out_bytes = in_bytes * 16;
+    const uint8_t* d_in = in;
+    uint8_t* d_out = out;
+    long long padded = 0, launches = 0;
+    auto body = [&]() -> int {
+        int rr;
+        if (host_buffers) {
+            if ((rr = ensure(h, ws->img_in, in_bytes))) return rr;
+            if ((rr = ensure(h, ws->img_out, out_bytes))) return rr;
+            d_in = (const uint8_t*)ws->img_in.p;
+            d_out = (uint8_t*)ws->img_out.p;
+        }
+        CK(cudaEventRecord(ws->ev0, ws->stream));
+        if (host_buffers) CK(cudaMemcpyAsync(ws->img_in.p, in, in_bytes, cudaMemcpyHostToDevice, ws->stream));
+        if ((rr = process_on_device(h, ws, d_in, w, hh, d_out, &padded, &launches))) return rr;
+        if (host_buffers) CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ws->stream));
+        CK(cudaEventRecord(ws->ev1, ws->stream));
+        CK(cudaStreamSynchronize(ws->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+        std::lock_guard<std::mutex> g(h->mu);
+        h->last_ms = ms;
+        h->last_padded = padded;
+        h->launches += launches;
+        return 0;
+    };
+    r = body();
+    if (r) cudaStreamSynchronize(ws->stream);
+    release_ws(h, ws);
+    return r;
+}
+
+int rsr_process(rsr_handle* h, const uint8_t* in, int w, int h_, int c, uint8_t* out) { return process_impl(h, in, w, h_, c, out, true); }
+
+int rsr_process_device(rsr_handle* h, const uint8_t* d_in, int w, int h_, int c, uint8_t* d_out)
+{
+    return process_impl(h, d_in, w, h_, c, d_out, false);
+}
+
+const char* rsr_last_error(const rsr_handle* h) { return h ? h->err.c_str() : "null handle"; }
+long long rsr_kernel_launches(const rsr_handle* h) { return h ? h->launches : 0; }
+double rsr_last_ms(const rsr_handle* h, int what) { return !h ? 0.0 : (what == 1 ? h->last_conv_ms : h->last_ms); }
+long long rsr_last_padded_pixels(const rsr_handle* h) { return h ? h->last_padded : 0; }
+
+int rsr_set_option(rsr_handle* h, const char* key, long long value)
+{
+    if (!h || !key) return RSR_ERR_GENERIC;
+    if (!strcmp(key, "max_batch")) h->max_batch = value;
+    else if (!strcmp(key, "desc_mode")) h->desc_mode = (int)value;
+    else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
+    else return set_err(h, RSR_ERR_GENERIC, std::string("unknown option ") + key);
+    return 0;
+}
+
+int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, int W, float* out32)
+{
+    if (!h || !h->loaded) return RSR_ERR_GENERIC;
+    if (conv_index < 1 || conv_index >= (int)h->model.convs.size()) return set_err(h, RSR_ERR_GENERIC, "bad conv index");
+    CK(cudaSetDevice(h->gpuid));
+    const ConvLayer& cl = h->model.convs[conv_index];
+    const int npad = h->dm.cout_pad[conv_index];
+    const size_t npx = (size_t)H * W;
+    __half *d_in = nullptr, *d_out = nullptr;
+    float* d_f = nullptr;
+    TileDesc* d_td = nullptr;
+    CK(cudaMalloc(&d_in, npx * cl.cin * 2));
+    CK(cudaMalloc(&d_out, npx * 64 * 2));
+    CK(cudaMalloc(&d_f, npx * 16));
+    CK(cudaMalloc(&d_td, sizeof(TileDesc)));
+    CK(cudaMemcpy(d_in, in16, npx * cl.cin * 2, cudaMemcpyHostToDevice));
+    TileDesc td{};
+    CK(cudaMemcpy(d_td, &td, sizeof td, cudaMemcpyHostToDevice));
+    CUtensorMap map;
+    int r = make_map(h, &map, d_in, cl.cin, W, H, 1);
+    if (r) return r;
+    ConvArgs a{};
+    a.wpk = h->dm.wpk[conv_index]; a.bias = h->dm.bias[conv_index]; a.cin = cl.cin;
+    a.H = H; a.W = W; a.B = 1;
+    a.act = cl.act; a.slope = cl.slope;
+    a.out16 = d_out; a.out_cs = npad; a.out_co = 0;
+    a.tiles = d_td; a.tta_out = d_f;
+    a.mode = npad == 16 ? CONV_LAST_F32 : CONV_STORE16;
+    a.desc_mode = h->desc_mode;
+    CK(launch_conv3x3_tc(&map, a, npad, 0));
+    CK(cudaDeviceSynchronize());
+    if (npad == 16) {
+        std::vector<float> tmp(npx * 4);
+        CK(cudaMemcpy(tmp.data(), d_f, npx * 16, cudaMemcpyDeviceToHost));
+        for (size_t p = 0; p < npx; p++)
+            for (int j = 0; j < cl.cout; j++) out32[p * cl.cout + j] = tmp[p * 4 + j];
+    } else {
+        std::vector<__half> tmp(npx * npad);
+        CK(cudaMemcpy(tmp.data(), d_out, npx * npad * 2, cudaMemcpyDeviceToHost));
+        for (size_t p = 0; p < npx; p++)
+            for (int j = 0; j < cl.cout; j++) out32[p * cl.cout + j] = __half2float(tmp[p * npad + j]);
+    }
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_f); cudaFree(d_td);
+    {
+        std::lock_guard<std::mutex> g(h->mu);
+        h->launches += 1;
+    }
+    return 0;
+}
+
+}  // extern "C"

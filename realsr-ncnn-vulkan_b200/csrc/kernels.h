@@ -1,0 +1,97 @@
+// kernels.h -- device-side interface of the RealSR B200 engine (all launches are asynchronous on `stream`).
+//
+// Data layout in HBM (per batch of same-shape padded tiles, B tiles of H x W network-input pixels):
+//   D16[2]  fp16 [B][H][W][192]  dense-block buffer: channels 0..63 = RDB input x0, 64..191 = x1..x4 (32 each).
+//                                 Concat (ncnn layer/concat.cpp:140-175) is never materialised: conv k of an RDB
+//                                 reads channels [0, 64+32(k-1)) and writes its 32 outputs right behind them.
+//   T32     fp32 [B][H][W][64]   residual stream (RDB input, exact fp32), updated in place by conv5's epilogue
+//   R32     fp32 [B][H][W][64]   RRDB input, updated in place at every third RDB
+//   F32     fp32 [B][H][W][64]   Conv_0 output `fea` (added back after the trunk conv, x4.param:994-995)
+//   U/V     fp16 [B][sH][sW][64] activations of the 2x / 4x tail
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rsr {
+
+// Geometry of one network input ("padded tile", reference src/realsr.cpp:545-553,:757-766) inside the source image
+// and of its cropped result inside the output image.
+struct TileDesc {
+    int in_x0, in_y0;    // image coords of padded-tile pixel (0,0) of TTA variant 0 (may be < 0: reflect-101)
+    int out_x0, out_y0;  // output-image coords of the cropped result
+    int crop_w, crop_h;  // size of the cropped result (tile_w_nopad*4, tile_h_nopad*4)
+    int variant;         // TTA dihedral variant 0..7 (0 when TTA is off), src/realsr.cpp:618-664
+    int base_h, base_w;  // padded-tile size of variant 0 (variants 4..7 run transposed)
+    int tta_slot;        // index of the fp32 result plane this tile writes in TTA mode
+};
+
+enum ConvMode {
+    CONV_STORE16 = 0,   // out16 = fp16(act(acc + b))
+    CONV_RDB_OUT = 1,   // t = 0.2*(acc+b) + T32 ; [rrdb_end: t = 0.2*t + R32 ; R32 = t] ; T32 = t ; out16 = fp16(t)
+    CONV_TRUNK = 2,     // out16 = fp16(acc + b + F32)
+    CONV_LAST_U8 = 3,   // v = acc+b -> crop, v*255+0.5, (int) trunc, clamp -> u8 HWC output image
+    CONV_LAST_F32 = 4,  // v = acc+b -> fp32 [slot][4H][4W][4] (TTA; averaged by tta_gather)
+};
+
+struct ConvArgs {
+    const __half* wpk;  // packed weights [chunk][tap][N][64] fp16, pre-swizzled smem image (see model.cpp)
+    const float* bias;  // [N]
+    int cin;            // real input channels (multiple of 16)
+    int H, W, B;        // spatial size of this conv's input == output, batch
+    int mode, act;      // ConvMode; act: 0 none, 2 leaky relu
+    float slope;
+    __half* out16;
+    int out_cs, out_co;  // channels per pixel of the output buffer, channel offset
+    float* t32;
+    float* r32;
+    const float* f32;
+    int rrdb_end;
+    // CONV_LAST_*
+    const TileDesc* tiles;
+    uint8_t* img_out;
+    int img_w, img_h;    // output image size (pixels)
+    int prepad_s;        // prepadding*scale
+    float* tta_out;
+    int desc_mode;       // 0: UMMA descriptor base_offset = 0 ; 1: base_offset = (addr>>7)&7
+};
+
+// conv3x3 s1 p1 as implicit GEMM on tcgen05 (conv_tc.cu). cout_pad in {16, 32, 64}.
+cudaError_t launch_conv3x3_tc(const CUtensorMap* in_map, const ConvArgs& a, int cout_pad, cudaStream_t stream);
+// box dims the kernel expects from the tensor map: {64 ch, 32 px, CONV_BH+2 rows, 1}
+constexpr int CONV_BH = 8;
+constexpr int CONV_P = 32;
+
+// Conv_0 (3->64, fp32 CUDA cores) fused with preproc (crop, reflect-101, x 1/255, TTA variant), conv_first.cu
+struct FirstArgs {
+    const uint8_t* img;  // u8 HWC RGB source image on the device
+    int img_w, img_h;
+    const TileDesc* tiles;
+    const float* w;      // [64][3][3][3] fp32 (OIHW as in the .bin), bias [64]
+    const float* bias;
+    int H, W, B;
+    __half* d16;         // D16[0], 192 ch per pixel, writes channels 0..63
+    float* t32;
+    float* r32;
+    float* f32;
+};
+cudaError_t launch_conv_first(const FirstArgs& a, cudaStream_t stream);
+
+// nearest x2 (ncnn layer/interp.cpp:598-618): NHWC fp16, reads channels 0..63 of a source with in_cs channels per
+// pixel, writes a dense 64-ch tensor
+cudaError_t launch_upsample2x(const __half* in, int in_cs, __half* out, int B, int H, int W, cudaStream_t stream);
+
+// TTA gather: average the 8 inverse-transformed fp32 results, x255 + 0.5, truncate, clamp (src/realsr.cpp:691-724)
+struct TtaGatherArgs {
+    const float* tta_out;  // [slots][4*H0][4*W0][4] per variant, see conv_tc.cu CONV_LAST_F32
+    const TileDesc* tiles; // the 8 descs of every tile, variant-major within a tile group
+    int ngroups;           // number of source tiles (each has 8 consecutive slots)
+    size_t slot_stride;    // floats per slot
+    uint8_t* img_out;
+    int img_w, img_h;
+    int prepad_s;
+};
+cudaError_t launch_tta_gather(const TtaGatherArgs& a, int max_crop_w, int max_crop_h, cudaStream_t stream);
+
+}  // namespace rsr

@@ -1,0 +1,193 @@
+// misc_kernels.cu -- the bandwidth-bound kernels around the conv stack.
+//   conv_first : reference preproc (src/realsr.cpp:735-766 / realsr_preproc.comp:47-95: crop, reflect-101 at the image
+//                border, x (1/255.f)), the TTA scatter (src/realsr.cpp:618-664) and Conv_0 (3->64, x4.param:4) in ONE
+//                fp32 CUDA-core kernel.  Conv_0 must see the exact u8/255 inputs in fp32 (rounding the
+//                input image to fp16 costs 4-5 LSB), so it never goes through the fp16 tensor-core path.
+//   upsample2x : ncnn Interp nearest (layer/interp.cpp:598-618) on NHWC fp16.
+//   tta_gather : inverse dihedral gather + average + postproc (src/realsr.cpp:691-724, :816-833).
+#include "kernels.h"
+
+namespace rsr {
+
+namespace {
+
+__device__ __forceinline__ int reflect101(int v, int n)
+{
+    v = abs(v);
+    v = (n - 1) - abs(v - (n - 1));
+    return min(max(v, 0), n - 1);  // only differs from the reference for images narrower than the prepadding
+}
+
+// variant-space coords (a = row, b = col) -> base-tile coords (i, j); inverse of src/realsr.cpp:640-660
+__device__ __forceinline__ void variant_to_base(int variant, int a, int b, int ph, int pw, int& i, int& j)
+{
+    switch (variant) {
+    default: i = a; j = b; break;
+    case 1: i = ph - 1 - a; j = b; break;
+    case 2: i = a; j = pw - 1 - b; break;
+    case 3: i = ph - 1 - a; j = pw - 1 - b; break;
+    case 4: i = b; j = a; break;
+    case 5: i = b; j = pw - 1 - a; break;
+    case 6: i = ph - 1 - b; j = a; break;
+    case 7: i = ph - 1 - b; j = pw - 1 - a; break;
+    }
+}
+
+constexpr int FIRST_THREADS = 256;
+
+__global__ void __launch_bounds__(FIRST_THREADS) conv_first_kernel(const FirstArgs a)
+{
+    // weights re-ordered to [c][tap][oc] so that 4 consecutive output channels are one float4
+    __shared__ float4 sw[27 * 16];
+    __shared__ float sb[64];
+    for (int i = threadIdx.x; i < 27 * 64; i += FIRST_THREADS) {
+        const int oc = i & 63, ct = i >> 6;  // ct = c*9 + tap
+        reinterpret_cast<float*>(sw)[ct * 64 + oc] = a.w[oc * 27 + ct];
+    }
+    if (threadIdx.x < 64) sb[threadIdx.x] = a.bias[threadIdx.x];
+    __syncthreads();
+
+    const int b = blockIdx.y;
+    const TileDesc td = a.tiles[b];
+    const long long gid = (long long)blockIdx.x * FIRST_THREADS + threadIdx.x;
+    const long long npix = (long long)a.H * a.W;
+    const long long p = gid >> 2;
+    const int quarter = (int)(gid & 3);
+    if (p >= npix) return;
+    const int y = (int)(p / a.W), x = (int)(p - (long long)y * a.W);
+
+    float in[27];
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+            const int aa = y + ky - 1, bb = x + kx - 1;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+            if (aa >= 0 && aa < a.H && bb >= 0 && bb < a.W) {  // zero padding of the conv at the padded-tile border
+                int i, j;
+                variant_to_base(td.variant, aa, bb, td.base_h, td.base_w, i, j);
+                const int X = reflect101(td.in_x0 + j, a.img_w);
+                const int Y = reflect101(td.in_y0 + i, a.img_h);
+                const uint8_t* px = a.img + ((size_t)Y * a.img_w + X) * 3;
+                v0 = (float)px[0] * (1 / 255.f);
+                v1 = (float)px[1] * (1 / 255.f);
+                v2 = (float)px[2] * (1 / 255.f);
+            }
+            in[0 * 9 + ky * 3 + kx] = v0;
+            in[1 * 9 + ky * 3 + kx] = v1;
+            in[2 * 9 + ky * 3 + kx] = v2;
+        }
+    }
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) acc[j] = sb[quarter * 16 + j];
+#pragma unroll
+    for (int ct = 0; ct < 27; ct++) {  // input-channel major, tap minor: the naive layer's summation order
+        const float v = in[ct];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; j4++) {
+            const float4 w = sw[ct * 16 + quarter * 4 + j4];
+            acc[j4 * 4 + 0] = fmaf(v, w.x, acc[j4 * 4 + 0]);
+            acc[j4 * 4 + 1] = fmaf(v, w.y, acc[j4 * 4 + 1]);
+            acc[j4 * 4 + 2] = fmaf(v, w.z, acc[j4 * 4 + 2]);
+            acc[j4 * 4 + 3] = fmaf(v, w.w, acc[j4 * 4 + 3]);
+        }
+    }
+    const size_t pix = (size_t)b * npix + p;
+    float4* t = reinterpret_cast<float4*>(a.t32 + pix * 64 + quarter * 16);
+    float4* r = reinterpret_cast<float4*>(a.r32 + pix * 64 + quarter * 16);
+    float4* f = reinterpret_cast<float4*>(a.f32 + pix * 64 + quarter * 16);
+#pragma unroll
+    for (int j4 = 0; j4 < 4; j4++) {
+        const float4 o = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
+        t[j4] = o; r[j4] = o; f[j4] = o;
+    }
+    uint4* d = reinterpret_cast<uint4*>(a.d16 + pix * 192 + quarter * 16);
+#pragma unroll
+    for (int j8 = 0; j8 < 2; j8++) {
+        __half2 h0 = __floats2half2_rn(acc[j8 * 8 + 0], acc[j8 * 8 + 1]);
+        __half2 h1 = __floats2half2_rn(acc[j8 * 8 + 2], acc[j8 * 8 + 3]);
+        __half2 h2 = __floats2half2_rn(acc[j8 * 8 + 4], acc[j8 * 8 + 5]);
+        __half2 h3 = __floats2half2_rn(acc[j8 * 8 + 6], acc[j8 * 8 + 7]);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&h0);
+        o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2);
+        o.w = *reinterpret_cast<uint32_t*>(&h3);
+        d[j8] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, int in_vec_stride, uint4* __restrict__ out, int B, int H, int W)
+{
+    // one thread = one 16-B vector (8 channels) of one output pixel; 8 vectors per output pixel (64 ch).
+    // in_vec_stride = 16-B vectors per source pixel (8 for a 64-ch tensor, 24 for the 192-ch dense buffer).
+    const long long n = (long long)B * (2 * H) * (2 * W) * 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i & 7);
+        long long p = i >> 3;
+        const int x = (int)(p % (2 * W)); p /= (2 * W);
+        const int y = (int)(p % (2 * H));
+        const int b = (int)(p / (2 * H));
+        out[i] = __ldg(in + (((size_t)b * H + (y >> 1)) * W + (x >> 1)) * in_vec_stride + v);
+    }
+}
+
+__global__ void __launch_bounds__(256) tta_gather_kernel(const TtaGatherArgs a)
+{
+    const int g = blockIdx.z;
+    const TileDesc td = a.tiles[g * 8];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= td.crop_h || j >= td.crop_w) return;
+    const int oh = td.base_h * 4, ow = td.base_w * 4, ps = a.prepad_s;
+    const float4* s = reinterpret_cast<const float4*>(a.tta_out) + (size_t)g * 8 * a.slot_stride;
+    const size_t ss = a.slot_stride;
+    const float4 v0 = s[0 * ss + (size_t)(i + ps) * ow + (j + ps)];
+    const float4 v1 = s[1 * ss + (size_t)(oh - 1 - i - ps) * ow + (j + ps)];
+    const float4 v2 = s[2 * ss + (size_t)(i + ps) * ow + (ow - 1 - ps - j)];
+    const float4 v3 = s[3 * ss + (size_t)(oh - 1 - i - ps) * ow + (ow - 1 - ps - j)];
+    const float4 v4 = s[4 * ss + (size_t)(j + ps) * oh + (i + ps)];
+    const float4 v5 = s[5 * ss + (size_t)(ow - 1 - j - ps) * oh + (i + ps)];
+    const float4 v6 = s[6 * ss + (size_t)(j + ps) * oh + (oh - 1 - i - ps)];
+    const float4 v7 = s[7 * ss + (size_t)(ow - 1 - j - ps) * oh + (oh - 1 - i - ps)];
+    float o[3];
+    o[0] = (v0.x + v1.x + v2.x + v3.x + v4.x + v5.x + v6.x + v7.x) / 8;
+    o[1] = (v0.y + v1.y + v2.y + v3.y + v4.y + v5.y + v6.y + v7.y) / 8;
+    o[2] = (v0.z + v1.z + v2.z + v3.z + v4.z + v5.z + v6.z + v7.z) / 8;
+    uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + i) * a.img_w + td.out_x0 + j) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int iv = (int)(o[c] * 255.f + 0.5f);
+        dst[c] = (uint8_t)min(max(iv, 0), 255);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_conv_first(const FirstArgs& a, cudaStream_t stream)
+{
+    const long long nthreads = (long long)a.H * a.W * 4;
+    dim3 grid((unsigned)((nthreads + FIRST_THREADS - 1) / FIRST_THREADS), a.B);
+    conv_first_kernel<<<grid, FIRST_THREADS, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_upsample2x(const __half* in, int in_cs, __half* out, int B, int H, int W, cudaStream_t stream)
+{
+    const long long n = (long long)B * 4 * H * W * 8;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    upsample2x_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), in_cs / 8, reinterpret_cast<uint4*>(out), B, H, W);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tta_gather(const TtaGatherArgs& a, int max_crop_w, int max_crop_h, cudaStream_t stream)
+{
+    dim3 block(32, 8);
+    dim3 grid((max_crop_w + 31) / 32, (max_crop_h + 7) / 8, a.ngroups);
+    tta_gather_kernel<<<grid, block, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace rsr

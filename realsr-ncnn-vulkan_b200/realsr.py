@@ -1,0 +1,142 @@
+"""Python mirror of the reference's tile-engine class (reference: /root/reference/src/realsr.h:13-42).
+
+Same names, argument meaning and call order as the C++ class the reference's main.cpp drives
+(src/main.cpp:778-791: construct, load, then set scale/tilesize/prepadding; :325: process(in, out)).  All work
+happens in librealsr_b200.so (hand-written CUDA for sm_100a) through ctypes; there is NO CPU fallback: if the
+library is missing or no B200 is visible the calls fail loudly.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class RealSRError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "librealsr_b200.so")
+
+
+def load_library():
+    """Loads librealsr_b200.so (built in-tree by csrc/build.sh / __graft_entry__.build()). Raises if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise RealSRError("librealsr_b200.so not found at %s -- build it with `python __graft_entry__.py build` "
+                          "(there is no CPU fallback)" % p)
+    lib = ctypes.CDLL(p)
+    vp, ci, cc, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_longlong
+    lib.rsr_create.restype = vp
+    lib.rsr_create.argtypes = [ci, ci, ci]
+    lib.rsr_destroy.restype = None
+    lib.rsr_destroy.argtypes = [vp]
+    lib.rsr_load.restype = ci
+    lib.rsr_load.argtypes = [vp, cc, cc]
+    lib.rsr_set.restype = ci
+    lib.rsr_set.argtypes = [vp, ci, ci, ci]
+    lib.rsr_process.restype = ci
+    lib.rsr_process.argtypes = [vp, vp, ci, ci, ci, vp]
+    lib.rsr_process_device.restype = ci
+    lib.rsr_process_device.argtypes = [vp, vp, ci, ci, ci, vp]
+    lib.rsr_last_error.restype = cc
+    lib.rsr_last_error.argtypes = [vp]
+    lib.rsr_kernel_launches.restype = ll
+    lib.rsr_kernel_launches.argtypes = [vp]
+    lib.rsr_last_ms.restype = ctypes.c_double
+    lib.rsr_last_ms.argtypes = [vp, ci]
+    lib.rsr_last_padded_pixels.restype = ll
+    lib.rsr_last_padded_pixels.argtypes = [vp]
+    lib.rsr_set_option.restype = ci
+    lib.rsr_set_option.argtypes = [vp, cc, ll]
+    lib.rsr_debug_conv.restype = ci
+    lib.rsr_debug_conv.argtypes = [vp, ci, vp, ci, ci, vp]
+    _LIB = lib
+    return lib
+
+
+class RealSR:
+    """RealSR(gpuid, tta_mode=False, num_threads=1) -- reference: src/realsr.h:16.
+
+    Public data members `scale`, `tilesize`, `prepadding` are plain attributes set after load(), exactly like the
+    reference (src/realsr.h:31-33, src/main.cpp:788-790)."""
+
+    def __init__(self, gpuid, tta_mode=False, num_threads=1):
+        self._lib = load_library()
+        self._h = self._lib.rsr_create(int(gpuid), 1 if tta_mode else 0, int(num_threads))
+        if not self._h:
+            raise RealSRError("rsr_create failed")
+        self.scale = 4
+        self.tilesize = 200
+        self.prepadding = 10
+        self.tta_mode = bool(tta_mode)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.rsr_destroy(h)
+
+    def last_error(self):
+        return self._lib.rsr_last_error(self._h).decode()
+
+    def load(self, parampath, modelpath):
+        """int RealSR::load(parampath, modelpath) -- reference: src/realsr.cpp:38-143. Returns 0 on success."""
+        return self._lib.rsr_load(self._h, os.fsencode(parampath), os.fsencode(modelpath))
+
+    def _push_params(self):
+        r = self._lib.rsr_set(self._h, int(self.scale), int(self.tilesize), int(self.prepadding))
+        if r:
+            raise RealSRError(self.last_error())
+
+    def process(self, inimage, outimage):
+        """int RealSR::process(const ncnn::Mat& in, ncnn::Mat& out) const -- reference: src/realsr.cpp:145-523.
+
+        inimage: uint8 ndarray (h, w, 3), C-contiguous, RGB; outimage: preallocated uint8 ndarray (4h, 4w, 3),
+        written in place (the reference's caller allocates it too, src/main.cpp:276).  Returns 0 on success,
+        a negative code otherwise (message in last_error())."""
+        if inimage.dtype != np.uint8 or inimage.ndim != 3 or not inimage.flags.c_contiguous:
+            raise RealSRError("inimage must be a C-contiguous uint8 HWC array")
+        h, w, c = inimage.shape
+        if outimage.dtype != np.uint8 or outimage.shape != (h * 4, w * 4, c) or not outimage.flags.c_contiguous:
+            raise RealSRError("outimage must be a preallocated C-contiguous uint8 array of shape (4h, 4w, c)")
+        self._push_params()
+        return self._lib.rsr_process(self._h, inimage.ctypes.data, w, h, c, outimage.ctypes.data)
+
+    def process_ptr(self, in_ptr, w, h, c, out_ptr):
+        """process() on raw HOST pointers (e.g. pinned torch tensors): same contract as the C ABI rsr_process."""
+        self._push_params()
+        return self._lib.rsr_process(self._h, ctypes.c_void_p(in_ptr), w, h, c, ctypes.c_void_p(out_ptr))
+
+    def process_device(self, d_in_ptr, w, h, c, d_out_ptr):
+        """Same computation on buffers already resident on the handle's GPU (raw device pointers)."""
+        self._push_params()
+        return self._lib.rsr_process_device(self._h, ctypes.c_void_p(d_in_ptr), w, h, c, ctypes.c_void_p(d_out_ptr))
+
+    # ---- introspection (no reference counterpart) ----
+    def set_option(self, key, value):
+        return self._lib.rsr_set_option(self._h, key.encode(), int(value))
+
+    def kernel_launches(self):
+        return int(self._lib.rsr_kernel_launches(self._h))
+
+    def last_ms(self, what=0):
+        return float(self._lib.rsr_last_ms(self._h, what))
+
+    def last_padded_pixels(self):
+        return int(self._lib.rsr_last_padded_pixels(self._h))
+
+    def debug_conv(self, conv_index, x16, cout):
+        """runs one conv layer of the loaded model on the tensor-core kernel: x16 (H, W, cin) float16 -> (H, W, cout) float32"""
+        x16 = np.ascontiguousarray(x16, dtype=np.float16)
+        H, W, _ = x16.shape
+        out = np.zeros((H, W, cout), dtype=np.float32)
+        r = self._lib.rsr_debug_conv(self._h, conv_index, x16.ctypes.data, H, W, out.ctypes.data)
+        if r:
+            raise RealSRError(self.last_error())
+        return out
