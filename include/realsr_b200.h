@@ -91,6 +91,15 @@ RSR_API int rsr_set_option(rsr_handle* h, const char* key, long long value);
  *           rounded to fp16 exactly as the engine stores it. */
 RSR_API int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, int W, float* out32);
 
+/* Host-only checks (no GPU needed): parse + verify a .param/.bin pair exactly as rsr_load() does.
+ * On success returns 0 and fills num_rrdb / num_convs; on failure returns RSR_ERR_MODEL and writes the reason to err. */
+RSR_API int rsr_check_model(const char* parampath, const char* modelpath, int* num_rrdb, int* num_convs, char* err, int errlen);
+/* Host-only: shape of conv #conv_index (file order) and, if `packed` is non-NULL, its weights in the swizzled
+ * [chunk][tap][cout_pad][64] fp16 layout the tensor-core kernel streams (capacity in uint16 elements).
+ * Returns the number of uint16 elements of the packed image, or a negative code. */
+RSR_API long long rsr_debug_pack(const char* parampath, const char* modelpath, int conv_index, int* cin, int* cout, int* cout_pad,
+                                 uint16_t* packed, long long capacity);
+
 #ifdef __cplusplus
 }
 #endif

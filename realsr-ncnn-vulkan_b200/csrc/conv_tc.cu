@@ -84,58 +84,62 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
     const uint32_t tmem_base = bars->tmem_ptr;
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int c = 0; c < nchunk; c++) {
-                const int s = c % NA;
-                mbar_wait(&bars->a_empty[s], ((c / NA) & 1) ^ 1);
+        const bool leader = elect_one();
+        for (int c = 0; c < nchunk; c++) {
+            const int s = c % NA;
+            mbar_wait(&bars->a_empty[s], ((c / NA) & 1) ^ 1);
+            if (leader) {
                 mbar_expect_tx(&bars->a_full[s], A_BYTES);
                 tma_load_4d(smA + s * A_STAGE, &tmap, &bars->a_full[s], c * 64, x0 - 1, y0 - 1, b);
             }
         }
     } else if (warp == 2) {
-        if (lane == 0) {
-            const uint8_t* w = reinterpret_cast<const uint8_t*>(a.wpk);
-            const int nit = nchunk * 9;
-            for (int it = 0; it < nit; it++) {
-                const int s = it % C::NB;
-                mbar_wait(&bars->b_empty[s], ((it / C::NB) & 1) ^ 1);
+        const bool leader = elect_one();
+        const uint8_t* w = reinterpret_cast<const uint8_t*>(a.wpk);
+        const int nit = nchunk * 9;
+        for (int it = 0; it < nit; it++) {
+            const int s = it % C::NB;
+            mbar_wait(&bars->b_empty[s], ((it / C::NB) & 1) ^ 1);
+            if (leader) {
                 mbar_expect_tx(&bars->b_full[s], C::B_SLAB);
                 bulk_load(smB + s * C::B_SLAB, w + (size_t)it * C::B_SLAB, C::B_SLAB, &bars->b_full[s]);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(128, N);
-            int it = 0;
-            for (int c = 0; c < nchunk; c++) {
-                const int sA = c % NA;
-                mbar_wait(&bars->a_full[sA], (c / NA) & 1);
+        // The whole warp runs the (warp-uniform) loop and one elected lane issues: descriptors then live in uniform
+        // registers and every tcgen05.mma is a single predicated UTCHMMA.  (Issuing from inside `if (lane == 0)`
+        // made the compiler wrap each MMA in a divergence loop: ~120 clk per MMA, measured.)
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = umma_idesc_f16(128, N);
+        const uint64_t desc_hi = umma_desc_sw128(0, 1024, 0);
+        int it = 0;
+        for (int c = 0; c < nchunk; c++) {
+            const int sA = c % NA;
+            mbar_wait(&bars->a_full[sA], (c / NA) & 1);
+            tc_fence_after();
+            const int rem = a.cin - c * 64;
+            const int ksteps = rem >= 64 ? 4 : (rem >> 4);
+            const uint32_t a_base = smem_u32(smA + sA * A_STAGE);
+            for (int tap = 0; tap < 9; tap++, it++) {
+                const int sB = it % C::NB;
+                mbar_wait(&bars->b_full[sB], (it / C::NB) & 1);
                 tc_fence_after();
-                const int rem = a.cin - c * 64;
-                const int ksteps = rem >= 64 ? 4 : (rem >> 4);
-                const uint32_t a_base = smem_u32(smA + sA * A_STAGE);
-                for (int tap = 0; tap < 9; tap++, it++) {
-                    const int sB = it % C::NB;
-                    mbar_wait(&bars->b_full[sB], (it / C::NB) & 1);
-                    tc_fence_after();
-                    const uint32_t b_base = smem_u32(smB + sB * C::B_SLAB);
-                    const int ky = tap / 3, kx = tap - ky * 3;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                const uint64_t db0 = desc_hi | (uint64_t)((smem_u32(smB + sB * C::B_SLAB) & 0x3FFFFu) >> 4);
 #pragma unroll
-                    for (int mt = 0; mt < MT; mt++) {
-                        const uint32_t a_row = a_base + (uint32_t)(ky * P + kx + mt * 128) * 128u;
-                        const uint32_t bo = a.desc_mode ? ((a_row >> 7) & 7u) : 0u;
-                        for (int ks = 0; ks < ksteps; ks++) {
-                            const uint64_t da = umma_desc_sw128(a_row + ks * 32, 1024, bo);
-                            const uint64_t db = umma_desc_sw128(b_base + ks * 32, 1024, 0);
-                            umma_f16(tmem_base + mt * N, da, db, idesc, (c | tap | ks) ? 1u : 0u);
-                        }
+                for (int mt = 0; mt < MT; mt++) {
+                    const uint64_t da0 = desc_hi | (uint64_t)(((a_base + (uint32_t)(ky * P + kx + mt * 128) * 128u) & 0x3FFFFu) >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        if (ks < ksteps && leader)
+                            umma_f16(tmem_base + mt * N, da0 + ks * 2, db0 + ks * 2, idesc, (c | tap | ks) ? 1u : 0u);
                     }
-                    umma_commit(&bars->b_empty[sB]);
                 }
-                umma_commit(&bars->a_empty[sA]);
+                if (leader) umma_commit(&bars->b_empty[sB]);
             }
-            umma_commit(&bars->acc_full);
+            if (leader) umma_commit(&bars->a_empty[sA]);
         }
+        if (leader) umma_commit(&bars->acc_full);
     } else {
         // ---------------- epilogue: warps 3..6, TMEM lane quarter = warp % 4 ----------------
         mbar_wait(&bars->acc_full, 0);

@@ -553,6 +553,39 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
     return 0;
 }
 
+int rsr_check_model(const char* parampath, const char* modelpath, int* num_rrdb, int* num_convs, char* err, int errlen)
+{
+    if (!parampath || !modelpath) return RSR_ERR_GENERIC;
+    Model m;
+    const int r = load_model(parampath, modelpath, m);
+    if (err && errlen > 0) snprintf(err, (size_t)errlen, "%s", m.error.c_str());
+    if (r) return RSR_ERR_MODEL;
+    if (num_rrdb) *num_rrdb = m.num_rrdb;
+    if (num_convs) *num_convs = (int)m.convs.size();
+    return 0;
+}
+
+long long rsr_debug_pack(const char* parampath, const char* modelpath, int conv_index, int* cin, int* cout, int* cout_pad, uint16_t* packed,
+                         long long capacity)
+{
+    if (!parampath || !modelpath) return RSR_ERR_GENERIC;
+    Model m;
+    if (load_model(parampath, modelpath, m)) return RSR_ERR_MODEL;
+    if (conv_index < 0 || conv_index >= (int)m.convs.size()) return RSR_ERR_GENERIC;
+    const ConvLayer& c = m.convs[conv_index];
+    const int npad = c.cout <= 16 ? 16 : (c.cout <= 32 ? 32 : 64);
+    if (cin) *cin = c.cin;
+    if (cout) *cout = c.cout;
+    if (cout_pad) *cout_pad = npad;
+    std::vector<uint16_t> out;
+    pack_conv_weights(c, npad, out);
+    if (packed) {
+        if ((long long)out.size() > capacity) return RSR_ERR_GENERIC;
+        memcpy(packed, out.data(), out.size() * 2);
+    }
+    return (long long)out.size();
+}
+
 int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, int W, float* out32)
 {
     if (!h || !h->loaded) return RSR_ERR_GENERIC;

@@ -1,0 +1,116 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/realsr_b200.h declares, the
+model loader accepts the shipped files / rejects broken ones, weight packing, and loud failure without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import realsr_ncnn_vulkan_b200 as rb
+from common import ROOT, model_paths, read_convs
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "realsr_b200.h")).read()
+    return sorted(set(re.findall(r"RSR_API\s+[\w\s\*]+?\b(rsr_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = rb.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+
+
+def check_model(param, binf):
+    lib = rb.load_library()
+    lib.rsr_check_model.restype = ctypes.c_int
+    nr, nc = ctypes.c_int(0), ctypes.c_int(0)
+    err = ctypes.create_string_buffer(512)
+    r = lib.rsr_check_model(param.encode(), binf.encode(), ctypes.byref(nr), ctypes.byref(nc), err, 512)
+    return r, nr.value, nc.value, err.value.decode()
+
+
+@pytest.mark.parametrize("model", ["models-DF2K", "models-DF2K_JPEG"])
+def test_shipped_models_parse(model, models_dir):
+    """351 convs = 1 + 23*15 + 5; .bin consumed exactly (33 424 520 B)"""
+    p, b = model_paths(model)
+    r, nr, nc, err = check_model(p, b)
+    assert (r, nr, nc) == (0, 23, 351), err
+    assert os.path.getsize(b) == 33424520
+
+
+def test_loader_rejects_bad_files(models_dir, tmp_path):
+    p, b = model_paths("models-DF2K")
+    r, _, _, err = check_model(str(tmp_path / "nope.param"), b)
+    assert r != 0 and "cannot open" in err
+    # truncated weights
+    tb = tmp_path / "trunc.bin"
+    tb.write_bytes(open(b, "rb").read()[:1000000])
+    r, _, _, err = check_model(p, str(tb))
+    assert r != 0 and "truncated" in err
+    # a graph that is not RRDBNet: drop one Eltwise line
+    lines = open(p).read().split("\n")
+    idx = [i for i, l in enumerate(lines) if l.startswith("Eltwise")][5]
+    bad = tmp_path / "bad.param"
+    bad.write_text("\n".join(lines[:idx] + lines[idx + 1:]).replace("\n999 ", "\n998 ", 1))
+    r, _, _, err = check_model(str(bad), b)
+    assert r != 0 and "RRDBNet" in err
+    # wrong magic
+    bad.write_text("123\n1 1\n")
+    r, _, _, err = check_model(str(bad), b)
+    assert r != 0 and "magic" in err
+
+
+def test_weight_packing_matches_numpy(models_dir):
+    """[chunk][tap][n][64] fp16 with the SWIZZLE_128B chunk permutation, zero padded"""
+    lib = rb.load_library()
+    lib.rsr_debug_pack.restype = ctypes.c_longlong
+    p, b = model_paths("models-DF2K")
+    convs = read_convs("models-DF2K")
+    for idx in (1, 2, 5, 350):
+        c = convs[idx]
+        cin, cout, npad = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        n = lib.rsr_debug_pack(p.encode(), b.encode(), idx, ctypes.byref(cin), ctypes.byref(cout), ctypes.byref(npad), None, ctypes.c_longlong(0))
+        assert (cin.value, cout.value) == (c["cin"], c["cout"])
+        nchunk = (c["cin"] + 63) // 64
+        assert n == nchunk * 9 * npad.value * 64
+        buf = np.zeros(n, dtype=np.uint16)
+        assert lib.rsr_debug_pack(p.encode(), b.encode(), idx, None, None, None, buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(n)) == n
+        ref = np.zeros((nchunk, 9, npad.value, 64), dtype=np.float16)
+        w = c["w"].reshape(c["cout"], c["cin"], 9)
+        for ch in range(nchunk):
+            k = min(64, c["cin"] - ch * 64)
+            blk = np.zeros((9, npad.value, 64), dtype=np.float16)
+            blk[:, :c["cout"], :k] = np.transpose(w[:, ch * 64:ch * 64 + k, :], (2, 0, 1))
+            # swizzle: 16-byte chunk j of row n goes to chunk j ^ (n & 7)
+            blk = blk.reshape(9, npad.value, 8, 8)
+            sw = np.zeros_like(blk)
+            for nrow in range(npad.value):
+                for j in range(8):
+                    sw[:, nrow, j ^ (nrow & 7)] = blk[:, nrow, j]
+            ref[ch] = sw.reshape(9, npad.value, 64)
+        assert np.array_equal(buf.view(np.float16).reshape(ref.shape).view(np.uint16), ref.view(np.uint16))
+
+
+def test_fails_loudly_without_gpu_or_with_cpu_id(models_dir):
+    """no CPU fallback: gpuid -1 (the reference's ncnn CPU mode) and a missing device are errors, not silent paths"""
+    p, b = model_paths("models-DF2K")
+    e = rb.RealSR(-1)
+    assert e.load(p, b) == -4 and "CPU" in e.last_error()
+    out = np.zeros((128, 128, 3), dtype=np.uint8)
+    assert e.process(np.zeros((32, 32, 3), dtype=np.uint8), out) != 0
+    e = rb.RealSR(63)
+    assert e.load(p, b) != 0 and "device" in e.last_error()
+
+
+def test_set_validation():
+    e = rb.RealSR(0)
+    e.scale = 2
+    with pytest.raises(rb.RealSRError):
+        e._push_params()
+    e.scale, e.tilesize = 4, 16
+    with pytest.raises(rb.RealSRError):
+        e._push_params()

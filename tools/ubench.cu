@@ -1,0 +1,223 @@
+// tools/ubench.cu -- B200 micro-benchmarks that size the conv kernel's design (not part of the product).
+//   1. tcgen05.mma kind::f16 throughput vs N with both operands in shared memory (SS), M=128, K=16 per instruction:
+//      is a small-N MMA limited by the tensor pipe (N/2 clk) or by the smem operand feed?
+//   2. same with A in TMEM (TS).
+//   3. L2 -> smem and HBM -> smem streaming bandwidth with cp.async.bulk, all SMs, deep pipeline.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/ubench tools/ubench.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../realsr-ncnn-vulkan_b200/csrc/ptx.cuh"
+
+using namespace rsr;
+
+#define CK(x)                                                                        \
+    do {                                                                             \
+        cudaError_t e = (x);                                                         \
+        if (e != cudaSuccess) {                                                      \
+            printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); \
+            exit(1);                                                                 \
+        }                                                                            \
+    } while (0)
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+#define UMMA_VARIANT(name, opc)                                                                                        \
+    __device__ __forceinline__ void name(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) \
+    {                                                                                                                  \
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t" opc " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),   \
+                     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)                                                    \
+                     : "memory");                                                                                      \
+    }
+UMMA_VARIANT(umma_a_fill, "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill")
+UMMA_VARIANT(umma_a_use, "tcgen05.mma.cta_group::1.kind::f16.collector::a::use")
+UMMA_VARIANT(umma_a_last, "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse")
+UMMA_VARIANT(umma_ws_fill, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill")
+UMMA_VARIANT(umma_ws_use, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::use")
+UMMA_VARIANT(umma_ws_last, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse")
+UMMA_VARIANT(umma_ws_discard, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::discard")
+
+// mode 3: groups of 4 MMAs share A (A_KEEP then A_REUSE), B differs; mode 4: .ws, groups of 4 share B (fill, use x3), A differs;
+// mode 5: .ws, every MMA discards (no reuse)
+// mode 0: SS aligned A; mode 1: SS with row-shifted A starts (like the conv taps); mode 2: TS (A in TMEM)
+template <int N>
+__global__ void __launch_bounds__(128, 1) mma_bench(int iters, int mode, int nacc, long long* out_cycles)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smA = smem;                       // 64 KB: 512 rows x 128 B
+    uint8_t* smB = smem + 65536;               // 256 rows x 128 B = 32 KB
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_ptr;
+    for (int i = threadIdx.x; i < (65536 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u ^ (i * 2654435761u & 0x03ff03ffu);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_ptr, 512);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = tmem_ptr;
+    if (threadIdx.x < 32) {  // warp-uniform loop; one elected lane issues
+        constexpr uint32_t idesc = umma_idesc_f16(128, N);
+        const uint32_t a0 = smem_u32(smA), b0 = smem_u32(smB);
+        const uint64_t da0 = umma_desc_sw128(a0, 1024, 0), db0 = umma_desc_sw128(b0, 1024, 0);
+        const bool leader = elect_one();
+        long long t0 = clock64();
+        uint32_t phase = 0;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+                const uint64_t da = da0 + (uint64_t)(mode == 1 ? (((tap / 3) * 32 + tap % 3) * 128) >> 4 : 0);
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    const uint32_t d = tm + (nacc == 2 ? ((tap + ks) & 1) * N : 0);
+                    if (leader) {
+                        if (mode == 2) umma_f16_ts(d, tm + 256 + ks * 8, db0 + ks * 2, idesc, 1);
+                        else if (mode == 3) {
+                            // same A (tap), B advanced per ks (pretend different weights): fill, use, use, lastuse
+                            if (ks == 0) umma_a_fill(d, da, db0 + ks * 2, idesc, 1);
+                            else if (ks == 3) umma_a_last(d, da, db0 + ks * 2, idesc, 1);
+                            else umma_a_use(d, da, db0 + ks * 2, idesc, 1);
+                        } else if (mode == 4) {
+                            // same B (tap), A differs per ks (pretend 4 M-tiles, 16 KB apart)
+                            const uint64_t dam = da0 + (uint64_t)(ks * 16384 >> 4);
+                            const uint32_t dd = tm + ks * N % 512;
+                            if (ks == 0) umma_ws_fill(dd, dam, db0 + (tap & 3) * 2, idesc, 1);
+                            else if (ks == 3) umma_ws_last(dd, dam, db0 + (tap & 3) * 2, idesc, 1);
+                            else umma_ws_use(dd, dam, db0 + (tap & 3) * 2, idesc, 1);
+                        } else if (mode == 5) umma_ws_discard(d, da + ks * 2, db0 + ks * 2, idesc, 1);
+                        else umma_f16(d, da + ks * 2, db0 + ks * 2, idesc, 1);
+                    }
+                }
+            }
+            if ((it & 7) == 7) {  // bound the number of MMAs in flight
+                if (leader) umma_commit(&bar);
+                mbar_wait(&bar, phase);
+                phase ^= 1;
+            }
+        }
+        if (leader) umma_commit(&bar);
+        mbar_wait(&bar, phase);
+        long long t1 = clock64();
+        if (leader) out_cycles[blockIdx.x] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
+template <int N>
+void run_mma(int mode, int nacc)
+{
+    long long* d;
+    CK(cudaMalloc(&d, 148 * 8));
+    const int smem = 1024 + 65536 + 32768;
+    CK(cudaFuncSetAttribute(mma_bench<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int iters = 2000;
+    mma_bench<N><<<148, 128, smem>>>(50, mode, nacc, d);  // warm-up
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    mma_bench<N><<<148, 128, smem>>>(iters, mode, nacc, d);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long h[148];
+    CK(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
+    double avg = 0;
+    for (int i = 0; i < 148; i++) avg += (double)h[i];
+    avg /= 148;
+    const double nmma = (double)iters * 36;
+    const double flops = nmma * 2.0 * 128 * N * 16 * 148;
+    printf("N=%3d mode=%d nacc=%d: %.2f clk/MMA (tensor floor %d)  -> %.1f TFLOP/s chip (%.3f ms)\n", N, mode, nacc, avg / nmma, N / 2,
+           flops / (ms * 1e-3) / 1e12, ms);
+    cudaFree(d);
+}
+
+// ---- streaming bandwidth: every CTA keeps `depth` bulk copies of `chunk` bytes in flight -------------------------------
+__global__ void __launch_bounds__(128, 1) stream_bench(const uint8_t* src, size_t span_bytes, int chunk, int depth, int nchunks, long long* out_cycles)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bars[16];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < depth; i++) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t nslots = span_bytes / chunk;
+        size_t slot = ((size_t)blockIdx.x * 7919) % nslots;
+        long long t0 = clock64();
+        for (int i = 0; i < nchunks + depth; i++) {
+            const int s = i % depth;
+            if (i >= depth) mbar_wait(&bars[s], ((i / depth) - 1) & 1);
+            if (i < nchunks) {
+                mbar_expect_tx(&bars[s], chunk);
+                bulk_load(smem + (size_t)s * chunk, src + slot * chunk, chunk, &bars[s]);
+                slot += gridDim.x;
+                if (slot >= nslots) slot -= nslots;
+            }
+        }
+        out_cycles[blockIdx.x] = clock64() - t0;
+    }
+}
+
+void run_stream(const char* name, size_t span, int chunk, int depth, int ctas_per_sm)
+{
+    uint8_t* buf;
+    CK(cudaMalloc(&buf, span));
+    CK(cudaMemset(buf, 1, span));
+    long long* d;
+    const int grid = 148 * ctas_per_sm;
+    CK(cudaMalloc(&d, grid * 8));
+    const int smem = 1024 + chunk * depth;
+    CK(cudaFuncSetAttribute(stream_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int nchunks = (int)((size_t)(64 << 20) / chunk);  // 64 MB per CTA
+    stream_bench<<<grid, 128, smem>>>(buf, span, chunk, depth, 256, d);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    stream_bench<<<grid, 128, smem>>>(buf, span, chunk, depth, nchunks, d);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long h[148 * 4];
+    CK(cudaMemcpy(h, d, grid * 8, cudaMemcpyDeviceToHost));
+    double avg = 0;
+    for (int i = 0; i < grid; i++) avg += (double)h[i];
+    avg /= grid;
+    const double bytes = (double)nchunks * chunk * grid;
+    printf("%-4s span %5zu MB chunk %3d KB depth %2d x%d CTA/SM: %.2f TB/s, %.1f B/clk/SM (%.3f ms)\n", name, span >> 20, chunk >> 10, depth, ctas_per_sm,
+           bytes / (ms * 1e-3) / 1e12, (double)nchunks * chunk * ctas_per_sm / avg, ms);
+    cudaFree(buf);
+    cudaFree(d);
+}
+
+int main()
+{
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, 0));
+    printf("%s, %d SMs, clock %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
+    for (int mode = 4; mode < 6; mode++) {
+        run_mma<64>(mode, 1);
+        run_mma<128>(mode, 1);
+        run_mma<256>(mode, 1);
+    }
+
+    return 0;
+}
