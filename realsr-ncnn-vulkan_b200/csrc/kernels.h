@@ -60,7 +60,7 @@ struct ConvArgs {
 // conv3x3 s1 p1 as implicit GEMM on tcgen05 (conv_tc.cu). cout_pad in {16, 32, 64}.
 cudaError_t launch_conv3x3_tc(const CUtensorMap* in_map, const ConvArgs& a, int cout_pad, cudaStream_t stream);
 // box dims the kernel expects from the tensor map: {64 ch, 32 px, CONV_BH+2 rows, 1}
-constexpr int CONV_BH = 8;
+constexpr int CONV_BH = 16;
 constexpr int CONV_P = 32;
 
 // Conv_0 (3->64, fp32 CUDA cores) fused with preproc (crop, reflect-101, x 1/255, TTA variant), conv_first.cu
