@@ -1,0 +1,154 @@
+"""GPU parity tests (run with `pytest -m gpu` on a B200).  Everything goes through the C ABI (librealsr_b200.so) via the
+Python mirror of the reference's `class RealSR`.
+
+Tolerance contract (vs the reference's own CPU path at the same tile size; stated here because the path is
+floating point: fp16 tensor-core operands with fp32 accumulation, fp32 Conv_0 and fp32 residual stream):
+  * natural images : every byte within 1 LSB, >= 95 % of bytes exact
+  * uniform noise  : max 2 LSB, at most 1 byte in 10 000 off by more than 1 LSB
+Per-layer: abs-or-relative 2e-3 against an fp32 torch conv on the same fp16 operands (ncnn's own Winograd-eligible
+conv tolerance, ncnn/tests/test_convolution.cpp:42-52), result rounded to fp16 as the engine stores it.
+"""
+import threading
+
+import numpy as np
+import pytest
+
+import realsr_ncnn_vulkan_b200 as rb
+from common import Oracle, diff_stats, golden, manifest, model_paths, read_convs
+
+pytestmark = pytest.mark.gpu
+
+_ENG = {}
+
+
+def engine(model, tta=False):
+    key = (model, tta)
+    if key not in _ENG:
+        e = rb.RealSR(0, tta_mode=tta)
+        p, b = model_paths(model)
+        assert e.load(p, b) == 0, e.last_error()
+        _ENG[key] = e
+    return _ENG[key]
+
+
+def run(model, img, tilesize, tta=False):
+    e = engine(model, tta)
+    e.tilesize = tilesize
+    out = np.zeros((img.shape[0] * 4, img.shape[1] * 4, 3), dtype=np.uint8)
+    assert e.process(img, out) == 0, e.last_error()
+    return out
+
+
+def check_contract(s, natural):
+    if natural:
+        assert s["max"] <= 1 and s["frac_diff"] <= 0.05, s
+    else:
+        assert s["max"] <= 2 and s["n_gt1"] <= max(2, s["n"] // 10000), s
+
+
+CASES = manifest()["cases"]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_vs_reference_cpu_path(case, models_dir):
+    """CUDA path vs the committed outputs of the real reference CPU path (oracle/_ref), same tile size"""
+    img, gold = golden(case["name"])
+    out = run(case["model"], img, case["tilesize"], bool(case["tta"]))
+    check_contract(diff_stats(out, gold), natural=not case["name"].startswith(("noise", "cfg1_noise")))
+
+
+@pytest.mark.parametrize("idx,H,W", [(1, 37, 45), (2, 16, 30), (3, 17, 31), (4, 64, 61), (5, 33, 95), (346, 40, 40), (347, 35, 62), (350, 29, 47)])
+def test_conv_layer_vs_torch(idx, H, W, models_dir):
+    """one 3x3 conv of the model on the tcgen05 kernel vs torch fp32 conv2d on identical fp16 operands"""
+    import torch
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = False
+    c = read_convs("models-DF2K")[idx]
+    rng = np.random.default_rng(idx * 1000 + H)
+    x = (rng.standard_normal((H, W, c["cin"])) * 0.5).astype(np.float16)
+    y = engine("models-DF2K").debug_conv(idx, x, c["cout"])
+    xt = torch.from_numpy(x.astype(np.float32)).cuda().permute(2, 0, 1)[None]
+    ref = F.conv2d(xt, torch.from_numpy(c["w"].astype(np.float32)).cuda(), torch.from_numpy(c["b"].copy()).cuda(), padding=1)
+    if c["act"] == 2:
+        ref = F.leaky_relu(ref, 0.2)
+    ref = ref[0].permute(1, 2, 0).cpu().numpy()
+    if c["cout"] != 3:
+        ref = ref.astype(np.float16).astype(np.float32)
+    err = np.abs(y - ref)
+    assert np.all((err <= 2e-3) | (err <= 2e-3 * np.abs(ref))), float(err.max())
+
+
+@pytest.mark.parametrize("w,h,tile,tta", [(16, 13, 32, False), (33, 47, 32, False), (61, 32, 32, True), (45, 45, 200, False)])
+def test_fresh_inputs_vs_oracle_port(w, h, tile, tta, models_dir):
+    """inputs that are not in the golden set, checked against the C restatement run here (edge tiles, ragged sizes)"""
+    img = np.random.default_rng(w * 100 + h).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref = Oracle("models-DF2K_JPEG").process(img, tile, tta=tta)
+    check_contract(diff_stats(run("models-DF2K_JPEG", img, tile, tta), ref), natural=False)
+
+
+def test_constant_and_extreme_images(models_dir):
+    for v in (0, 255, 128):
+        img = np.full((40, 52, 3), v, dtype=np.uint8)
+        ref = Oracle("models-DF2K").process(img, 32)
+        check_contract(diff_stats(run("models-DF2K", img, 32), ref), natural=True)
+
+
+def test_full_size_properties(models_dir):
+    """BASELINE configs[1] size (1920x1080, tile 400), where the CPU oracle would take minutes: size-independent
+    properties.  (a) deterministic; (b) device-resident path == host path; (c) a tile's output only depends on its own
+    padded input: changing the bottom-right tile leaves the bytes of all non-adjacent tiles unchanged; (d) the top-left
+    tile equals a stand-alone run on its padded crop (same tile geometry) -> ties the big run to the small-case parity."""
+    import torch
+    img = np.random.default_rng(7).integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    e = engine("models-DF2K")
+    a = run("models-DF2K", img, 400)
+    b = run("models-DF2K", img, 400)
+    assert np.array_equal(a, b)
+    d_in, d_out = torch.from_numpy(img).cuda(), torch.empty((4320, 7680, 3), dtype=torch.uint8, device="cuda")
+    assert e.process_device(d_in.data_ptr(), 1920, 1080, 3, d_out.data_ptr()) == 0
+    assert np.array_equal(d_out.cpu().numpy(), a)
+    img2 = img.copy()
+    img2[900:, 1700:] = 255 - img2[900:, 1700:]
+    c = run("models-DF2K", img2, 400)
+    assert np.array_equal(c[:3200, :], a[:3200, :]) and np.array_equal(c[:, :6400], a[:, :6400])
+    assert not np.array_equal(c[3600:, 6800:], a[3600:, 6800:])
+    crop = np.ascontiguousarray(img[:410, :410])  # tile (0,0) sees rows/cols [0, 410)
+    s = run("models-DF2K", crop, 400)
+    assert np.array_equal(s[:1600, :1600], a[:1600, :1600])
+    assert e.last_padded_pixels() == 420 * 420 + 2 * 420 * 30 + 30 * 30
+
+
+def test_reentrant_same_handle(models_dir):
+    """RealSR::process is const and is called concurrently on one object (src/main.cpp:811-828)"""
+    imgs = [np.random.default_rng(50 + i).integers(0, 256, (48, 70, 3), dtype=np.uint8) for i in range(4)]
+    serial = [run("models-DF2K", im, 32) for im in imgs]
+    e = engine("models-DF2K")
+    e.tilesize = 32
+    outs = [np.zeros_like(s) for s in serial]
+    rcs = [None] * 4
+
+    def work(i):
+        rcs[i] = e._lib.rsr_process(e._h, imgs[i].ctypes.data, 70, 48, 3, outs[i].ctypes.data)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert rcs == [0, 0, 0, 0]
+    for o, s in zip(outs, serial):
+        assert np.array_equal(o, s)
+
+
+def test_tta_is_dihedral_equivariant(models_dir):
+    """TTA averages the 8 dihedral variants, so flipping the input flips the output (up to fp32 summation order)"""
+    img = np.random.default_rng(99).integers(0, 256, (36, 36, 3), dtype=np.uint8)
+    a = run("models-DF2K", img, 200, tta=True)
+    b = run("models-DF2K", np.ascontiguousarray(img[::-1]), 200, tta=True)[::-1]
+    assert diff_stats(a, b)["max"] <= 1
+
+
+def test_errors_are_reported(models_dir):
+    e = rb.RealSR(0)
+    assert e.process(np.zeros((8, 8, 3), np.uint8), np.zeros((32, 32, 3), np.uint8)) != 0 and "no model" in e.last_error()
+    g = engine("models-DF2K")
+    assert g.process(np.zeros((8, 8, 4), np.uint8), np.zeros((32, 32, 4), np.uint8)) != 0  # RGBA not implemented: loud
+    assert g.kernel_launches() > 0
