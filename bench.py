@@ -179,23 +179,9 @@ def main():
 
     # Weights: rank 0 reads the model files, every other rank receives the bytes over NCCL once at init (no hot-path
     # collective).  The engine API loads from a path, so the received bytes go through a private temp dir.
+    import realsr_ncnn_vulkan_b200.dist as rdist
     p, b = model_paths()
-    tmpdir = None
-    if world > 1:
-        blobs = []
-        for path in (p, b):
-            n = torch.tensor([os.path.getsize(path) if rank == 0 else 0], dtype=torch.int64, device="cuda")
-            dist.broadcast(n, 0)
-            t = torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                t.copy_(torch.from_numpy(np.fromfile(path, dtype=np.uint8)))
-            dist.broadcast(t, 0)
-            blobs.append(t)
-        if rank != 0:
-            tmpdir = tempfile.TemporaryDirectory()
-            p, b = os.path.join(tmpdir.name, "x4.param"), os.path.join(tmpdir.name, "x4.bin")
-            blobs[0].cpu().numpy().tofile(p)
-            blobs[1].cpu().numpy().tofile(b)
+    p, b, _keep = rdist.broadcast_model_files(p, b, rank, world, device="cuda")
     eng = rb.RealSR(local, tta_mode=False, num_threads=1)
     if eng.load(p, b):
         raise SystemExit("rsr_load failed: " + eng.last_error())

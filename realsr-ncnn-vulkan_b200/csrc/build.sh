@@ -16,3 +16,7 @@ pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT build/conv_tc.o build/misc_kernels.o build/engine.o build/model.o -ccbin /usr/bin/g++
 echo "built $(realpath $OUT)"
+# host-side C++ mirror of the reference interface (class RealSR over the C ABI) + a minimal caller written like the
+# reference's proc stage
+/usr/bin/g++ -O2 -std=c++11 -Wall -o ../realsr_raw_cli ../host/realsr_raw_cli.cpp -L.. -lrealsr_b200 -Wl,-rpath,'$ORIGIN' -lpthread
+echo "built $(realpath ../realsr_raw_cli)"

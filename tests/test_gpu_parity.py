@@ -152,3 +152,20 @@ def test_errors_are_reported(models_dir):
     g = engine("models-DF2K")
     assert g.process(np.zeros((8, 8, 4), np.uint8), np.zeros((32, 32, 4), np.uint8)) != 0  # RGBA not implemented: loud
     assert g.kernel_launches() > 0
+
+
+def test_cpp_wrapper_cli_concurrent_jobs(tmp_path, models_dir):
+    """the C++ `class RealSR` wrapper driven like the reference's proc stage: 3 threads call process() on one object"""
+    import os
+    import subprocess
+    from common import ROOT
+    exe = os.path.join(ROOT, "realsr-ncnn-vulkan_b200", "realsr_raw_cli")
+    if not os.path.exists(exe):
+        pytest.skip("realsr_raw_cli not built")
+    img, gold = golden("natural_48x40_df2k_t32")
+    fi, fo = tmp_path / "i.raw", tmp_path / "o.raw"
+    img.tofile(fi)
+    r = subprocess.run([exe, os.path.join(models_dir, "models-DF2K"), str(fi), "48", "40", str(fo), "-t", "32", "-j", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(fo, dtype=np.uint8).reshape(gold.shape)
+    check_contract(diff_stats(out, gold), natural=True)

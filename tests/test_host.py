@@ -114,3 +114,24 @@ def test_set_validation():
     e.scale, e.tilesize = 4, 16
     with pytest.raises(rb.RealSRError):
         e._push_params()
+
+
+def test_cpp_wrapper_compiles_and_fails_loudly(tmp_path, models_dir):
+    """class RealSR (host/realsr.h, the reference's signatures) over the C ABI: builds with a plain g++ and reports the
+    missing GPU instead of falling back to anything"""
+    import subprocess
+    exe = tmp_path / "cli"
+    host = os.path.join(ROOT, "realsr-ncnn-vulkan_b200", "host")
+    libdir = os.path.join(ROOT, "realsr-ncnn-vulkan_b200")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++11", "-Wall", "-Werror", "-o", str(exe), os.path.join(host, "realsr_raw_cli.cpp"),
+                           "-L" + libdir, "-lrealsr_b200", "-Wl,-rpath," + libdir, "-lpthread"])
+    raw = tmp_path / "in.raw"
+    np.zeros((8, 8, 3), np.uint8).tofile(raw)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    r = subprocess.run([str(exe), os.path.join(models_dir, "models-DF2K"), str(raw), "8", "8", str(tmp_path / "o.raw")], capture_output=True, text=True)
+    if not has_gpu:
+        assert r.returncode == 4 and "invalid gpu device" in r.stderr
