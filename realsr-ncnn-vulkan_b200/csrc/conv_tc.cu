@@ -12,7 +12,7 @@
 // input the producer TMA-loads ONE haloed box {64 ch, P=32 px, BH+2 rows} (out-of-bounds = zeros = the conv's zero
 // padding) into shared memory as (BH+2)*32 rows of 128 B (SWIZZLE_128B, K-major).  Because the box is stored with a
 // fixed pitch of P pixels, the A operand of tap (ky,kx) for 128 consecutive "flattened" output positions q = r*P + c
-// is just the 128 consecutive smem rows starting at row q + ky*P + kx: the 9 taps re-use the same bytes through 9
+// is just the 128 consecutive smem rows starting at row q + ky*P + kx: the 9 taps re-use the same bytes through
 // row-shifted UMMA descriptors (measured on B200: the 128B swizzle is a function of the absolute smem address, so a
 // start address that is a multiple of 128 B needs no base offset) -- no im2col, no per-tap reload.  Positions with
 // c >= 30 compute garbage that is never stored (6.25 % of the MMA work).
@@ -22,14 +22,20 @@
 // weight-stationary form `tcgen05.mma.ws` keeps the B operand (the weights of one (chunk, tap, k-step): N x 16) in a
 // collector buffer: with B filled once and re-used for the 4 M-tiles of the work tile it runs at ~52 clk per
 // 128x64x16 MMA (A streams at the smem limit of 32 clk).  So every conv runs as N=64 .ws MMAs, loop order
-// (chunk, tap, k-step) outer / M-tile inner; the Cout=32 convs read a 64-row B window whose upper half is whatever
-// follows in the weight ring (their D columns 32..63 are never read) -- still faster than SS N=32.
+// (chunk, tap, k-step) outer / M-tile inner.
 //
-// Persistent CTAs (one per SM, static round-robin over work tiles), warp roles (224 threads):
+// Tap grouping.  N=64 is wider than Cout=32 / Cout=3, so horizontally adjacent taps share one MMA: the weights of
+// (ky,0),(ky,1)[,(ky,2)] are stacked along N and run with the A window of (ky,0).  Column group g of the accumulator
+// row of position q then holds tap (ky,g)'s contribution to the output at q - g; since the 32 lanes of an epilogue warp
+// are the 32 consecutive positions of one tile row, the epilogue fetches it with one warp shuffle:
+//     out[q] = D[q][grp 0] + shfl_down(D[.][grp 1], 1) + shfl_down(D[.][grp 2], 2).
+// Cout=32: 6 MMAs per k-step instead of 9 (pair + single with a zero upper half); Cout=3: 3 instead of 9; Cout=64: 9.
+//
+// Persistent CTAs (one per SM, static round-robin over work tiles), warp roles (352 threads):
 //   warp 0 = TMA producer for A (2 stages x 72 KB), warp 2 = bulk-copy producer for the weight ring (8 x 8 KB),
 //   warp 1 = MMA issuer (whole warp runs the uniform loop, one elected lane issues) + TMEM alloc,
-//   warps 3..6 = epilogue (TMEM -> registers -> global); TMEM holds two accumulator sets (2 x 4 x 64 columns) so the
-//   epilogue of work tile i overlaps the MMAs of tile i+1.
+//   warps 3..10 = epilogue (TMEM -> registers -> global), two warps per TMEM lane quarter; TMEM holds two accumulator
+//   sets (2 x 4 x 64 columns) so the epilogue of work tile i overlaps the MMAs of tile i+1.
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -46,8 +52,9 @@ constexpr int NA = 2;             // A stages
 constexpr int A_BYTES = (BH + 2) * P * 128;
 constexpr int A_STAGE = A_BYTES + 1024;  // taps of the last (garbage) positions read up to 2 rows past the box
 constexpr int NB = 8;                    // weight ring slots
-constexpr int B_SLOT = NMMA * 128;       // 8 KB: one (chunk, tap) slab [<=64][64] fp16
-constexpr int NTHREADS = 224;
+constexpr int B_SLOT = NMMA * 128;       // 8 KB: one weight slab [64][64] fp16
+constexpr int NEPI = 8;                  // epilogue warps
+constexpr int NTHREADS = (3 + NEPI) * 32;
 constexpr int ACC_COLS = MT * NMMA;      // 256 TMEM columns per accumulator set
 constexpr int TMEM_COLS = 2 * ACC_COLS;  // 512
 constexpr int SMEM_BYTES = 1024 /*align*/ + NA * A_STAGE + NB * B_SLOT + 256 /*barriers*/;
@@ -80,17 +87,32 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b)
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// NREAL = Cout rounded up to 16/32/64: rows of a weight slab actually stored / columns the epilogue reads
-template <int NREAL>
+__device__ __forceinline__ void store_h32(__half* dst, const float (&f)[32])
+{
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j8 = 0; j8 < 4; j8++) {
+        uint4 o;
+        o.x = pack_h2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
+        o.y = pack_h2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
+        o.z = pack_h2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
+        o.w = pack_h2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
+        d[j8] = o;
+    }
+}
+
+// NREAL = Cout rounded up to 16/32/64 (selects the tap grouping), MODE = ConvMode (epilogue)
+template <int NREAL, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
 {
-    constexpr int B_SLAB = NREAL * 128;
+    constexpr int NTAPS = NREAL == 64 ? 9 : (NREAL == 32 ? 6 : 3);  // MMA "taps" per k-step (see header)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smA = smem;
     uint8_t* smB = smem + NA * A_STAGE;
     Bars* bars = reinterpret_cast<Bars*>(smB + NB * B_SLOT);
+    __shared__ float s_bias[64];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = (a.cin + 63) >> 6;
@@ -101,12 +123,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
     if (threadIdx.x == 0) {
         for (int i = 0; i < NA; i++) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
         for (int i = 0; i < NB; i++) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], NEPI); }
         mbar_fence_init();
         tma_prefetch_desc(&tmap);
     }
-    __shared__ float s_bias[64];
     if (threadIdx.x >= 64 && threadIdx.x < 64 + NREAL) s_bias[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
+    // The rows behind each A box are read (times zero weights, or into positions that are never stored) by the taps of the
+    // last two positions; with tap grouping such a product lands in a column group that a VALID neighbour adds, so the
+    // bytes must be finite: zero them once (TMA never writes there).
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + NA * 64) {
+        const int i = threadIdx.x - 128;
+        reinterpret_cast<uint4*>(smA + (i >> 6) * A_STAGE + A_BYTES)[i & 63] = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 1) tmem_alloc(&bars->tmem_ptr, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
@@ -133,15 +162,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
         // ---------------- weight producer ----------------
         const bool leader = elect_one();
         const uint8_t* w = reinterpret_cast<const uint8_t*>(a.wpk);
-        const int nit = nchunk * 9;
+        const int nit = nchunk * NTAPS;
         int cb = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             for (int it = 0; it < nit; it++, cb++) {
                 const int s = cb % NB;
                 mbar_wait(&bars->b_empty[s], ((cb / NB) & 1) ^ 1);
                 if (leader) {
-                    mbar_expect_tx(&bars->b_full[s], B_SLAB);
-                    bulk_load(smB + s * B_SLOT, w + (size_t)it * B_SLAB, B_SLAB, &bars->b_full[s]);
+                    mbar_expect_tx(&bars->b_full[s], B_SLOT);
+                    bulk_load(smB + s * B_SLOT, w + (size_t)it * B_SLOT, B_SLOT, &bars->b_full[s]);
                 }
             }
         }
@@ -163,11 +192,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                 const int rem = a.cin - c * 64;
                 const int ksteps = rem >= 64 ? 4 : (rem >> 4);
                 const uint32_t a_base = smem_u32(smA + sA * A_STAGE);
-                for (int tap = 0; tap < 9; tap++, cb++) {
+                for (int tap = 0; tap < NTAPS; tap++, cb++) {
                     const int sB = cb % NB;
                     mbar_wait(&bars->b_full[sB], (cb / NB) & 1);
                     tc_fence_after();
-                    const int ky = tap / 3, kx = tap - ky * 3;
+                    // A window of the (first) tap of this group
+                    const int ky = NREAL == 64 ? tap / 3 : (NREAL == 32 ? (tap >> 1) : tap);
+                    const int kx = NREAL == 64 ? tap - (tap / 3) * 3 : (NREAL == 32 ? (tap & 1) * 2 : 0);
                     const uint64_t db0 = desc_hi | (uint64_t)((smem_u32(smB + sB * B_SLOT) & 0x3FFFFu) >> 4);
                     const uint64_t da0 = desc_hi | (uint64_t)(((a_base + (uint32_t)(ky * P + kx) * 128u) & 0x3FFFFu) >> 4);
 #pragma unroll
@@ -189,37 +220,63 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
             if (leader) umma_commit(&bars->acc_full[buf]);
         }
     } else {
-        // ---------------- epilogue: warps 3..6, TMEM lane quarter = warp % 4 ----------------
+        // ---------------- epilogue: warps 3..10; TMEM lane quarter = warp % 4; M-tiles {half, half+2} ----------------
         const int q4 = warp & 3;
+        const int half = (warp - 3) >> 2;
         int ti = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ti++) {
             const int b = t / tiles_per_img, rem = t - b * tiles_per_img;
             const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
             const int x0 = tx * BW, y0 = ty * BH;
             const int buf = ti & 1;
+            // per-position geometry of this thread's two M-tiles
+            bool valid[2];
+            size_t pix[2];
+            int yy[2];
+            const int x = x0 + lane;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int mt = half + 2 * i;
+                yy[i] = y0 + mt * 4 + q4;
+                valid[i] = (lane < BW) && (x < a.W) && (yy[i] < a.H);
+                pix[i] = ((size_t)b * a.H + yy[i]) * a.W + x;
+            }
+            // residual-stream operands do not depend on the accumulators: fetch the first M-tile's before waiting for the
+            // MMAs, the second M-tile's while the first is processed (register budget: 64 floats in flight per thread)
+            float4 res[2][8];  // [nb][j4]; only MODE RDB_OUT / TRUNK use it (dead otherwise)
+            auto load_res = [&](int i, int nb) {
+                if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
+                    if (valid[i]) {
+                        const float4* p = reinterpret_cast<const float4*>((MODE == CONV_RDB_OUT ? a.t32 : a.f32) + pix[i] * 64 + nb * 32);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; j4++) res[nb][j4] = p[j4];
+                    }
+                }
+            };
+            load_res(0, 0);
+            load_res(0, 1);
             mbar_wait(&bars->acc_full[buf], (ti >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int mt = 0; mt < MT; mt++) {
-                const int q = mt * 128 + q4 * 32 + lane;
-                const int r = q / P, cp = q - r * P;
-                const int y = y0 + r, x = x0 + cp;
-                const bool valid = (cp < BW) && (x < a.W) && (y < a.H);
-                const size_t pix = ((size_t)b * a.H + y) * a.W + x;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int mt = half + 2 * i;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS + mt * NMMA;
                 if constexpr (NREAL == 16) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr, v);
+                    uint32_t v[32], u[16];
+                    tmem_ld32(taddr, v);
+                    tmem_ld16(taddr + 32, u);
                     tmem_ld_wait();
-                    if (valid) {
-                        const TileDesc td = a.tiles[b];
-                        float o[3];
+                    float o[3];
 #pragma unroll
-                        for (int j = 0; j < 3; j++) o[j] = __uint_as_float(v[j]) + s_bias[j];
-                        if (a.mode == CONV_LAST_U8) {
-                            const int i = y - a.prepad_s, jx = x - a.prepad_s;
-                            if (i >= 0 && i < td.crop_h && jx >= 0 && jx < td.crop_w) {
-                                uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + i) * a.img_w + td.out_x0 + jx) * 3;
+                    for (int j = 0; j < 3; j++)
+                        o[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 1) +
+                               __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 2) + s_bias[j];
+                    if (valid[i]) {
+                        const TileDesc td = a.tiles[b];
+                        if constexpr (MODE == CONV_LAST_U8) {
+                            const int ii = yy[i] - a.prepad_s, jx = x - a.prepad_s;
+                            if (ii >= 0 && ii < td.crop_h && jx >= 0 && jx < td.crop_w) {
+                                uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + ii) * a.img_w + td.out_x0 + jx) * 3;
 #pragma unroll
                                 for (int j = 0; j < 3; j++) {
                                     int iv = (int)(o[j] * 255.f + 0.5f);
@@ -227,46 +284,50 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                                 }
                             }
                         } else {
-                            float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)a.H * a.W) + (size_t)y * a.W + x;
+                            float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)a.H * a.W) + (size_t)yy[i] * a.W + x;
                             *dst = make_float4(o[0], o[1], o[2], 0.f);
                         }
                     }
+                } else if constexpr (NREAL == 32) {
+                    uint32_t v[32], u[32];
+                    tmem_ld32(taddr, v);
+                    tmem_ld32(taddr + 32, u);
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        f[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) + s_bias[j];
+                        if (a.act == 2) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+                    }
+                    if (valid[i]) store_h32(a.out16 + pix[i] * a.out_cs + a.out_co, f);
                 } else {
-#pragma unroll 1
-                    for (int nb = 0; nb < NREAL / 32; nb++) {
+#pragma unroll
+                    for (int nb = 0; nb < 2; nb++) {
                         uint32_t v[32];
                         tmem_ld32(taddr + nb * 32, v);
                         tmem_ld_wait();
-                        if (valid) {
-                            float f[32];
+                        float f[32];
 #pragma unroll
-                            for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]) + s_bias[nb * 32 + j];
-                            if (a.mode == CONV_STORE16) {
-                                if (a.act == 2) {
+                        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]) + s_bias[nb * 32 + j];
+                        if constexpr (MODE == CONV_STORE16) {
+                            if (a.act == 2) {
 #pragma unroll
-                                    for (int j = 0; j < 32; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
-                                }
-                            } else if (a.mode == CONV_RDB_OUT) {
-                                // All loads first, then math, then stores: t32/r32/out16 may alias as far as the compiler
-                                // knows, and interleaving made every load wait for the previous store (measured: this
-                                // epilogue was 10x the MMA time).
-                                float4* tp = reinterpret_cast<float4*>(a.t32 + pix * 64 + nb * 32);
-                                float4* rp = reinterpret_cast<float4*>(a.r32 + pix * 64 + nb * 32);
-                                float4 tt[8], rr[8];
+                                for (int j = 0; j < 32; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+                            }
+                        } else if constexpr (MODE == CONV_RDB_OUT) {
 #pragma unroll
-                                for (int j4 = 0; j4 < 8; j4++) tt[j4] = tp[j4];
+                            for (int j4 = 0; j4 < 8; j4++) {
+                                f[j4 * 4 + 0] = f[j4 * 4 + 0] * 0.2f + res[nb][j4].x;
+                                f[j4 * 4 + 1] = f[j4 * 4 + 1] * 0.2f + res[nb][j4].y;
+                                f[j4 * 4 + 2] = f[j4 * 4 + 2] * 0.2f + res[nb][j4].z;
+                                f[j4 * 4 + 3] = f[j4 * 4 + 3] * 0.2f + res[nb][j4].w;
+                            }
+                            if (valid[i]) {
                                 if (a.rrdb_end) {
+                                    float4* rp = reinterpret_cast<float4*>(a.r32 + pix[i] * 64 + nb * 32);
+                                    float4 rr[8];
 #pragma unroll
                                     for (int j4 = 0; j4 < 8; j4++) rr[j4] = rp[j4];
-                                }
-#pragma unroll
-                                for (int j4 = 0; j4 < 8; j4++) {
-                                    f[j4 * 4 + 0] = f[j4 * 4 + 0] * 0.2f + tt[j4].x;
-                                    f[j4 * 4 + 1] = f[j4 * 4 + 1] * 0.2f + tt[j4].y;
-                                    f[j4 * 4 + 2] = f[j4 * 4 + 2] * 0.2f + tt[j4].z;
-                                    f[j4 * 4 + 3] = f[j4 * 4 + 3] * 0.2f + tt[j4].w;
-                                }
-                                if (a.rrdb_end) {
 #pragma unroll
                                     for (int j4 = 0; j4 < 8; j4++) {
                                         f[j4 * 4 + 0] = f[j4 * 4 + 0] * 0.2f + rr[j4].x;
@@ -277,33 +338,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
 #pragma unroll
                                     for (int j4 = 0; j4 < 8; j4++) rp[j4] = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
                                 }
+                                float4* tp = reinterpret_cast<float4*>(a.t32 + pix[i] * 64 + nb * 32);
 #pragma unroll
                                 for (int j4 = 0; j4 < 8; j4++) tp[j4] = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
-                            } else {  // CONV_TRUNK
-                                const float4* fp = reinterpret_cast<const float4*>(a.f32 + pix * 64 + nb * 32);
-                                float4 tt[8];
-#pragma unroll
-                                for (int j4 = 0; j4 < 8; j4++) tt[j4] = __ldg(fp + j4);
-#pragma unroll
-                                for (int j4 = 0; j4 < 8; j4++) {
-                                    f[j4 * 4 + 0] += tt[j4].x; f[j4 * 4 + 1] += tt[j4].y; f[j4 * 4 + 2] += tt[j4].z; f[j4 * 4 + 3] += tt[j4].w;
-                                }
                             }
-                            uint4* dst = reinterpret_cast<uint4*>(a.out16 + pix * a.out_cs + a.out_co + nb * 32);
+                        } else {  // CONV_TRUNK
 #pragma unroll
-                            for (int j8 = 0; j8 < 4; j8++) {
-                                uint4 o;
-                                o.x = pack_h2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
-                                o.y = pack_h2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
-                                o.z = pack_h2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
-                                o.w = pack_h2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-                                dst[j8] = o;
+                            for (int j4 = 0; j4 < 8; j4++) {
+                                f[j4 * 4 + 0] += res[nb][j4].x; f[j4 * 4 + 1] += res[nb][j4].y;
+                                f[j4 * 4 + 2] += res[nb][j4].z; f[j4 * 4 + 3] += res[nb][j4].w;
                             }
                         }
+                        if (valid[i]) store_h32(a.out16 + pix[i] * a.out_cs + a.out_co + nb * 32, f);
+                        if (i == 0) load_res(1, nb);
                     }
                 }
             }
-            // this warp has drained its quarter of the accumulator set: hand it back to the MMA issuer
+            // this warp has drained its part of the accumulator set: hand it back to the MMA issuer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
@@ -315,8 +366,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int NREAL>
-cudaError_t launch_n(const CUtensorMap* in_map, const ConvArgs& a, cudaStream_t stream)
+template <int NREAL, int MODE>
+cudaError_t launch_nm(const CUtensorMap* in_map, const ConvArgs& a, cudaStream_t stream)
 {
     static bool attr_done[64] = {};  // per device: function attributes live in the device's context
     static int num_sms[64] = {};
@@ -325,14 +376,14 @@ cudaError_t launch_n(const CUtensorMap* in_map, const ConvArgs& a, cudaStream_t 
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     dev &= 63;
     if (!attr_done[dev]) {
-        e = cudaFuncSetAttribute(conv3x3_tc_kernel<NREAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        e = cudaFuncSetAttribute(conv3x3_tc_kernel<NREAL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         attr_done[dev] = true;
     }
     const long long ntiles = (long long)((a.W + BW - 1) / BW) * ((a.H + BH - 1) / BH) * a.B;
     const int grid = (int)(ntiles < num_sms[dev] ? ntiles : num_sms[dev]);
-    conv3x3_tc_kernel<NREAL><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*in_map, a);
+    conv3x3_tc_kernel<NREAL, MODE><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*in_map, a);
     return cudaGetLastError();
 }
 
@@ -340,12 +391,13 @@ cudaError_t launch_n(const CUtensorMap* in_map, const ConvArgs& a, cudaStream_t 
 
 cudaError_t launch_conv3x3_tc(const CUtensorMap* in_map, const ConvArgs& a, int cout_pad, cudaStream_t stream)
 {
-    switch (cout_pad) {
-    case 16: return launch_n<16>(in_map, a, stream);
-    case 32: return launch_n<32>(in_map, a, stream);
-    case 64: return launch_n<64>(in_map, a, stream);
-    default: return cudaErrorInvalidValue;
-    }
+    if (cout_pad == 32 && a.mode == CONV_STORE16) return launch_nm<32, CONV_STORE16>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_STORE16) return launch_nm<64, CONV_STORE16>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_RDB_OUT) return launch_nm<64, CONV_RDB_OUT>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_TRUNK) return launch_nm<64, CONV_TRUNK>(in_map, a, stream);
+    if (cout_pad == 16 && a.mode == CONV_LAST_U8) return launch_nm<16, CONV_LAST_U8>(in_map, a, stream);
+    if (cout_pad == 16 && a.mode == CONV_LAST_F32) return launch_nm<16, CONV_LAST_F32>(in_map, a, stream);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace rsr

@@ -47,6 +47,7 @@ int load_model(const std::string& parampath, const std::string& binpath, Model& 
 // Packs one conv's fp16 weights into the swizzled shared-memory image the tensor-core kernel streams:
 // [chunk = ceil(cin/64)][tap = 9][n = cout_pad][k = 64] fp16, each [n][64] slab laid out as a K-major SWIZZLE_128B
 // UMMA operand (row n at n*128 B, 16-B chunk j of the row stored at chunk j ^ (n & 7)).  Missing channels / rows = 0.
+// cout_pad == 32 uses the tap-paired layout instead: [chunk][ky = 3][half = 2][64 rows][64] (see model.cpp).
 void pack_conv_weights(const ConvLayer& c, int cout_pad, std::vector<uint16_t>& out);
 
 }  // namespace rsr

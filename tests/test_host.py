@@ -76,22 +76,36 @@ def test_weight_packing_matches_numpy(models_dir):
         n = lib.rsr_debug_pack(p.encode(), b.encode(), idx, ctypes.byref(cin), ctypes.byref(cout), ctypes.byref(npad), None, ctypes.c_longlong(0))
         assert (cin.value, cout.value) == (c["cin"], c["cout"])
         nchunk = (c["cin"] + 63) // 64
-        assert n == nchunk * 9 * npad.value * 64
+        paired = npad.value == 32  # Cout <= 32: [chunk][ky][half][64 rows][64], taps (ky,0)+(ky,1) stacked, (ky,2)+zeros
+        tripled = npad.value == 16  # Cout <= 16: [chunk][ky][64 rows][64], rows 16*kx + n
+        nslab, nrow = (6, 64) if paired else ((3, 64) if tripled else (9, npad.value))
+        assert n == nchunk * nslab * nrow * 64
         buf = np.zeros(n, dtype=np.uint16)
         assert lib.rsr_debug_pack(p.encode(), b.encode(), idx, None, None, None, buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(n)) == n
-        ref = np.zeros((nchunk, 9, npad.value, 64), dtype=np.float16)
+        ref = np.zeros((nchunk, nslab, nrow, 64), dtype=np.float16)
         w = c["w"].reshape(c["cout"], c["cin"], 9)
         for ch in range(nchunk):
             k = min(64, c["cin"] - ch * 64)
-            blk = np.zeros((9, npad.value, 64), dtype=np.float16)
-            blk[:, :c["cout"], :k] = np.transpose(w[:, ch * 64:ch * 64 + k, :], (2, 0, 1))
+            blk = np.zeros((nslab, nrow, 64), dtype=np.float16)
+            wt = np.transpose(w[:, ch * 64:ch * 64 + k, :], (2, 0, 1))  # [tap][cout][k]
+            if paired:
+                for ky in range(3):
+                    blk[ky * 2, 0:c["cout"], :k] = wt[ky * 3 + 0]
+                    blk[ky * 2, 32:32 + c["cout"], :k] = wt[ky * 3 + 1]
+                    blk[ky * 2 + 1, 0:c["cout"], :k] = wt[ky * 3 + 2]
+            elif tripled:
+                for ky in range(3):
+                    for kx in range(3):
+                        blk[ky, 16 * kx:16 * kx + c["cout"], :k] = wt[ky * 3 + kx]
+            else:
+                blk[:, :c["cout"], :k] = wt
             # swizzle: 16-byte chunk j of row n goes to chunk j ^ (n & 7)
-            blk = blk.reshape(9, npad.value, 8, 8)
+            blk = blk.reshape(nslab, nrow, 8, 8)
             sw = np.zeros_like(blk)
-            for nrow in range(npad.value):
+            for r in range(nrow):
                 for j in range(8):
-                    sw[:, nrow, j ^ (nrow & 7)] = blk[:, nrow, j]
-            ref[ch] = sw.reshape(9, npad.value, 64)
+                    sw[:, r, j ^ (r & 7)] = blk[:, r, j]
+            ref[ch] = sw.reshape(nslab, nrow, 64)
         assert np.array_equal(buf.view(np.float16).reshape(ref.shape).view(np.uint16), ref.view(np.uint16))
 
 

@@ -44,6 +44,17 @@ UMMA_VARIANT(umma_ws_fill, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0:
 UMMA_VARIANT(umma_ws_use, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::use")
 UMMA_VARIANT(umma_ws_last, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse")
 UMMA_VARIANT(umma_ws_discard, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::discard")
+UMMA_VARIANT(umma_ws1_fill, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b1::fill")
+UMMA_VARIANT(umma_ws1_use, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b1::use")
+UMMA_VARIANT(umma_ws1_last, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b1::lastuse")
+UMMA_VARIANT(umma_ws2_fill, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b2::fill")
+UMMA_VARIANT(umma_ws2_use, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b2::use")
+UMMA_VARIANT(umma_ws2_last, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b2::lastuse")
+UMMA_VARIANT(umma_ws3_fill, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b3::fill")
+UMMA_VARIANT(umma_ws3_use, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b3::use")
+UMMA_VARIANT(umma_ws3_last, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b3::lastuse")
+// mode 6: like mode 4 but successive groups rotate through collector buffers b0..b3
+// mode 7: like mode 4 with groups of 8 M-tiles sharing B (fill, use x6, lastuse)
 
 // mode 3: groups of 4 MMAs share A (A_KEEP then A_REUSE), B differs; mode 4: .ws, groups of 4 share B (fill, use x3), A differs;
 // mode 5: .ws, every MMA discards (no reuse)
@@ -93,6 +104,26 @@ __global__ void __launch_bounds__(128, 1) mma_bench(int iters, int mode, int nac
                             if (ks == 0) umma_ws_fill(dd, dam, db0 + (tap & 3) * 2, idesc, 1);
                             else if (ks == 3) umma_ws_last(dd, dam, db0 + (tap & 3) * 2, idesc, 1);
                             else umma_ws_use(dd, dam, db0 + (tap & 3) * 2, idesc, 1);
+                        } else if (mode == 6) {
+                            const uint64_t dam = da0 + (uint64_t)(ks * 16384 >> 4);
+                            const uint32_t dd = tm + ks * N % 512;
+                            const uint64_t dbb = db0 + (tap & 3) * 2;
+                            switch (tap & 3) {
+                            case 0: if (ks == 0) umma_ws_fill(dd, dam, dbb, idesc, 1); else if (ks == 3) umma_ws_last(dd, dam, dbb, idesc, 1); else umma_ws_use(dd, dam, dbb, idesc, 1); break;
+                            case 1: if (ks == 0) umma_ws1_fill(dd, dam, dbb, idesc, 1); else if (ks == 3) umma_ws1_last(dd, dam, dbb, idesc, 1); else umma_ws1_use(dd, dam, dbb, idesc, 1); break;
+                            case 2: if (ks == 0) umma_ws2_fill(dd, dam, dbb, idesc, 1); else if (ks == 3) umma_ws2_last(dd, dam, dbb, idesc, 1); else umma_ws2_use(dd, dam, dbb, idesc, 1); break;
+                            default: if (ks == 0) umma_ws3_fill(dd, dam, dbb, idesc, 1); else if (ks == 3) umma_ws3_last(dd, dam, dbb, idesc, 1); else umma_ws3_use(dd, dam, dbb, idesc, 1); break;
+                            }
+                        } else if (mode == 7) {
+                            // 8 MMAs per B: (tap even, ks 0..3) then (tap odd, ks 0..3) share the B of the even tap
+                            const int g = (tap & 1) * 4 + ks;
+                            const uint64_t dam = da0 + (uint64_t)((g & 3) * 16384 >> 4) + (g >> 2) * 8;
+                            const uint32_t dd = tm + (g * N) % 512;
+                            const uint64_t dbb = db0 + ((tap >> 1) & 3) * 2;
+                            if (tap == 8) umma_ws_discard(dd, dam, dbb, idesc, 1);
+                            else if (g == 0) umma_ws_fill(dd, dam, dbb, idesc, 1);
+                            else if (g == 7) umma_ws_last(dd, dam, dbb, idesc, 1);
+                            else umma_ws_use(dd, dam, dbb, idesc, 1);
                         } else if (mode == 5) umma_ws_discard(d, da + ks * 2, db0 + ks * 2, idesc, 1);
                         else umma_f16(d, da + ks * 2, db0 + ks * 2, idesc, 1);
                     }
@@ -213,11 +244,13 @@ int main()
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, 0));
     printf("%s, %d SMs, clock %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
-    for (int mode = 4; mode < 6; mode++) {
+    for (int mode = 6; mode < 8; mode++) {
         run_mma<64>(mode, 1);
         run_mma<128>(mode, 1);
-        run_mma<256>(mode, 1);
     }
+    run_mma<96>(4, 1);
+    run_mma<96>(6, 1);
+    run_mma<192>(4, 1);
 
     return 0;
 }
