@@ -51,19 +51,20 @@ constexpr int NMMA = 64;          // N of every MMA
 constexpr int NA = 2;             // A stages
 constexpr int A_BYTES = (BH + 2) * P * 128;
 constexpr int A_STAGE = A_BYTES + 1024;  // taps of the last (garbage) positions read up to 2 rows past the box
-constexpr int NB = 8;                    // weight ring slots
-constexpr int B_SLOT = NMMA * 128;       // 8 KB: one weight slab [64][64] fp16
 constexpr int NEPI = 8;                  // epilogue warps
+constexpr int NB = 7;                    // weight ring slots
+constexpr int B_SLOT = NMMA * 128;       // 8 KB: one weight slab [64][64] fp16
 constexpr int NTHREADS = (3 + NEPI) * 32;
 constexpr int ACC_COLS = MT * NMMA;      // 256 TMEM columns per accumulator set
 constexpr int TMEM_COLS = 2 * ACC_COLS;  // 512
-constexpr int SMEM_BYTES = 1024 /*align*/ + NA * A_STAGE + NB * B_SLOT + 256 /*barriers*/;
+constexpr int STAGE_BYTES = 32 * 20 * 4;  // per epilogue warp: 32 rows x (16 + 4 pad) words transpose tile
+constexpr int SMEM_BYTES = 1024 /*align*/ + NA * A_STAGE + NB * B_SLOT + NEPI * STAGE_BYTES + 256 /*barriers*/;
 static_assert(MT == 4, "collector usage below assumes 4 M-tiles");
 static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 
 struct Bars {
     uint64_t a_full[NA], a_empty[NA];
-    uint64_t b_full[NB], b_empty[NB];
+    uint64_t b_full[8], b_empty[8];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_ptr;
 };
@@ -87,32 +88,19 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b)
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__device__ __forceinline__ void store_h32(__half* dst, const float (&f)[32])
-{
-    uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-    for (int j8 = 0; j8 < 4; j8++) {
-        uint4 o;
-        o.x = pack_h2(f[j8 * 8 + 0], f[j8 * 8 + 1]);
-        o.y = pack_h2(f[j8 * 8 + 2], f[j8 * 8 + 3]);
-        o.z = pack_h2(f[j8 * 8 + 4], f[j8 * 8 + 5]);
-        o.w = pack_h2(f[j8 * 8 + 6], f[j8 * 8 + 7]);
-        d[j8] = o;
-    }
-}
-
 // NREAL = Cout rounded up to 16/32/64 (selects the tap grouping), MODE = ConvMode (epilogue)
 template <int NREAL, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
+conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
 {
     constexpr int NTAPS = NREAL == 64 ? 9 : (NREAL == 32 ? 6 : 3);  // MMA "taps" per k-step (see header)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smA = smem;
     uint8_t* smB = smem + NA * A_STAGE;
-    Bars* bars = reinterpret_cast<Bars*>(smB + NB * B_SLOT);
-    __shared__ float s_bias[64];
+    uint8_t* smStage = smB + NB * B_SLOT;
+    Bars* bars = reinterpret_cast<Bars*>(smStage + NEPI * STAGE_BYTES);
+    __shared__ __align__(16) float s_bias[64];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = (a.cin + 63) >> 6;
@@ -125,7 +113,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
         for (int i = 0; i < NB; i++) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
         for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], NEPI); }
         mbar_fence_init();
-        tma_prefetch_desc(&tmap);
+        for (int i = 0; i < 3; i++) tma_prefetch_desc(&maps.m[i]);
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + NREAL) s_bias[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
     // The rows behind each A box are read (times zero weights, or into positions that are never stored) by the taps of the
@@ -153,8 +141,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                 const int s = ca % NA;
                 mbar_wait(&bars->a_empty[s], ((ca / NA) & 1) ^ 1);
                 if (leader) {
-                    mbar_expect_tx(&bars->a_full[s], A_BYTES);
-                    tma_load_4d(smA + s * A_STAGE, &tmap, &bars->a_full[s], c * 64, tx * BW - 1, ty * BH - 1, b);
+                    if (a.desc_mode & 2) {  // timing experiment: no A traffic
+                        mbar_arrive(&bars->a_full[s]);
+                    } else {
+                        mbar_expect_tx(&bars->a_full[s], A_BYTES);
+                        tma_load_4d(smA + s * A_STAGE, &maps.m[c], &bars->a_full[s], 0, tx * BW - 1, ty * BH - 1, b);
+                    }
                 }
             }
         }
@@ -169,8 +161,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                 const int s = cb % NB;
                 mbar_wait(&bars->b_empty[s], ((cb / NB) & 1) ^ 1);
                 if (leader) {
-                    mbar_expect_tx(&bars->b_full[s], B_SLOT);
-                    bulk_load(smB + s * B_SLOT, w + (size_t)it * B_SLOT, B_SLOT, &bars->b_full[s]);
+                    if (a.desc_mode & 4) {  // timing experiment: no weight traffic
+                        mbar_arrive(&bars->b_full[s]);
+                    } else {
+                        mbar_expect_tx(&bars->b_full[s], B_SLOT);
+                        bulk_load(smB + s * B_SLOT, w + (size_t)it * B_SLOT, B_SLOT, &bars->b_full[s]);
+                    }
                 }
             }
         }
@@ -203,7 +199,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                     const uint64_t da0 = desc_hi | (uint64_t)(((a_base + (uint32_t)(ky * P + kx) * 128u) & 0x3FFFFu) >> 4);
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++) {
-                        if (ks < ksteps && leader) {
+                        if (ks < ksteps && leader && !(a.desc_mode & 1)) {
                             const uint32_t accum = (c | tap | ks) ? 1u : 0u;
                             const uint64_t db = db0 + ks * 2;
                             // M-tile mt starts 128 rows = 16 KB further: +1024 in descriptor units of 16 B
@@ -221,45 +217,54 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
         }
     } else {
         // ---------------- epilogue: warps 3..10; TMEM lane quarter = warp % 4; M-tiles {half, half+2} ----------------
+        // TMEM hands every lane one POSITION (32 accumulator columns of one pixel).  Storing that directly makes each
+        // warp-wide access touch 32 different lines with 16 B each (the LSU retires ~1 line per clock: measured, this
+        // epilogue alone cost 81 ms of a 141 ms step).  So every 32x16-word block goes through a private smem staging
+        // tile and comes back "transposed": 4 consecutive lanes hold 64 contiguous bytes of one pixel, a warp-wide
+        // access covers 8 pixels x 64 B.
         const int q4 = warp & 3;
-        const int half = (warp - 3) >> 2;
+        const int ew = warp - 3;
+        const int half = ew >> 2;
+        uint32_t* stg = reinterpret_cast<uint32_t*>(smStage + ew * STAGE_BYTES);  // [32 rows][20 words]
+        const int tr = lane >> 2, tc = lane & 3;  // transposed domain: row (position) offset, 16-B chunk
+        const bool dbg_noepi = (a.desc_mode & 8) != 0;  // timing experiment: drain TMEM only
         int ti = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ti++) {
             const int b = t / tiles_per_img, rem = t - b * tiles_per_img;
             const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
             const int x0 = tx * BW, y0 = ty * BH;
             const int buf = ti & 1;
-            // per-position geometry of this thread's two M-tiles
-            bool valid[2];
-            size_t pix[2];
+            // transposed-domain validity of the 4 positions (tr + 8r) this lane stores, per M-tile row
+            bool vcol[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < a.W) && !dbg_noepi;
             int yy[2];
-            const int x = x0 + lane;
+            size_t rowpix[2];  // pixel index of position 0 of the row
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-                const int mt = half + 2 * i;
-                yy[i] = y0 + mt * 4 + q4;
-                valid[i] = (lane < BW) && (x < a.W) && (yy[i] < a.H);
-                pix[i] = ((size_t)b * a.H + yy[i]) * a.W + x;
+                yy[i] = y0 + (half + 2 * i) * 4 + q4;
+                rowpix[i] = ((size_t)b * a.H + yy[i]) * a.W + x0;
             }
-            // residual-stream operands do not depend on the accumulators: fetch the first M-tile's before waiting for the
-            // MMAs, the second M-tile's while the first is processed (register budget: 64 floats in flight per thread)
-            float4 res[2][8];  // [nb][j4]; only MODE RDB_OUT / TRUNK use it (dead otherwise)
+            // residual-stream operands (fp32, 64 ch per pixel) in the transposed domain: [hf][r] = 4 channels of position
+            // tr+8r; fetched one (M-tile, 32-channel block) ahead of use -- they do not depend on the accumulators
+            float4 res[2][4];
             auto load_res = [&](int i, int nb) {
                 if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
-                    if (valid[i]) {
-                        const float4* p = reinterpret_cast<const float4*>((MODE == CONV_RDB_OUT ? a.t32 : a.f32) + pix[i] * 64 + nb * 32);
+                    const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + nb * 32 + tc * 4;
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; j4++) res[nb][j4] = p[j4];
-                    }
+                    for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                        for (int r = 0; r < 4; r++)
+                            if (vcol[r] && yy[i] < a.H) res[hf][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
                 }
             };
             load_res(0, 0);
-            load_res(0, 1);
             mbar_wait(&bars->acc_full[buf], (ti >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int i = 0; i < 2; i++) {
                 const int mt = half + 2 * i;
+                const bool vrow = yy[i] < a.H;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS + mt * NMMA;
                 if constexpr (NREAL == 16) {
                     uint32_t v[32], u[16];
@@ -271,7 +276,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                     for (int j = 0; j < 3; j++)
                         o[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 1) +
                                __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 2) + s_bias[j];
-                    if (valid[i]) {
+                    const int x = x0 + lane;
+                    if (lane < BW && x < a.W && vrow && !dbg_noepi) {  // adjacent lanes write adjacent 3-byte pixels: already coalesced
                         const TileDesc td = a.tiles[b];
                         if constexpr (MODE == CONV_LAST_U8) {
                             const int ii = yy[i] - a.prepad_s, jx = x - a.prepad_s;
@@ -288,69 +294,111 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
                             *dst = make_float4(o[0], o[1], o[2], 0.f);
                         }
                     }
-                } else if constexpr (NREAL == 32) {
-                    uint32_t v[32], u[32];
-                    tmem_ld32(taddr, v);
-                    tmem_ld32(taddr + 32, u);
-                    tmem_ld_wait();
-                    float f[32];
+                } else if constexpr (MODE == CONV_STORE16) {
+                    // bias + activation + fp16 pack in the native domain, then one staged transpose per 32 channels
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        f[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) + s_bias[j];
-                        if (a.act == 2) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+                    for (int nb = 0; nb < NREAL / 32; nb++) {
+                        uint32_t v[32];
+                        tmem_ld32(taddr + nb * 32, v);
+                        float f[32];
+                        if constexpr (NREAL == 32) {
+                            uint32_t u[32];
+                            tmem_ld32(taddr + 32, u);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) + s_bias[j];
+                        } else {
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]) + s_bias[nb * 32 + j];
+                        }
+                        if (a.act == 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) =
+                                make_uint4(pack_h2(f[8 * k + 0], f[8 * k + 1]), pack_h2(f[8 * k + 2], f[8 * k + 3]),
+                                           pack_h2(f[8 * k + 4], f[8 * k + 5]), pack_h2(f[8 * k + 6], f[8 * k + 7]));
+                        __syncwarp();
+                        __half* orow = a.out16 + rowpix[i] * a.out_cs + a.out_co + nb * 32 + tc * 8;
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const uint4 o = *reinterpret_cast<const uint4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
+                            if (vcol[r] && vrow) *reinterpret_cast<uint4*>(orow + (size_t)(tr + 8 * r) * a.out_cs) = o;
+                        }
+                        __syncwarp();
                     }
-                    if (valid[i]) store_h32(a.out16 + pix[i] * a.out_cs + a.out_co, f);
                 } else {
+                    // CONV_RDB_OUT / CONV_TRUNK: fp32 math against the residual stream in the transposed domain
 #pragma unroll
                     for (int nb = 0; nb < 2; nb++) {
                         uint32_t v[32];
                         tmem_ld32(taddr + nb * 32, v);
                         tmem_ld_wait();
-                        float f[32];
+                        float4 nxt[2][4];
 #pragma unroll
-                        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]) + s_bias[nb * 32 + j];
-                        if constexpr (MODE == CONV_STORE16) {
-                            if (a.act == 2) {
+                        for (int hf = 0; hf < 2; hf++) {
 #pragma unroll
-                                for (int j = 0; j < 32; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
-                            }
-                        } else if constexpr (MODE == CONV_RDB_OUT) {
+                            for (int k = 0; k < 4; k++)
+                                *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) = make_uint4(v[16 * hf + 4 * k], v[16 * hf + 4 * k + 1], v[16 * hf + 4 * k + 2], v[16 * hf + 4 * k + 3]);
+                            __syncwarp();
+                            const int ch0 = nb * 32 + hf * 16 + tc * 4;
+                            const float4 bb = *reinterpret_cast<const float4*>(&s_bias[ch0]);
+                            float4 acc[4];
 #pragma unroll
-                            for (int j4 = 0; j4 < 8; j4++) {
-                                f[j4 * 4 + 0] = f[j4 * 4 + 0] * 0.2f + res[nb][j4].x;
-                                f[j4 * 4 + 1] = f[j4 * 4 + 1] * 0.2f + res[nb][j4].y;
-                                f[j4 * 4 + 2] = f[j4 * 4 + 2] * 0.2f + res[nb][j4].z;
-                                f[j4 * 4 + 3] = f[j4 * 4 + 3] * 0.2f + res[nb][j4].w;
-                            }
-                            if (valid[i]) {
-                                if (a.rrdb_end) {
-                                    float4* rp = reinterpret_cast<float4*>(a.r32 + pix[i] * 64 + nb * 32);
-                                    float4 rr[8];
+                            for (int r = 0; r < 4; r++) acc[r] = *reinterpret_cast<const float4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
+                            __syncwarp();
+                            if (hf == 0) {  // prefetch the residual operands of the next (M-tile, 32-channel block)
+                                const int ni = nb == 1 ? i + 1 : i, nnb = nb ^ 1;
+                                if (ni < 2) {
+                                    if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
+                                        const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[ni] * 64 + nnb * 32 + tc * 4;
 #pragma unroll
-                                    for (int j4 = 0; j4 < 8; j4++) rr[j4] = rp[j4];
+                                        for (int h2 = 0; h2 < 2; h2++)
 #pragma unroll
-                                    for (int j4 = 0; j4 < 8; j4++) {
-                                        f[j4 * 4 + 0] = f[j4 * 4 + 0] * 0.2f + rr[j4].x;
-                                        f[j4 * 4 + 1] = f[j4 * 4 + 1] * 0.2f + rr[j4].y;
-                                        f[j4 * 4 + 2] = f[j4 * 4 + 2] * 0.2f + rr[j4].z;
-                                        f[j4 * 4 + 3] = f[j4 * 4 + 3] * 0.2f + rr[j4].w;
+                                            for (int r = 0; r < 4; r++)
+                                                if (vcol[r] && yy[ni] < a.H) nxt[h2][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + h2 * 16);
                                     }
-#pragma unroll
-                                    for (int j4 = 0; j4 < 8; j4++) rp[j4] = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
                                 }
-                                float4* tp = reinterpret_cast<float4*>(a.t32 + pix[i] * 64 + nb * 32);
-#pragma unroll
-                                for (int j4 = 0; j4 < 8; j4++) tp[j4] = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
                             }
-                        } else {  // CONV_TRUNK
+                            float4 rr[4];
+                            if (MODE == CONV_RDB_OUT && a.rrdb_end) {
 #pragma unroll
-                            for (int j4 = 0; j4 < 8; j4++) {
-                                f[j4 * 4 + 0] += res[nb][j4].x; f[j4 * 4 + 1] += res[nb][j4].y;
-                                f[j4 * 4 + 2] += res[nb][j4].z; f[j4 * 4 + 3] += res[nb][j4].w;
+                                for (int r = 0; r < 4; r++)
+                                    if (vcol[r] && vrow) rr[r] = *reinterpret_cast<const float4*>(a.r32 + (rowpix[i] + tr + 8 * r) * 64 + ch0);
+                            }
+#pragma unroll
+                            for (int r = 0; r < 4; r++) {
+                                float4 o;
+                                if constexpr (MODE == CONV_RDB_OUT) {
+                                    o.x = (acc[r].x + bb.x) * 0.2f + res[hf][r].x;
+                                    o.y = (acc[r].y + bb.y) * 0.2f + res[hf][r].y;
+                                    o.z = (acc[r].z + bb.z) * 0.2f + res[hf][r].z;
+                                    o.w = (acc[r].w + bb.w) * 0.2f + res[hf][r].w;
+                                    if (a.rrdb_end) {
+                                        o.x = o.x * 0.2f + rr[r].x; o.y = o.y * 0.2f + rr[r].y;
+                                        o.z = o.z * 0.2f + rr[r].z; o.w = o.w * 0.2f + rr[r].w;
+                                    }
+                                } else {
+                                    o.x = acc[r].x + bb.x + res[hf][r].x; o.y = acc[r].y + bb.y + res[hf][r].y;
+                                    o.z = acc[r].z + bb.z + res[hf][r].z; o.w = acc[r].w + bb.w + res[hf][r].w;
+                                }
+                                if (vcol[r] && vrow) {
+                                    const size_t px = rowpix[i] + tr + 8 * r;
+                                    if constexpr (MODE == CONV_RDB_OUT) {
+                                        if (a.rrdb_end) *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0) = o;
+                                        *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o;
+                                    }
+                                    *reinterpret_cast<uint2*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                                }
                             }
                         }
-                        if (valid[i]) store_h32(a.out16 + pix[i] * a.out_cs + a.out_co + nb * 32, f);
-                        if (i == 0) load_res(1, nb);
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; h2++)
+#pragma unroll
+                            for (int r = 0; r < 4; r++) res[h2][r] = nxt[h2][r];
                     }
                 }
             }
@@ -367,7 +415,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvArgs a)
 }
 
 template <int NREAL, int MODE>
-cudaError_t launch_nm(const CUtensorMap* in_map, const ConvArgs& a, cudaStream_t stream)
+cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
 {
     static bool attr_done[64] = {};  // per device: function attributes live in the device's context
     static int num_sms[64] = {};
@@ -389,7 +437,7 @@ cudaError_t launch_nm(const CUtensorMap* in_map, const ConvArgs& a, cudaStream_t
 
 }  // namespace
 
-cudaError_t launch_conv3x3_tc(const CUtensorMap* in_map, const ConvArgs& a, int cout_pad, cudaStream_t stream)
+cudaError_t launch_conv3x3_tc(const ConvMaps* in_map, const ConvArgs& a, int cout_pad, cudaStream_t stream)
 {
     if (cout_pad == 32 && a.mode == CONV_STORE16) return launch_nm<32, CONV_STORE16>(in_map, a, stream);
     if (cout_pad == 64 && a.mode == CONV_STORE16) return launch_nm<64, CONV_STORE16>(in_map, a, stream);

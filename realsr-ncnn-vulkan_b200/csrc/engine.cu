@@ -177,7 +177,7 @@ struct BatchCtx {
     size_t nconv_ev = 0;
 };
 
-int conv(BatchCtx& c, const CUtensorMap* map, ConvArgs a, int conv_idx)
+int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
 {
     rsr_handle* h = c.h;
     const DeviceModel& dm = h->dm;
@@ -229,14 +229,18 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, uint8_t* 
     CK(cudaMemcpyAsync(ws->tiles.p, tiles.data(), sizeof(TileDesc) * (size_t)B, cudaMemcpyHostToDevice, st));
     const TileDesc* d_tiles = (const TileDesc*)ws->tiles.p;
 
+    // dense-block buffers: three 64-channel planes each (x0 | x1,x2 | x3,x4)
     __half* D[2] = {(__half*)ws->d16[0].p, (__half*)ws->d16[1].p};
-    CUtensorMap mapD[2], mapU1, mapV1, mapU2, mapV2;
-    if ((r = make_map(h, &mapD[0], D[0], 192, W, H, B))) return r;
-    if ((r = make_map(h, &mapD[1], D[1], 192, W, H, B))) return r;
-    if ((r = make_map(h, &mapU1, ws->u1.p, 64, 2 * W, 2 * H, B))) return r;
-    if ((r = make_map(h, &mapV1, ws->v1.p, 64, 2 * W, 2 * H, B))) return r;
-    if ((r = make_map(h, &mapU2, ws->u2.p, 64, 4 * W, 4 * H, B))) return r;
-    if ((r = make_map(h, &mapV2, ws->v2.p, 64, 4 * W, 4 * H, B))) return r;
+    const size_t plane = npx * 64;
+    ConvMaps mapD[2], mapU1, mapV1, mapU2, mapV2;
+    for (int i = 0; i < 2; i++)
+        for (int pl = 0; pl < 3; pl++)
+            if ((r = make_map(h, &mapD[i].m[pl], D[i] + pl * plane, 64, W, H, B))) return r;
+    if ((r = make_map(h, &mapU1.m[0], ws->u1.p, 64, 2 * W, 2 * H, B))) return r;
+    if ((r = make_map(h, &mapV1.m[0], ws->v1.p, 64, 2 * W, 2 * H, B))) return r;
+    if ((r = make_map(h, &mapU2.m[0], ws->u2.p, 64, 4 * W, 4 * H, B))) return r;
+    if ((r = make_map(h, &mapV2.m[0], ws->v2.p, 64, 4 * W, 4 * H, B))) return r;
+    for (ConvMaps* cm : {&mapU1, &mapV1, &mapU2, &mapV2}) cm->m[1] = cm->m[2] = cm->m[0];
 
     // Conv_0 + preproc
     {
@@ -255,26 +259,26 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, uint8_t* 
     int cur = 0;
     for (int rrdb = 0; rrdb < m.num_rrdb; rrdb++)
         for (int rdb = 0; rdb < 3; rdb++) {
-            for (int k = 0; k < 4; k++) {  // x_{k+1} = lrelu(conv([x0..xk])) -> channel slice 64+32k of the same buffer
+            for (int k = 0; k < 4; k++) {  // x_{k+1} = lrelu(conv([x0..xk])) -> half of plane 1 + k/2 of the same buffer
                 ConvArgs a = base;
                 a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_rdb(rrdb, rdb, k)].slope;
-                a.out16 = D[cur]; a.out_cs = 192; a.out_co = 64 + 32 * k;
+                a.out16 = D[cur] + (1 + k / 2) * plane; a.out_cs = 64; a.out_co = 32 * (k & 1);
                 if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, k)))) return r;
             }
             ConvArgs a = base;  // x5 -> residual(s) -> x0 of the next RDB in the other buffer
             a.mode = CONV_RDB_OUT; a.rrdb_end = (rdb == 2);
-            a.out16 = D[cur ^ 1]; a.out_cs = 192; a.out_co = 0;
+            a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
             if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, 4)))) return r;
             cur ^= 1;
         }
     {   // trunk conv + fea (BinaryOp ADD), result in channels 0..63 of the other dense buffer
         ConvArgs a = base;
-        a.mode = CONV_TRUNK; a.out16 = D[cur ^ 1]; a.out_cs = 192; a.out_co = 0;
+        a.mode = CONV_TRUNK; a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
         if ((r = conv(c, &mapD[cur], a, m.idx_trunk()))) return r;
         cur ^= 1;
     }
-    // nearest x2 -> conv+lrelu, twice (x4.param:996-999). The first source has 192 channels per pixel (reads 0..63).
-    CK(launch_upsample2x(D[cur], 192, (__half*)ws->u1.p, B, H, W, st));
+    // nearest x2 -> conv+lrelu, twice (x4.param:996-999); the first source is plane 0 of the dense buffer
+    CK(launch_upsample2x(D[cur], 64, (__half*)ws->u1.p, B, H, W, st));
     c.launches++;
     {
         ConvArgs a = base;
@@ -597,16 +601,23 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     __half *d_in = nullptr, *d_out = nullptr;
     float* d_f = nullptr;
     TileDesc* d_td = nullptr;
-    CK(cudaMalloc(&d_in, npx * cl.cin * 2));
+    const int nplane = (cl.cin + 63) / 64;
+    CK(cudaMalloc(&d_in, npx * nplane * 64 * 2));
     CK(cudaMalloc(&d_out, npx * 64 * 2));
     CK(cudaMalloc(&d_f, npx * 16));
     CK(cudaMalloc(&d_td, sizeof(TileDesc)));
-    CK(cudaMemcpy(d_in, in16, npx * cl.cin * 2, cudaMemcpyHostToDevice));
+    {   // [H][W][cin] -> planes [plane][H][W][64] (zero padded), the engine's dense-buffer layout
+        std::vector<uint16_t> planes(npx * nplane * 64, 0);
+        for (size_t p = 0; p < npx; p++)
+            for (int ci = 0; ci < cl.cin; ci++) planes[((size_t)(ci >> 6) * npx + p) * 64 + (ci & 63)] = in16[p * cl.cin + ci];
+        CK(cudaMemcpy(d_in, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice));
+    }
     TileDesc td{};
     CK(cudaMemcpy(d_td, &td, sizeof td, cudaMemcpyHostToDevice));
-    CUtensorMap map;
-    int r = make_map(h, &map, d_in, cl.cin, W, H, 1);
-    if (r) return r;
+    ConvMaps map;
+    int r = 0;
+    for (int pl = 0; pl < 3; pl++)
+        if ((r = make_map(h, &map.m[pl], d_in + (size_t)(pl < nplane ? pl : 0) * npx * 64, 64, W, H, 1))) return r;
     ConvArgs a{};
     a.wpk = h->dm.wpk[conv_index]; a.bias = h->dm.bias[conv_index]; a.cin = cl.cin;
     a.H = H; a.W = W; a.B = 1;

@@ -1,9 +1,11 @@
 // kernels.h -- device-side interface of the RealSR B200 engine (all launches are asynchronous on `stream`).
 //
 // Data layout in HBM (per batch of same-shape padded tiles, B tiles of H x W network-input pixels):
-//   D16[2]  fp16 [B][H][W][192]  dense-block buffer: channels 0..63 = RDB input x0, 64..191 = x1..x4 (32 each).
-//                                 Concat (ncnn layer/concat.cpp:140-175) is never materialised: conv k of an RDB
-//                                 reads channels [0, 64+32(k-1)) and writes its 32 outputs right behind them.
+//   D16[2]  fp16 [3][B][H][W][64] dense-block buffer as three 64-channel planes: plane 0 = RDB input x0, plane 1 =
+//                                 [x1,x2], plane 2 = [x3,x4].  Concat (ncnn layer/concat.cpp:140-175) is never
+//                                 materialised: conv k of an RDB reads planes 0..ceil((64+32(k-1))/64)-1 and writes its
+//                                 32 outputs into half a plane.  Planar (not 192-interleaved) so that one row of a TMA
+//                                 box is 32 px x 128 B = 4 KB contiguous in DRAM.
 //   T32     fp32 [B][H][W][64]   residual stream (RDB input, exact fp32), updated in place by conv5's epilogue
 //   R32     fp32 [B][H][W][64]   RRDB input, updated in place at every third RDB
 //   F32     fp32 [B][H][W][64]   Conv_0 output `fea` (added back after the trunk conv, x4.param:994-995)
@@ -57,8 +59,12 @@ struct ConvArgs {
     int desc_mode;       // 0: UMMA descriptor base_offset = 0 ; 1: base_offset = (addr>>7)&7
 };
 
+// one tensor map per 64-channel input plane (chunk) of a conv
+struct alignas(64) ConvMaps {
+    CUtensorMap m[3];
+};
 // conv3x3 s1 p1 as implicit GEMM on tcgen05 (conv_tc.cu). cout_pad in {16, 32, 64}.
-cudaError_t launch_conv3x3_tc(const CUtensorMap* in_map, const ConvArgs& a, int cout_pad, cudaStream_t stream);
+cudaError_t launch_conv3x3_tc(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
 // box dims the kernel expects from the tensor map: {64 ch, 32 px, CONV_BH+2 rows, 1}
 constexpr int CONV_BH = 16;
 constexpr int CONV_P = 32;
@@ -71,7 +77,7 @@ struct FirstArgs {
     const float* w;      // [64][3][3][3] fp32 (OIHW as in the .bin), bias [64]
     const float* bias;
     int H, W, B;
-    __half* d16;         // D16[0], 192 ch per pixel, writes channels 0..63
+    __half* d16;         // plane 0 of D16[0] (64 ch per pixel)
     float* t32;
     float* r32;
     float* f32;

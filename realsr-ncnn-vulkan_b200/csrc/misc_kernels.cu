@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(FIRST_THREADS) conv_first_kernel(const FirstAr
         const float4 o = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
         t[j4] = o; r[j4] = o; f[j4] = o;
     }
-    uint4* d = reinterpret_cast<uint4*>(a.d16 + pix * 192 + quarter * 16);
+    uint4* d = reinterpret_cast<uint4*>(a.d16 + pix * 64 + quarter * 16);
 #pragma unroll
     for (int j8 = 0; j8 < 2; j8++) {
         __half2 h0 = __floats2half2_rn(acc[j8 * 8 + 0], acc[j8 * 8 + 1]);
