@@ -551,7 +551,7 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
 {
     if (!h || !key) return RSR_ERR_GENERIC;
     if (!strcmp(key, "max_batch")) h->max_batch = value;
-    else if (!strcmp(key, "desc_mode")) h->desc_mode = (int)value;
+    else if (!strcmp(key, "debug_mask") || !strcmp(key, "desc_mode")) h->desc_mode = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
     else return set_err(h, RSR_ERR_GENERIC, std::string("unknown option ") + key);
     return 0;

@@ -56,7 +56,7 @@ struct ConvArgs {
     int img_w, img_h;    // output image size (pixels)
     int prepad_s;        // prepadding*scale
     float* tta_out;
-    int desc_mode;       // 0: UMMA descriptor base_offset = 0 ; 1: base_offset = (addr>>7)&7
+    int desc_mode;       // debug mask for timing experiments (0 in production): 1 no MMA, 2 no A loads, 4 no B loads, 8 no epilogue I/O
 };
 
 // one tensor map per 64-channel input plane (chunk) of a conv

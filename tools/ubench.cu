@@ -145,6 +145,103 @@ __global__ void __launch_bounds__(128, 1) mma_bench(int iters, int mode, int nac
     if (threadIdx.x < 32) tmem_dealloc(tm, 512);
 }
 
+// ---- cta_group::2: one instruction drives the tensor cores of both SMs of a CTA pair (M = 256) -----------------------------
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc),
+                 "l"(b_desc), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+template <int N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma2_bench(int iters, long long* out_cycles)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + 65536;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_ptr;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    for (int i = threadIdx.x; i < (65536 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u ^ (i * 2654435761u & 0x03ff03ffu);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const uint32_t tm = tmem_ptr;
+    if (rank == 0 && threadIdx.x < 32) {
+        const uint32_t idesc = umma_idesc_f16(256, N);
+        const uint64_t da0 = umma_desc_sw128(smem_u32(smA), 1024, 0), db0 = umma_desc_sw128(smem_u32(smB), 1024, 0);
+        const bool leader = elect_one();
+        long long t0 = clock64();
+        uint32_t phase = 0;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    if (leader) umma2_f16(tm + ((tap + ks) & 1) * N, da0 + ks * 2 + (tap % 3) * 8, db0 + ks * 2, idesc, 1);
+                }
+            }
+            if ((it & 7) == 7) {
+                if (leader)
+                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar)),
+                                 "h"((uint16_t)1)
+                                 : "memory");
+                mbar_wait(&bar, phase);
+                phase ^= 1;
+            }
+        }
+        if (leader)
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar)),
+                         "h"((uint16_t)1)
+                         : "memory");
+        mbar_wait(&bar, phase);
+        long long t1 = clock64();
+        if (leader) out_cycles[blockIdx.x / 2] = t1 - t0;
+    }
+    tc_fence_before();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u) : "memory");
+}
+
+template <int N>
+void run_mma2()
+{
+    long long* d;
+    CK(cudaMalloc(&d, 148 * 8));
+    const int smem = 1024 + 65536 + 32768;
+    CK(cudaFuncSetAttribute(mma2_bench<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int iters = 2000;
+    mma2_bench<N><<<148, 128, smem>>>(50, d);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    mma2_bench<N><<<148, 128, smem>>>(iters, d);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    long long h[74];
+    CK(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
+    double avg = 0;
+    for (int i = 0; i < 74; i++) avg += (double)h[i];
+    avg /= 74;
+    const double nmma = (double)iters * 36;
+    const double flops = nmma * 2.0 * 256 * N * 16 * 74;
+    printf("cta_group::2 M=256 N=%3d: %.2f clk/MMA (per-SM floor %d)  -> %.1f TFLOP/s chip (%.3f ms)\n", N, avg / nmma, N / 2, flops / (ms * 1e-3) / 1e12, ms);
+    cudaFree(d);
+}
+
 template <int N>
 void run_mma(int mode, int nacc)
 {
@@ -244,13 +341,10 @@ int main()
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, 0));
     printf("%s, %d SMs, clock %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
-    for (int mode = 6; mode < 8; mode++) {
-        run_mma<64>(mode, 1);
-        run_mma<128>(mode, 1);
-    }
-    run_mma<96>(4, 1);
-    run_mma<96>(6, 1);
-    run_mma<192>(4, 1);
+    run_mma2<32>();
+    run_mma2<64>();
+    run_mma2<128>();
+    run_mma2<256>();
 
     return 0;
 }
