@@ -36,6 +36,8 @@
 //   warp 1 = MMA issuer (whole warp runs the uniform loop, one elected lane issues) + TMEM alloc,
 //   warps 3..10 = epilogue (TMEM -> registers -> global), two warps per TMEM lane quarter; TMEM holds two accumulator
 //   sets (2 x 4 x 64 columns) so the epilogue of work tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -129,6 +131,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_ptr;
+    // Programmatic dependent launch: let the next conv's CTAs be scheduled onto SMs as soon as this grid's CTAs retire
+    // (they run their prologue and then block here), and wait until the previous grid has completed and flushed its
+    // outputs before touching any activation.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         // ---------------- A producer ----------------
@@ -431,7 +438,18 @@ cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t st
     }
     const long long ntiles = (long long)((a.W + BW - 1) / BW) * ((a.H + BH - 1) / BH) * a.B;
     const int grid = (int)(ntiles < num_sms[dev] ? ntiles : num_sms[dev]);
-    conv3x3_tc_kernel<NREAL, MODE><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*in_map, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const int use_pdl = getenv("RSR_NOPDL") ? 0 : 1;  // bring-up switch
+    cfg.numAttrs = use_pdl;
+    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NREAL, MODE>, *in_map, a)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

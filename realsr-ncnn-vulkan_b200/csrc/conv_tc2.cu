@@ -1,0 +1,433 @@
+// conv_tc2.cu -- the 3x3 conv as an implicit GEMM on CTA PAIRS (tcgen05 cta_group::2).
+//
+// Same algorithm, data layout and epilogues as conv_tc.cu (read its header first: haloed TMA box per 64-channel plane,
+// row-shifted UMMA descriptors instead of im2col, horizontal tap grouping resolved by warp shuffles in the epilogue,
+// smem-staged transposed stores).  What changes is the MMA: tools/ubench.cu measured that a cta_group::2 instruction
+// (M = 256: 128 rows in each SM of a pair, B split N/2 + N/2 between the two CTAs' shared memories) retires in
+// 43.6 clk at N=64 and 64.7 clk at N=128 -- i.e. at the tensor-pipe floor for N=128 -- where the single-CTA forms cost
+// 75 (SS) / 52 (.ws) clk at N=64.  So here:
+//   * a cluster of 2 CTAs works on a 16 x 30-pixel band: CTA r owns rows 8r..8r+7 (2 M-tiles, its own 40 KB A box),
+//   * every MMA is N=128 where the tap grouping can fill it: Cout=64 -> taps (ky,0)+(ky,1) in one N=128 MMA, (ky,2) as
+//     N=64; Cout=32 -> all three taps of a kernel row in one N=128 MMA (96 useful columns); Cout=3 -> one N=64 MMA,
+//   * each CTA streams only ITS half of every weight block (rows 64r..64r+63) -- weight traffic per SM halves,
+//   * 4 A stages (3 x 40 KB in flight per SM) instead of 2 x 72 KB.
+// Synchronisation: "full" barriers live in the leader CTA and collect the TMA bytes of both CTAs (cp.async.bulk.tensor
+// .cta_group::2 signalling a shared::cluster mbarrier); "empty" barriers and "accumulator full" are signalled in both
+// CTAs at once by tcgen05.commit ... multicast::cluster; the peer's epilogue warps hand the accumulator back with a
+// remote mbarrier.arrive.
+#include <stdlib.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace rsr {
+
+namespace {
+
+constexpr int P = CONV_P;
+constexpr int BW = P - 2;
+constexpr int BH = 8;                         // output rows per CTA
+constexpr int BAND = 2 * BH;                  // output rows per CTA pair
+constexpr int MT = BH * P / 128;              // 2 M-tiles per CTA
+constexpr int NA = 4;                         // A stages
+constexpr int A_BYTES = (BH + 2) * P * 128;   // 40 KB
+constexpr int A_STAGE = A_BYTES + 1024;
+constexpr int NB = 5;                         // weight ring slots
+constexpr int B_SLOT = 64 * 128;              // this CTA's half of a weight block: up to 64 rows x 64 k
+constexpr int NEPI = 8;
+constexpr int NTHREADS = (3 + NEPI) * 32;
+constexpr int STAGE_BYTES = 32 * 20 * 4;
+constexpr int DCOLS = 128;                    // TMEM columns per M-tile
+constexpr int ACC_COLS = MT * DCOLS;          // 256 per accumulator set
+constexpr int TMEM_COLS = 2 * ACC_COLS;
+constexpr int SMEM_BYTES = 1024 + NA * A_STAGE + NB * B_SLOT + NEPI * STAGE_BYTES + 256;
+static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+
+struct Bars {
+    uint64_t a_full[NA], a_empty[NA];
+    uint64_t b_full[NB], b_empty[NB];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_ptr;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b)
+{
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int NREAL, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
+{
+    constexpr int NGROUPS = NREAL == 64 ? 2 : 1;           // MMA groups per kernel row (pair + single, or one triple)
+    constexpr int ROWS_PER_KY = NREAL == 64 ? 192 : (NREAL == 32 ? 128 : 64);  // weight rows per (plane, ky), see model.cpp
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + NA * A_STAGE;
+    uint8_t* smStage = smB + NB * B_SLOT;
+    Bars* bars = reinterpret_cast<Bars*>(smStage + NEPI * STAGE_BYTES);
+    __shared__ __align__(16) float s_bias[64];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool is_leader = rank == 0;
+    const int nchunk = (a.cin + 63) >> 6;
+    const int tiles_x = (a.W + BW - 1) / BW, bands_y = (a.H + BAND - 1) / BAND;
+    const int tiles_per_img = tiles_x * bands_y;
+    const int ntiles = tiles_per_img * a.B;       // pair tiles
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NA; i++) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
+        for (int i = 0; i < NB; i++) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 2 * NEPI); }
+        mbar_fence_init();
+        for (int i = 0; i < 3; i++) tma_prefetch_desc(&maps.m[i]);
+        tma_prefetch_desc(&maps.w);
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + NREAL) s_bias[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
+    // rows behind each A box: read by the kx=2 taps of the last two (never stored) positions; keep them finite
+    if (threadIdx.x >= 96 && threadIdx.x < 96 + NA * 64) {
+        const int i = threadIdx.x - 96;
+        reinterpret_cast<uint4*>(smA + (i >> 6) * A_STAGE + A_BYTES)[i & 63] = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    cluster_sync();  // barriers of both CTAs are initialised before anybody signals across
+    if (warp == 1) tmem_alloc2(&bars->tmem_ptr, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_ptr;
+    // Programmatic dependent launch: let the next conv's CTAs be scheduled onto SMs as soon as this grid's CTAs retire
+    // (they run their prologue and then block here), and wait until the previous grid has completed and flushed its
+    // outputs before touching any activation.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (warp == 0) {
+        // ---------------- A producer (both CTAs; bytes are counted on the leader's barrier) ----------------
+        const bool leader = elect_one();
+        int ca = 0;
+        for (int t = cluster_id; t < ntiles; t += nclusters) {
+            const int b = t / tiles_per_img, rem = t - b * tiles_per_img;
+            const int by = rem / tiles_x, tx = rem - by * tiles_x;
+            for (int c = 0; c < nchunk; c++, ca++) {
+                const int s = ca % NA;
+                mbar_wait(&bars->a_empty[s], ((ca / NA) & 1) ^ 1);
+                if (leader) {
+                    if (a.desc_mode & 2) {
+                        if (is_leader) mbar_arrive(&bars->a_full[s]);
+                    } else {
+                        if (is_leader) mbar_expect_tx(&bars->a_full[s], 2 * A_BYTES);
+                        tma2_load_4d(smA + s * A_STAGE, &maps.m[c], mapa_u32(smem_u32(&bars->a_full[s]), 0), 0, tx * BW - 1,
+                                     by * BAND + (int)rank * BH - 1, b);
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ---------------- weight producer: this CTA's half of every block ----------------
+        const bool leader = elect_one();
+        int cb = 0;
+        for (int t = cluster_id; t < ntiles; t += nclusters) {
+            for (int c = 0; c < nchunk; c++)
+                for (int ky = 0; ky < 3; ky++)
+                    for (int g = 0; g < NGROUPS; g++, cb++) {
+                        const int s = cb % NB;
+                        mbar_wait(&bars->b_empty[s], ((cb / NB) & 1) ^ 1);
+                        if (leader) {
+                            if (a.desc_mode & 4) {
+                                if (is_leader) mbar_arrive(&bars->b_full[s]);
+                            } else {
+                                // block of N rows starting at row0; CTA r streams rows [r*N/2, (r+1)*N/2) (box = 64 rows;
+                                // for N=64 blocks the upper 32 rows of the box are simply not read by the MMA)
+                                const int nrows_half = (NREAL == 16 || g == 1) ? 32 : 64;
+                                const int row0 = (c * 3 + ky) * ROWS_PER_KY + g * 128 + (int)rank * nrows_half;
+                                if (is_leader) mbar_expect_tx(&bars->b_full[s], 2 * B_SLOT);
+                                tma2_load_2d(smB + s * B_SLOT, &maps.w, mapa_u32(smem_u32(&bars->b_full[s]), 0), 0, row0);
+                            }
+                        }
+                    }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (leader CTA only) ----------------
+        if (is_leader) {
+            const bool leader = elect_one();
+            constexpr uint32_t idesc128 = umma_idesc_f16(256, 128);
+            constexpr uint32_t idesc64 = umma_idesc_f16(256, 64);
+            const uint64_t desc_hi = umma_desc_sw128(0, 1024, 0);
+            int ca = 0, cb = 0, ti = 0;
+            for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
+                const int buf = ti & 1;
+                mbar_wait(&bars->acc_empty[buf], ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + buf * ACC_COLS;
+                for (int c = 0; c < nchunk; c++, ca++) {
+                    const int sA = ca % NA;
+                    mbar_wait(&bars->a_full[sA], (ca / NA) & 1);
+                    tc_fence_after();
+                    const int rem = a.cin - c * 64;
+                    const int ksteps = rem >= 64 ? 4 : (rem >> 4);
+                    const uint32_t a_base = smem_u32(smA + sA * A_STAGE);
+                    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+                        for (int g = 0; g < NGROUPS; g++, cb++) {
+                            const int sB = cb % NB;
+                            mbar_wait(&bars->b_full[sB], (cb / NB) & 1);
+                            tc_fence_after();
+                            const uint32_t idesc = (NREAL == 16 || g == 1) ? idesc64 : idesc128;
+                            const uint64_t db0 = desc_hi | (uint64_t)((smem_u32(smB + sB * B_SLOT) & 0x3FFFFu) >> 4);
+                            const uint64_t da0 = desc_hi | (uint64_t)(((a_base + (uint32_t)(ky * P + g * 2) * 128u) & 0x3FFFFu) >> 4);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ks++) {
+                                if (ks < ksteps && leader && !(a.desc_mode & 1)) {
+                                    const uint32_t accum = (c | ky | g | ks) ? 1u : 0u;
+                                    umma2_f16(acc + 0 * DCOLS, da0 + ks * 2, db0 + ks * 2, idesc, accum);
+                                    umma2_f16(acc + 1 * DCOLS, da0 + ks * 2 + 1024, db0 + ks * 2, idesc, accum);
+                                }
+                            }
+                            if (leader) umma2_commit(&bars->b_empty[sB], 3);
+                        }
+                    if (leader) umma2_commit(&bars->a_empty[sA], 3);
+                }
+                if (leader) umma2_commit(&bars->acc_full[buf], 3);
+            }
+        }
+    } else {
+        // ---------------- epilogue: warps 3..10; TMEM lane quarter = warp % 4; M-tile = (warp-3)/4 ----------------
+        const int q4 = warp & 3;
+        const int ew = warp - 3;
+        const int mt = ew >> 2;
+        uint32_t* stg = reinterpret_cast<uint32_t*>(smStage + ew * STAGE_BYTES);  // [32 rows][20 words]
+        const int tr = lane >> 2, tc = lane & 3;
+        const bool dbg_noepi = (a.desc_mode & 8) != 0;
+        const uint32_t acc_empty_leader[2] = {mapa_u32(smem_u32(&bars->acc_empty[0]), 0), mapa_u32(smem_u32(&bars->acc_empty[1]), 0)};
+        int ti = 0;
+        for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
+            const int b = t / tiles_per_img, rem = t - b * tiles_per_img;
+            const int by = rem / tiles_x, tx = rem - by * tiles_x;
+            const int x0 = tx * BW;
+            const int yy = by * BAND + (int)rank * BH + mt * 4 + q4;
+            const int buf = ti & 1;
+            const bool vrow = yy < a.H;
+            bool vcol[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < a.W) && vrow && !dbg_noepi;
+            const size_t rowpix = ((size_t)b * a.H + yy) * a.W + x0;
+            float4 res[2][4];
+            auto load_res = [&](int nb) {
+                if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
+                    const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix * 64 + nb * 32 + tc * 4;
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                        for (int r = 0; r < 4; r++)
+                            if (vcol[r]) res[hf][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
+                }
+            };
+            load_res(0);
+            mbar_wait(&bars->acc_full[buf], (ti >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS + mt * DCOLS;
+            if constexpr (NREAL == 16) {
+                uint32_t v[32], u[16];
+                tmem_ld32(taddr, v);
+                tmem_ld16(taddr + 32, u);
+                tmem_ld_wait();
+                float o[3];
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                    o[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 1) +
+                           __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 2) + s_bias[j];
+                const int x = x0 + lane;
+                if (lane < BW && x < a.W && vrow && !dbg_noepi) {
+                    const TileDesc td = a.tiles[b];
+                    if constexpr (MODE == CONV_LAST_U8) {
+                        const int ii = yy - a.prepad_s, jx = x - a.prepad_s;
+                        if (ii >= 0 && ii < td.crop_h && jx >= 0 && jx < td.crop_w) {
+                            uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + ii) * a.img_w + td.out_x0 + jx) * 3;
+#pragma unroll
+                            for (int j = 0; j < 3; j++) {
+                                int iv = (int)(o[j] * 255.f + 0.5f);
+                                dst[j] = (uint8_t)min(max(iv, 0), 255);
+                            }
+                        }
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)a.H * a.W) + (size_t)yy * a.W + x;
+                        *dst = make_float4(o[0], o[1], o[2], 0.f);
+                    }
+                }
+            } else if constexpr (MODE == CONV_STORE16) {
+#pragma unroll
+                for (int nb = 0; nb < NREAL / 32; nb++) {
+                    float f[32];
+                    if constexpr (NREAL == 32) {  // D[0:32] + right neighbour's D[32:64] + second right neighbour's D[64:96]
+                        uint32_t v[32], u[32], w[32];
+                        tmem_ld32(taddr, v);
+                        tmem_ld32(taddr + 32, u);
+                        tmem_ld32(taddr + 64, w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            f[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
+                                   __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2) + s_bias[j];
+                    } else {  // D[nb*32..] + right neighbour's D[64 + nb*32..]
+                        uint32_t v[32], u[32];
+                        tmem_ld32(taddr + nb * 32, v);
+                        tmem_ld32(taddr + 64 + nb * 32, u);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            f[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) + s_bias[nb * 32 + j];
+                    }
+                    if (a.act == 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) =
+                            make_uint4(pack_h2(f[8 * k + 0], f[8 * k + 1]), pack_h2(f[8 * k + 2], f[8 * k + 3]),
+                                       pack_h2(f[8 * k + 4], f[8 * k + 5]), pack_h2(f[8 * k + 6], f[8 * k + 7]));
+                    __syncwarp();
+                    __half* orow = a.out16 + rowpix * a.out_cs + a.out_co + nb * 32 + tc * 8;
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const uint4 o = *reinterpret_cast<const uint4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
+                        if (vcol[r]) *reinterpret_cast<uint4*>(orow + (size_t)(tr + 8 * r) * a.out_cs) = o;
+                    }
+                    __syncwarp();
+                }
+            } else {
+                // CONV_RDB_OUT / CONV_TRUNK (Cout = 64): fp32 math against the residual stream in the transposed domain
+#pragma unroll
+                for (int nb = 0; nb < 2; nb++) {
+                    uint32_t v[32], u[32];
+                    tmem_ld32(taddr + nb * 32, v);
+                    tmem_ld32(taddr + 64 + nb * 32, u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1));
+                    float4 nxt[2][4];
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) = make_uint4(v[16 * hf + 4 * k], v[16 * hf + 4 * k + 1], v[16 * hf + 4 * k + 2], v[16 * hf + 4 * k + 3]);
+                        __syncwarp();
+                        const int ch0 = nb * 32 + hf * 16 + tc * 4;
+                        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[ch0]);
+                        float4 acc4[4];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) acc4[r] = *reinterpret_cast<const float4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
+                        __syncwarp();
+                        if (hf == 0 && nb == 0) {  // prefetch the residual operands of the second 32-channel block
+                            const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix * 64 + 32 + tc * 4;
+#pragma unroll
+                            for (int h2 = 0; h2 < 2; h2++)
+#pragma unroll
+                                for (int r = 0; r < 4; r++)
+                                    if (vcol[r]) nxt[h2][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + h2 * 16);
+                        }
+                        float4 rr[4];
+                        if (MODE == CONV_RDB_OUT && a.rrdb_end) {
+#pragma unroll
+                            for (int r = 0; r < 4; r++)
+                                if (vcol[r]) rr[r] = *reinterpret_cast<const float4*>(a.r32 + (rowpix + tr + 8 * r) * 64 + ch0);
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            float4 o;
+                            if constexpr (MODE == CONV_RDB_OUT) {
+                                o.x = (acc4[r].x + bb.x) * 0.2f + res[hf][r].x;
+                                o.y = (acc4[r].y + bb.y) * 0.2f + res[hf][r].y;
+                                o.z = (acc4[r].z + bb.z) * 0.2f + res[hf][r].z;
+                                o.w = (acc4[r].w + bb.w) * 0.2f + res[hf][r].w;
+                                if (a.rrdb_end) {
+                                    o.x = o.x * 0.2f + rr[r].x; o.y = o.y * 0.2f + rr[r].y;
+                                    o.z = o.z * 0.2f + rr[r].z; o.w = o.w * 0.2f + rr[r].w;
+                                }
+                            } else {
+                                o.x = acc4[r].x + bb.x + res[hf][r].x; o.y = acc4[r].y + bb.y + res[hf][r].y;
+                                o.z = acc4[r].z + bb.z + res[hf][r].z; o.w = acc4[r].w + bb.w + res[hf][r].w;
+                            }
+                            if (vcol[r]) {
+                                const size_t px = rowpix + tr + 8 * r;
+                                if constexpr (MODE == CONV_RDB_OUT) {
+                                    if (a.rrdb_end) *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0) = o;
+                                    *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o;
+                                }
+                                *reinterpret_cast<uint2*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                            }
+                        }
+                    }
+                    if (nb == 0) {
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; h2++)
+#pragma unroll
+                            for (int r = 0; r < 4; r++) res[h2][r] = nxt[h2][r];
+                    }
+                }
+            }
+            // accumulator set drained by this warp: tell the leader's MMA issuer (remote arrive from the peer CTA)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_leader[buf]);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync();  // nobody frees TMEM / exits while the peer may still signal or be read
+    if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
+template <int NREAL, int MODE>
+cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
+{
+    static bool attr_done[64] = {};
+    static int num_sms[64] = {};
+    cudaError_t e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    dev &= 63;
+    if (!attr_done[dev]) {
+        e = cudaFuncSetAttribute(conv3x3_tc2_kernel<NREAL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        attr_done[dev] = true;
+    }
+    const long long ntiles = (long long)((a.W + BW - 1) / BW) * ((a.H + BAND - 1) / BAND) * a.B;
+    long long nclusters = num_sms[dev] / 2;
+    if (ntiles < nclusters) nclusters = ntiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * nclusters));
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const int use_pdl = getenv("RSR_NOPDL") ? 0 : 1;  // bring-up switch
+    cfg.numAttrs = use_pdl;
+    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<NREAL, MODE>, *in_map, a)) != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_conv3x3_tc2(const ConvMaps* in_map, const ConvArgs& a, int cout_pad, cudaStream_t stream)
+{
+    if (cout_pad == 32 && a.mode == CONV_STORE16) return launch_nm<32, CONV_STORE16>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_STORE16) return launch_nm<64, CONV_STORE16>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_RDB_OUT) return launch_nm<64, CONV_RDB_OUT>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_TRUNK) return launch_nm<64, CONV_TRUNK>(in_map, a, stream);
+    if (cout_pad == 16 && a.mode == CONV_LAST_U8) return launch_nm<16, CONV_LAST_U8>(in_map, a, stream);
+    if (cout_pad == 16 && a.mode == CONV_LAST_F32) return launch_nm<16, CONV_LAST_F32>(in_map, a, stream);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace rsr

@@ -59,6 +59,7 @@ struct DeviceModel {
     std::vector<__half*> wpk;   // per conv (index 0 unused)
     std::vector<float*> bias;   // per conv, padded to cout_pad
     std::vector<int> cout_pad;
+    std::vector<CUtensorMap> wmap;  // per conv: 2-D map over its weight rows (CTA-pair kernel)
     float* w0 = nullptr;        // Conv_0 fp32 weights [64][27]
     void* blob = nullptr;       // one allocation holding everything
 };
@@ -76,6 +77,7 @@ struct rsr_handle {
     std::string err;
     // options
     long long max_batch = 0;  // 0 = auto
+    int conv_impl = 1;  // 1 = single-CTA .ws kernel (conv_tc.cu, default: fastest end to end in round 1), 2 = CTA-pair kernel (conv_tc2.cu)
     int desc_mode = 0;  // measured on B200: SWIZZLE_128B is a function of the absolute smem address => base_offset 0 for row-shifted starts
     int time_convs = 0;
     // stats
@@ -115,13 +117,27 @@ int ensure(rsr_handle* h, DevBuf& b, size_t bytes)
     return 0;
 }
 
-int make_map(rsr_handle* h, CUtensorMap* m, const void* base, int C, int W, int H, int B)
+int make_wmap(rsr_handle* h, CUtensorMap* m, const void* base, int rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight map");
+    return 0;
+}
+
+int make_map(rsr_handle* h, CUtensorMap* m, const void* base, int C, int W, int H, int B, int box_rows = CONV_BH + 2)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)CONV_P, (cuuint32_t)(CONV_BH + 2), 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)CONV_P, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -198,7 +214,13 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
         c.nconv_ev++;
         CK(cudaEventRecord(e0, c.ws->stream));
     }
-    CK(launch_conv3x3_tc(map, a, dm.cout_pad[conv_idx], c.ws->stream));
+    if (h->conv_impl == 2) {
+        ConvMaps mm = *map;
+        mm.w = dm.wmap[conv_idx];
+        CK(launch_conv3x3_tc2(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
+    } else {
+        CK(launch_conv3x3_tc(map, a, dm.cout_pad[conv_idx], c.ws->stream));
+    }
     if (e1) CK(cudaEventRecord(e1, c.ws->stream));
     c.launches++;
     return 0;
@@ -233,13 +255,14 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, uint8_t* 
     __half* D[2] = {(__half*)ws->d16[0].p, (__half*)ws->d16[1].p};
     const size_t plane = npx * 64;
     ConvMaps mapD[2], mapU1, mapV1, mapU2, mapV2;
+    const int brows = (h->conv_impl == 2 ? CONV2_BH : CONV_BH) + 2;
     for (int i = 0; i < 2; i++)
         for (int pl = 0; pl < 3; pl++)
-            if ((r = make_map(h, &mapD[i].m[pl], D[i] + pl * plane, 64, W, H, B))) return r;
-    if ((r = make_map(h, &mapU1.m[0], ws->u1.p, 64, 2 * W, 2 * H, B))) return r;
-    if ((r = make_map(h, &mapV1.m[0], ws->v1.p, 64, 2 * W, 2 * H, B))) return r;
-    if ((r = make_map(h, &mapU2.m[0], ws->u2.p, 64, 4 * W, 4 * H, B))) return r;
-    if ((r = make_map(h, &mapV2.m[0], ws->v2.p, 64, 4 * W, 4 * H, B))) return r;
+            if ((r = make_map(h, &mapD[i].m[pl], D[i] + pl * plane, 64, W, H, B, brows))) return r;
+    if ((r = make_map(h, &mapU1.m[0], ws->u1.p, 64, 2 * W, 2 * H, B, brows))) return r;
+    if ((r = make_map(h, &mapV1.m[0], ws->v1.p, 64, 2 * W, 2 * H, B, brows))) return r;
+    if ((r = make_map(h, &mapU2.m[0], ws->u2.p, 64, 4 * W, 4 * H, B, brows))) return r;
+    if ((r = make_map(h, &mapV2.m[0], ws->v2.p, 64, 4 * W, 4 * H, B, brows))) return r;
     for (ConvMaps* cm : {&mapU1, &mapV1, &mapU2, &mapV2}) cm->m[1] = cm->m[2] = cm->m[0];
 
     // Conv_0 + preproc
@@ -445,8 +468,9 @@ int rsr_load(rsr_handle* h, const char* parampath, const char* modelpath)
     if (r) return set_err(h, RSR_ERR_MODEL, m.error);
     // pack + upload: one blob, 1024-B aligned sub-allocations (bulk copies need 16 B; keep slabs nicely aligned)
     const int nconv = (int)m.convs.size();
-    std::vector<std::vector<uint16_t>> packed(nconv);
-    std::vector<size_t> off_w(nconv, 0), off_b(nconv, 0);
+    std::vector<std::vector<uint16_t>> packed(nconv), packed_rows(nconv);
+    std::vector<size_t> off_w(nconv, 0), off_b(nconv, 0), off_r(nconv, 0);
+    std::vector<int> nrows(nconv, 0);
     DeviceModel dm;
     dm.cout_pad.assign(nconv, 0);
     size_t total = 0;
@@ -459,6 +483,8 @@ int rsr_load(rsr_handle* h, const char* parampath, const char* modelpath)
             if (c.cout > 64 || (c.cin % 16)) return set_err(h, RSR_ERR_MODEL, "unsupported conv shape in " + c.name);
             pack_conv_weights(c, dm.cout_pad[i], packed[i]);
             off_w[i] = bump(packed[i].size() * 2);
+            nrows[i] = pack_conv_weight_rows(c, dm.cout_pad[i], packed_rows[i]);
+            off_r[i] = bump(packed_rows[i].size() * 2);
         }
         off_b[i] = bump(64 * 4);
     }
@@ -468,12 +494,18 @@ int rsr_load(rsr_handle* h, const char* parampath, const char* modelpath)
     memcpy(host.data() + off_w0, m.convs[0].weight.data(), 64 * 27 * 4);
     for (int i = 0; i < nconv; i++) {
         if (i > 0) memcpy(host.data() + off_w[i], packed[i].data(), packed[i].size() * 2);
+        if (i > 0) memcpy(host.data() + off_r[i], packed_rows[i].data(), packed_rows[i].size() * 2);
         memcpy(host.data() + off_b[i], m.convs[i].bias.data(), m.convs[i].cout * 4);
     }
     CK(cudaMemcpy(dm.blob, host.data(), total, cudaMemcpyHostToDevice));
     dm.w0 = (float*)((uint8_t*)dm.blob + off_w0);
     dm.wpk.assign(nconv, nullptr);
     dm.bias.assign(nconv, nullptr);
+    dm.wmap.resize(nconv);
+    for (int i = 1; i < nconv; i++) {
+        int rr = make_wmap(h, &dm.wmap[i], (uint8_t*)dm.blob + off_r[i], nrows[i]);
+        if (rr) return rr;
+    }
     for (int i = 0; i < nconv; i++) {
         if (i > 0) dm.wpk[i] = (__half*)((uint8_t*)dm.blob + off_w[i]);
         dm.bias[i] = (float*)((uint8_t*)dm.blob + off_b[i]);
@@ -553,6 +585,7 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
     if (!strcmp(key, "max_batch")) h->max_batch = value;
     else if (!strcmp(key, "debug_mask") || !strcmp(key, "desc_mode")) h->desc_mode = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
+    else if (!strcmp(key, "conv_impl")) h->conv_impl = (int)value;
     else return set_err(h, RSR_ERR_GENERIC, std::string("unknown option ") + key);
     return 0;
 }
@@ -617,7 +650,8 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     ConvMaps map;
     int r = 0;
     for (int pl = 0; pl < 3; pl++)
-        if ((r = make_map(h, &map.m[pl], d_in + (size_t)(pl < nplane ? pl : 0) * npx * 64, 64, W, H, 1))) return r;
+        if ((r = make_map(h, &map.m[pl], d_in + (size_t)(pl < nplane ? pl : 0) * npx * 64, 64, W, H, 1, (h->conv_impl == 2 ? CONV2_BH : CONV_BH) + 2))) return r;
+    map.w = h->dm.wmap[conv_index];
     ConvArgs a{};
     a.wpk = h->dm.wpk[conv_index]; a.bias = h->dm.bias[conv_index]; a.cin = cl.cin;
     a.H = H; a.W = W; a.B = 1;
@@ -626,7 +660,8 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     a.tiles = d_td; a.tta_out = d_f;
     a.mode = npad == 16 ? CONV_LAST_F32 : CONV_STORE16;
     a.desc_mode = h->desc_mode;
-    CK(launch_conv3x3_tc(&map, a, npad, 0));
+    if (h->conv_impl == 2) CK(launch_conv3x3_tc2(&map, a, npad, 0));
+    else CK(launch_conv3x3_tc(&map, a, npad, 0));
     CK(cudaDeviceSynchronize());
     if (npad == 16) {
         std::vector<float> tmp(npx * 4);

@@ -62,9 +62,13 @@ struct ConvArgs {
 // one tensor map per 64-channel input plane (chunk) of a conv
 struct alignas(64) ConvMaps {
     CUtensorMap m[3];
+    CUtensorMap w;  // 2-D map over the conv's weight rows [rows][64] (CTA-pair kernel only)
 };
 // conv3x3 s1 p1 as implicit GEMM on tcgen05 (conv_tc.cu). cout_pad in {16, 32, 64}.
 cudaError_t launch_conv3x3_tc(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
+// same contract, CTA-pair (cta_group::2) implementation (conv_tc2.cu); needs in_maps->w and 10-row activation boxes
+cudaError_t launch_conv3x3_tc2(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
+constexpr int CONV2_BH = 8;
 // box dims the kernel expects from the tensor map: {64 ch, 32 px, CONV_BH+2 rows, 1}
 constexpr int CONV_BH = 16;
 constexpr int CONV_P = 32;

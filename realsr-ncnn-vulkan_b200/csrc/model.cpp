@@ -307,6 +307,27 @@ static void pack_conv_weights_tripled(const ConvLayer& c, std::vector<uint16_t>&
         }
 }
 
+int pack_conv_weight_rows(const ConvLayer& c, int cout_pad, std::vector<uint16_t>& out)
+{
+    const int nchunk = (c.cin + 63) / 64;
+    const int grp = cout_pad;                               // rows per tap group
+    const int rows_per_ky = cout_pad == 64 ? 192 : 4 * grp;  // 3 tap groups (+ one zero group when Cout < 64)
+    const int rows = nchunk * 3 * rows_per_ky;
+    out.assign((size_t)rows * 64, 0);
+    for (int ch = 0; ch < nchunk; ch++)
+        for (int ky = 0; ky < 3; ky++)
+            for (int kx = 0; kx < 3; kx++)
+                for (int n = 0; n < c.cout; n++) {
+                    uint16_t* row = out.data() + ((size_t)(ch * 3 + ky) * rows_per_ky + kx * grp + n) * 64;
+                    for (int k = 0; k < 64; k++) {
+                        const int ci = ch * 64 + k;
+                        if (ci >= c.cin) break;
+                        row[k] = c.weight_h[((size_t)n * c.cin + ci) * 9 + ky * 3 + kx];
+                    }
+                }
+    return rows;
+}
+
 void pack_conv_weights(const ConvLayer& c, int cout_pad, std::vector<uint16_t>& out)
 {
     if (cout_pad == 32) {

@@ -154,6 +154,39 @@ def test_errors_are_reported(models_dir):
     assert g.kernel_launches() > 0
 
 
+def test_cta_pair_kernel_same_contract(models_dir):
+    """the cta_group::2 implementation of the conv (conv_tc2.cu, rsr_set_option("conv_impl", 2)) meets the same per-layer
+    tolerance and the same end-to-end contract as the default single-CTA kernel"""
+    import torch
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = False
+    e = rb.RealSR(0)
+    p, b = model_paths("models-DF2K")
+    assert e.load(p, b) == 0
+    e.set_option("conv_impl", 2)
+    convs = read_convs("models-DF2K")
+    for idx, H, W in [(1, 37, 45), (2, 17, 31), (4, 40, 61), (5, 33, 64), (346, 24, 30), (350, 29, 47)]:
+        c = convs[idx]
+        x = (np.random.default_rng(idx).standard_normal((H, W, c["cin"])) * 0.5).astype(np.float16)
+        y = e.debug_conv(idx, x, c["cout"])
+        ref = F.conv2d(torch.from_numpy(x.astype(np.float32)).cuda().permute(2, 0, 1)[None], torch.from_numpy(c["w"].astype(np.float32)).cuda(),
+                       torch.from_numpy(c["b"].copy()).cuda(), padding=1)
+        if c["act"] == 2:
+            ref = F.leaky_relu(ref, 0.2)
+        ref = ref[0].permute(1, 2, 0).cpu().numpy()
+        if c["cout"] != 3:
+            ref = ref.astype(np.float16).astype(np.float32)
+        err = np.abs(y - ref)
+        assert np.all((err <= 2e-3) | (err <= 2e-3 * np.abs(ref))), (idx, float(err.max()))
+    for name, natural in (("natural_48x40_df2k_t32", True), ("noise_50x33_df2k_t32", False), ("readme0_crop96x80_df2k_t64", True)):
+        case = [c for c in CASES if c["name"] == name][0]
+        img, gold = golden(name)
+        e.tilesize = case["tilesize"]
+        out = np.zeros_like(gold)
+        assert e.process(img, out) == 0, e.last_error()
+        check_contract(diff_stats(out, gold), natural)
+
+
 def test_cpp_wrapper_cli_concurrent_jobs(tmp_path, models_dir):
     """the C++ `class RealSR` wrapper driven like the reference's proc stage: 3 threads call process() on one object"""
     import os
