@@ -13,7 +13,7 @@ shape batch.
            (rsr_process_device), device time from CUDA events on the engine's stream, max over ranks.
   e2e    : the same metric through the reference-facing call (rsr_process == RealSR::process) with pinned HOST buffers:
            H2D of the u8 source and D2H of the 16x larger u8 result are inside the timed region.
-  roofline: the dominant kernel (conv3x3_tc_kernel, 350 launches per batch): algorithmic FLOPs (35.853696 MFLOP per
+  roofline: the dominant kernel (conv3x3_tc2_kernel, 350 launches per batch): algorithmic FLOPs (35.853696 MFLOP per
            network-input pixel) / summed CUDA-event duration of those launches, against the measured bf16
            peak in MEASURED_PEAKS.json (sustained figure: the kernel is timed inside a long step).
   cpu_baseline: the REAL reference CPU path (oracle/_ref = reference process_cpu + ncnn b4ba207) on this box's host
@@ -277,7 +277,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "conv3x3_tc_kernel (tcgen05.mma.ws)", "launches_per_step": n_conv_launches,
+                         "kernel": "conv3x3_tc2_kernel (tcgen05.mma cta_group::2, M=256 over an SM pair)", "launches_per_step": n_conv_launches,
                          "avg_launch_ms": conv_ms / n_conv_launches, "peak_source": peak_src,
                          "flops_per_step": FLOP_PER_PADDED_PX * padded},
         }

@@ -29,23 +29,25 @@ constexpr int BW = P - 2;
 constexpr int BH = 8;                         // output rows per CTA
 constexpr int BAND = 2 * BH;                  // output rows per CTA pair
 constexpr int MT = BH * P / 128;              // 2 M-tiles per CTA
-constexpr int NA = 4;                         // A stages
+constexpr int NA_MAX = 4;                     // A stages (run-time count: as many as fit next to the resident weights)
 constexpr int A_BYTES = (BH + 2) * P * 128;   // 40 KB
 constexpr int A_STAGE = A_BYTES + 1024;
-constexpr int NB = 5;                         // weight ring slots
-constexpr int B_SLOT = 64 * 128;              // this CTA's half of a weight block: up to 64 rows x 64 k
 constexpr int NEPI = 8;
 constexpr int NTHREADS = (3 + NEPI) * 32;
 constexpr int STAGE_BYTES = 32 * 20 * 4;
 constexpr int DCOLS = 128;                    // TMEM columns per M-tile
 constexpr int ACC_COLS = MT * DCOLS;          // 256 per accumulator set
 constexpr int TMEM_COLS = 2 * ACC_COLS;
-constexpr int SMEM_BYTES = 1024 + NA * A_STAGE + NB * B_SLOT + NEPI * STAGE_BYTES + 256;
-static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+constexpr int SMEM_MAX = 227 * 1024 - 1024;  // dynamic part; the kernel also has ~300 B of static shared memory
+constexpr int SMEM_FIXED = 1024 /*align*/ + NEPI * STAGE_BYTES + 256 /*barriers*/;
+
+// this CTA's half of the weights of one (plane, ky): Cout=64 -> pair half (64 rows) + single half (32 rows);
+// Cout<=32 -> triple half (64 rows); Cout<=16 -> 32 rows
+__host__ __device__ constexpr int w_bytes_per_ky(int nreal) { return nreal == 64 ? 12288 : (nreal == 32 ? 8192 : 4096); }
 
 struct Bars {
-    uint64_t a_full[NA], a_empty[NA];
-    uint64_t b_full[NB], b_empty[NB];
+    uint64_t a_full[NA_MAX], a_empty[NA_MAX];
+    uint64_t w_full;
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_ptr;
 };
@@ -58,38 +60,40 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b)
 
 template <int NREAL, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
+conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const int NA)
 {
     constexpr int NGROUPS = NREAL == 64 ? 2 : 1;           // MMA groups per kernel row (pair + single, or one triple)
     constexpr int ROWS_PER_KY = NREAL == 64 ? 192 : (NREAL == 32 ? 128 : 64);  // weight rows per (plane, ky), see model.cpp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int nchunk = (a.cin + 63) >> 6;
+    constexpr int W_KY = w_bytes_per_ky(NREAL);
     uint8_t* smA = smem;
-    uint8_t* smB = smem + NA * A_STAGE;
-    uint8_t* smStage = smB + NB * B_SLOT;
+    uint8_t* smW = smem + NA * A_STAGE;                  // resident weights: [plane][ky] x W_KY bytes
+    uint8_t* smStage = smW + nchunk * 3 * W_KY;
     Bars* bars = reinterpret_cast<Bars*>(smStage + NEPI * STAGE_BYTES);
     __shared__ __align__(16) float s_bias[64];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool is_leader = rank == 0;
-    const int nchunk = (a.cin + 63) >> 6;
     const int tiles_x = (a.W + BW - 1) / BW, bands_y = (a.H + BAND - 1) / BAND;
     const int tiles_per_img = tiles_x * bands_y;
     const int ntiles = tiles_per_img * a.B;       // pair tiles
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NA; i++) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
-        for (int i = 0; i < NB; i++) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+        for (int i = 0; i < NA_MAX; i++) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
+        mbar_init(&bars->w_full, 1);
         for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 2 * NEPI); }
         mbar_fence_init();
         for (int i = 0; i < 3; i++) tma_prefetch_desc(&maps.m[i]);
         tma_prefetch_desc(&maps.w);
+        tma_prefetch_desc(&maps.w32);
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + NREAL) s_bias[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
     // rows behind each A box: read by the kx=2 taps of the last two (never stored) positions; keep them finite
-    if (threadIdx.x >= 96 && threadIdx.x < 96 + NA * 64) {
+    if (threadIdx.x >= 96 && threadIdx.x < 96 + NA * 64) {  // NA <= 4
         const int i = threadIdx.x - 96;
         reinterpret_cast<uint4*>(smA + (i >> 6) * A_STAGE + A_BYTES)[i & 63] = make_uint4(0, 0, 0, 0);
     }
@@ -100,6 +104,24 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_ptr;
+    // Resident weights: every CTA fetches ITS half of all weight blocks once (before the grid dependency is resolved --
+    // weights are constants, so this overlaps the previous conv's tail).  All bytes are counted on the leader's w_full.
+    if (warp == 2) {
+        if (elect_one() && !(a.desc_mode & 4)) {
+            const uint32_t wbar = mapa_u32(smem_u32(&bars->w_full), 0);
+            if (is_leader) mbar_expect_tx(&bars->w_full, 2u * (uint32_t)(nchunk * 3 * W_KY));
+            for (int c = 0; c < nchunk; c++)
+                for (int ky = 0; ky < 3; ky++) {
+                    uint8_t* dst = smW + (c * 3 + ky) * W_KY;
+                    const int row0 = (c * 3 + ky) * ROWS_PER_KY;
+                    if (NREAL == 16) tma2_load_2d(dst, &maps.w32, wbar, 0, row0 + (int)rank * 32);
+                    else tma2_load_2d(dst, &maps.w, wbar, 0, row0 + (int)rank * 64);
+                    if (NREAL == 64) tma2_load_2d(dst + 8192, &maps.w32, wbar, 0, row0 + 128 + (int)rank * 32);
+                }
+        } else if (is_leader && (a.desc_mode & 4) && lane == 0) {
+            mbar_arrive(&bars->w_full);
+        }
+    }
     // Programmatic dependent launch: let the next conv's CTAs be scheduled onto SMs as soon as this grid's CTAs retire
     // (they run their prologue and then block here), and wait until the previous grid has completed and flushed its
     // outputs before touching any activation.
@@ -127,30 +149,6 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
                 }
             }
         }
-    } else if (warp == 2) {
-        // ---------------- weight producer: this CTA's half of every block ----------------
-        const bool leader = elect_one();
-        int cb = 0;
-        for (int t = cluster_id; t < ntiles; t += nclusters) {
-            for (int c = 0; c < nchunk; c++)
-                for (int ky = 0; ky < 3; ky++)
-                    for (int g = 0; g < NGROUPS; g++, cb++) {
-                        const int s = cb % NB;
-                        mbar_wait(&bars->b_empty[s], ((cb / NB) & 1) ^ 1);
-                        if (leader) {
-                            if (a.desc_mode & 4) {
-                                if (is_leader) mbar_arrive(&bars->b_full[s]);
-                            } else {
-                                // block of N rows starting at row0; CTA r streams rows [r*N/2, (r+1)*N/2) (box = 64 rows;
-                                // for N=64 blocks the upper 32 rows of the box are simply not read by the MMA)
-                                const int nrows_half = (NREAL == 16 || g == 1) ? 32 : 64;
-                                const int row0 = (c * 3 + ky) * ROWS_PER_KY + g * 128 + (int)rank * nrows_half;
-                                if (is_leader) mbar_expect_tx(&bars->b_full[s], 2 * B_SLOT);
-                                tma2_load_2d(smB + s * B_SLOT, &maps.w, mapa_u32(smem_u32(&bars->b_full[s]), 0), 0, row0);
-                            }
-                        }
-                    }
-        }
     } else if (warp == 1) {
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (is_leader) {
@@ -158,7 +156,10 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
             constexpr uint32_t idesc128 = umma_idesc_f16(256, 128);
             constexpr uint32_t idesc64 = umma_idesc_f16(256, 64);
             const uint64_t desc_hi = umma_desc_sw128(0, 1024, 0);
-            int ca = 0, cb = 0, ti = 0;
+            int ca = 0, ti = 0;
+            mbar_wait(&bars->w_full, 0);
+            tc_fence_after();
+            const uint32_t w_base = smem_u32(smW);
             for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
                 const int buf = ti & 1;
                 mbar_wait(&bars->acc_empty[buf], ((ti >> 1) & 1) ^ 1);
@@ -173,12 +174,9 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
                     const uint32_t a_base = smem_u32(smA + sA * A_STAGE);
                     for (int ky = 0; ky < 3; ky++)
 #pragma unroll
-                        for (int g = 0; g < NGROUPS; g++, cb++) {
-                            const int sB = cb % NB;
-                            mbar_wait(&bars->b_full[sB], (cb / NB) & 1);
-                            tc_fence_after();
+                        for (int g = 0; g < NGROUPS; g++) {
                             const uint32_t idesc = (NREAL == 16 || g == 1) ? idesc64 : idesc128;
-                            const uint64_t db0 = desc_hi | (uint64_t)((smem_u32(smB + sB * B_SLOT) & 0x3FFFFu) >> 4);
+                            const uint64_t db0 = desc_hi | (uint64_t)(((w_base + (uint32_t)((c * 3 + ky) * W_KY + g * 8192)) & 0x3FFFFu) >> 4);
                             const uint64_t da0 = desc_hi | (uint64_t)(((a_base + (uint32_t)(ky * P + g * 2) * 128u) & 0x3FFFFu) >> 4);
 #pragma unroll
                             for (int ks = 0; ks < 4; ks++) {
@@ -188,13 +186,14 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
                                     umma2_f16(acc + 1 * DCOLS, da0 + ks * 2 + 1024, db0 + ks * 2, idesc, accum);
                                 }
                             }
-                            if (leader) umma2_commit(&bars->b_empty[sB], 3);
                         }
                     if (leader) umma2_commit(&bars->a_empty[sA], 3);
                 }
                 if (leader) umma2_commit(&bars->acc_full[buf], 3);
             }
         }
+    } else if (warp == 2) {
+        // weight warp: its work (the one-time resident-weight fetch) happened in the prologue
     } else {
         // ---------------- epilogue: warps 3..10; TMEM lane quarter = warp % 4; M-tile = (warp-3)/4 ----------------
         const int q4 = warp & 3;
@@ -394,7 +393,7 @@ cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t st
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     dev &= 63;
     if (!attr_done[dev]) {
-        e = cudaFuncSetAttribute(conv3x3_tc2_kernel<NREAL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        e = cudaFuncSetAttribute(conv3x3_tc2_kernel<NREAL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
         if (e != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         attr_done[dev] = true;
@@ -405,7 +404,13 @@ cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t st
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * nclusters));
     cfg.blockDim = dim3(NTHREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
+    // resident weights first, then as many 41 KB A stages as fit (2..4)
+    const int nchunk = (a.cin + 63) / 64;
+    const int wbytes = nchunk * 3 * w_bytes_per_ky(NREAL);
+    int na = (SMEM_MAX - SMEM_FIXED - wbytes) / A_STAGE;
+    if (na > NA_MAX) na = NA_MAX;
+    if (na < 2) return cudaErrorInvalidValue;
+    cfg.dynamicSmemBytes = SMEM_FIXED + wbytes + na * A_STAGE;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -413,7 +418,7 @@ cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t st
     cfg.attrs = attr;
     static const int use_pdl = getenv("RSR_NOPDL") ? 0 : 1;  // bring-up switch
     cfg.numAttrs = use_pdl;
-    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<NREAL, MODE>, *in_map, a)) != cudaSuccess) return e;
+    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<NREAL, MODE>, *in_map, a, na)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

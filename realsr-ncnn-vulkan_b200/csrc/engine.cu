@@ -59,7 +59,7 @@ struct DeviceModel {
     std::vector<__half*> wpk;   // per conv (index 0 unused)
     std::vector<float*> bias;   // per conv, padded to cout_pad
     std::vector<int> cout_pad;
-    std::vector<CUtensorMap> wmap;  // per conv: 2-D map over its weight rows (CTA-pair kernel)
+    std::vector<CUtensorMap> wmap, wmap32;  // per conv: 2-D maps over its weight rows, box 64 / 32 rows (CTA-pair kernel)
     float* w0 = nullptr;        // Conv_0 fp32 weights [64][27]
     void* blob = nullptr;       // one allocation holding everything
 };
@@ -77,7 +77,7 @@ struct rsr_handle {
     std::string err;
     // options
     long long max_batch = 0;  // 0 = auto
-    int conv_impl = 1;  // 1 = single-CTA .ws kernel (conv_tc.cu, default: fastest end to end in round 1), 2 = CTA-pair kernel (conv_tc2.cu)
+    int conv_impl = 2;  // 2 = CTA-pair kernel (conv_tc2.cu, default), 1 = single-CTA .ws kernel (conv_tc.cu, kept for A/B: tools/ab_impl.py)
     int desc_mode = 0;  // measured on B200: SWIZZLE_128B is a function of the absolute smem address => base_offset 0 for row-shifted starts
     int time_convs = 0;
     // stats
@@ -117,13 +117,13 @@ int ensure(rsr_handle* h, DevBuf& b, size_t bytes)
     return 0;
 }
 
-int make_wmap(rsr_handle* h, CUtensorMap* m, const void* base, int rows)
+int make_wmap(rsr_handle* h, CUtensorMap* m, const void* base, int rows, int box_rows)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[2] = {64, (cuuint64_t)rows};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, 64};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -217,6 +217,7 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
     if (h->conv_impl == 2) {
         ConvMaps mm = *map;
         mm.w = dm.wmap[conv_idx];
+        mm.w32 = dm.wmap32[conv_idx];
         CK(launch_conv3x3_tc2(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
     } else {
         CK(launch_conv3x3_tc(map, a, dm.cout_pad[conv_idx], c.ws->stream));
@@ -502,8 +503,10 @@ int rsr_load(rsr_handle* h, const char* parampath, const char* modelpath)
     dm.wpk.assign(nconv, nullptr);
     dm.bias.assign(nconv, nullptr);
     dm.wmap.resize(nconv);
+    dm.wmap32.resize(nconv);
     for (int i = 1; i < nconv; i++) {
-        int rr = make_wmap(h, &dm.wmap[i], (uint8_t*)dm.blob + off_r[i], nrows[i]);
+        int rr = make_wmap(h, &dm.wmap[i], (uint8_t*)dm.blob + off_r[i], nrows[i], 64);
+        if (!rr) rr = make_wmap(h, &dm.wmap32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], 32);
         if (rr) return rr;
     }
     for (int i = 0; i < nconv; i++) {
@@ -652,6 +655,7 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     for (int pl = 0; pl < 3; pl++)
         if ((r = make_map(h, &map.m[pl], d_in + (size_t)(pl < nplane ? pl : 0) * npx * 64, 64, W, H, 1, (h->conv_impl == 2 ? CONV2_BH : CONV_BH) + 2))) return r;
     map.w = h->dm.wmap[conv_index];
+    map.w32 = h->dm.wmap32[conv_index];
     ConvArgs a{};
     a.wpk = h->dm.wpk[conv_index]; a.bias = h->dm.bias[conv_index]; a.cin = cl.cin;
     a.H = H; a.W = W; a.B = 1;

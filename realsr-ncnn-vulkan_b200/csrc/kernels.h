@@ -62,7 +62,8 @@ struct ConvArgs {
 // one tensor map per 64-channel input plane (chunk) of a conv
 struct alignas(64) ConvMaps {
     CUtensorMap m[3];
-    CUtensorMap w;  // 2-D map over the conv's weight rows [rows][64] (CTA-pair kernel only)
+    CUtensorMap w;    // 2-D map over the conv's weight rows [rows][64], box 64 rows (CTA-pair kernel only)
+    CUtensorMap w32;  // same tensor, box 32 rows
 };
 // conv3x3 s1 p1 as implicit GEMM on tcgen05 (conv_tc.cu). cout_pad in {16, 32, 64}.
 cudaError_t launch_conv3x3_tc(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);

@@ -154,16 +154,16 @@ def test_errors_are_reported(models_dir):
     assert g.kernel_launches() > 0
 
 
-def test_cta_pair_kernel_same_contract(models_dir):
-    """the cta_group::2 implementation of the conv (conv_tc2.cu, rsr_set_option("conv_impl", 2)) meets the same per-layer
-    tolerance and the same end-to-end contract as the default single-CTA kernel"""
+def test_single_cta_ws_kernel_same_contract(models_dir):
+    """the alternate single-CTA weight-stationary implementation of the conv (conv_tc.cu, rsr_set_option("conv_impl", 1))
+    meets the same per-layer tolerance and the same end-to-end contract as the default CTA-pair kernel (conv_tc2.cu)"""
     import torch
     import torch.nn.functional as F
     torch.backends.cudnn.allow_tf32 = False
     e = rb.RealSR(0)
     p, b = model_paths("models-DF2K")
     assert e.load(p, b) == 0
-    e.set_option("conv_impl", 2)
+    e.set_option("conv_impl", 1)
     convs = read_convs("models-DF2K")
     for idx, H, W in [(1, 37, 45), (2, 17, 31), (4, 40, 61), (5, 33, 64), (346, 24, 30), (350, 29, 47)]:
         c = convs[idx]

@@ -25,6 +25,9 @@ out = np.zeros((h * 4, w * 4, 3), dtype=np.uint8)
 for i in range(iters):
     t0 = time.time()
     r = e.process(img, out)
+    if r:
+        print("process failed", r, e.last_error(), flush=True)
+        break
     print("rc", r, "wall %.2f ms device %.2f ms" % ((time.time() - t0) * 1e3, e.last_ms()), "launches", e.kernel_launches(),
           "conv ms %.2f" % e.last_ms(1), "padded px", e.last_padded_pixels(), "-> %.1f out-MP/s, conv %.0f TFLOP/s" %
           (w * h * 16 / 1e6 / (e.last_ms() * 1e-3), e.last_padded_pixels() * 35.853696e6 / max(e.last_ms(1), 1e-9) / 1e9), flush=True)
