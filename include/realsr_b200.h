@@ -63,7 +63,7 @@ RSR_API int rsr_set(rsr_handle* h, int scale, int tilesize, int prepadding);
  *         (ncnn::Mat(w, h, pixels, elemsize=c, elempack=c), src/main.cpp:275); owned by the caller.
  *   out : (4w)*(4h)*c bytes, tightly packed HWC, allocated by the caller before the call (src/main.cpp:276) and
  *         written in place.
- *   c   : 3 (RGB).  c == 4 (RGBA, bicubic alpha) is not implemented yet and returns RSR_ERR_GENERIC.
+ *   c   : 3 (RGB) or 4 (RGBA: the alpha plane is up-scaled bicubically per tile like realsr.cpp:431-442, not by the network).
  * Host pointers.  Blocks until `out` is complete. */
 RSR_API int rsr_process(rsr_handle* h, const uint8_t* in, int w, int h_, int c, uint8_t* out);
 

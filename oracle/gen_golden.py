@@ -61,16 +61,34 @@ def main():
         cases.append(("readme0_crop96x80_df2k_t64", np.ascontiguousarray(im[40:120, 30:126]), "models-DF2K", 64, 0))
     except Exception as e:  # PIL or the image absent
         print("skipping README image cases:", e)
+    # RGBA (single-tile only: the reference's CPU branch is not self-consistent for multi-tile RGBA, see realsr_oracle.c)
+    def rgba(img, seed):
+        h, w, _ = img.shape
+        r = np.random.default_rng(seed)
+        yy, xx = np.mgrid[0:h, 0:w]
+        a = np.clip((xx * 6 + yy * 3) % 256 + r.integers(-20, 20, (h, w)), 0, 255).astype(np.uint8)
+        a[: h // 4, : w // 3] = 255
+        a[h // 2:, w // 2:] = 0
+        return np.ascontiguousarray(np.dstack([img, a]))
+    cases.append(("rgba_noise_41x30_df2k_t200", rgba(noise(30, 41, 1006), 6), "models-DF2K", 200, 0))
+    cases.append(("rgba_natural_36x28_jpeg_t200", rgba(natural(28, 36, 1007), 7), "models-DF2K_JPEG", 200, 0))
+    only_new = "--only-new" in sys.argv
     manifest = {"generator": "oracle/gen_golden.py", "reference_binary": "oracle/_ref/oracle_ref_avx2 (ncnn b4ba207, AVX2+FMA, OpenMP)",
                 "prepadding": 10, "cases": []}
     flags = [l for l in open("/proc/cpuinfo") if l.startswith("model name")][:1]
     manifest["host_cpu"] = flags[0].split(":", 1)[1].strip() if flags else "?"
+    old = {}
+    if only_new and os.path.exists(os.path.join(GOLD, "manifest.json")):
+        old = {c["name"]: c for c in json.load(open(os.path.join(GOLD, "manifest.json")))["cases"]}
     for name, img, model, ts, tta in cases:
+        if name in old:
+            manifest["cases"].append(old[name])
+            continue
         out, info = run_ref(img, model, ts, tta)
         np.save(os.path.join(GOLD, name + ".in.npy"), img)
         np.save(os.path.join(GOLD, name + ".out.npy"), out)
         manifest["cases"].append({"name": name, "model": model, "tilesize": ts, "tta": tta, "h": img.shape[0],
-                                  "w": img.shape[1], "ref_seconds": info["seconds"]})
+                                  "w": img.shape[1], "c": int(img.shape[2]), "ref_seconds": info["seconds"]})
         print(name, info["seconds"], "s")
     json.dump(manifest, open(os.path.join(GOLD, "manifest.json"), "w"), indent=1)
 

@@ -23,7 +23,12 @@
  *                 gather/average :691-724.
  * The executor is a plain in-order interpreter over the 7 layer types the shipped graphs use
  * (Input, Convolution, Split, Concat, Eltwise, BinaryOp, Interp); arithmetic is fp32 throughout, like the
- * reference's -g -1 path.  RGB (3-channel) images only; the alpha path is a "next" row.
+ * reference's -g -1 path.  RGBA: the 4th channel is not run through the network but up-scaled bicubically (A = -0.75,
+ * ncnn layer/interp.cpp:178-249,:645-668 via realsr.cpp:129-140) and truncated by to_pixels without the +0.5 the colour
+ * channels get (realsr.cpp:809-812,:816-833).  The reference's CPU branch is only self-consistent for single-tile RGBA
+ * images (for several tiles it copies a halo-sized alpha plane into a tile-sized one, realsr.cpp:752,:811); per tile this
+ * restatement follows the GPU shaders instead (realsr_preproc.comp:79-88: alpha of the un-padded tile region only), which
+ * coincides with the CPU branch in the single-tile case -- that case is what the golden vectors pin.
  */
 #include <math.h>
 #include <stdint.h>
@@ -392,6 +397,64 @@ int rsr_oracle_net(rsr_oracle *o, const float *in, int h, int w, float *out)
     return ret;
 }
 
+/* ---- bicubic x4 of the alpha plane (layer/interp.cpp:178-249 coefficients, :251-330 two-pass resize) ------------ */
+
+static void interpolate_cubic(float fx, float *coeffs)
+{
+    const float A = -0.75f;
+    float fx0 = fx + 1, fx1 = fx, fx2 = 1 - fx;
+    coeffs[0] = A * fx0 * fx0 * fx0 - 5 * A * fx0 * fx0 + 8 * A * fx0 - 4 * A;
+    coeffs[1] = (A + 2) * fx1 * fx1 * fx1 - (A + 3) * fx1 * fx1 + 1;
+    coeffs[2] = (A + 2) * fx2 * fx2 * fx2 - (A + 3) * fx2 * fx2 + 1;
+    coeffs[3] = 1.f - coeffs[0] - coeffs[1] - coeffs[2];
+}
+
+void rsr_oracle_cubic_coeffs(int w, int outw, int *xofs, float *alpha)
+{
+    double scale = (double)w / outw;
+    for (int dx = 0; dx < outw; dx++) {
+        float fx = (float)((dx + 0.5) * scale - 0.5);
+        int sx = (int)floorf(fx);
+        fx -= sx;
+        float *a = alpha + dx * 4;
+        interpolate_cubic(fx, a);
+        if (sx <= -1) { sx = 1; a[0] = 1.f - a[3]; a[1] = a[3]; a[2] = 0.f; a[3] = 0.f; }
+        if (sx == 0) { sx = 1; a[0] = a[0] + a[1]; a[1] = a[2]; a[2] = a[3]; a[3] = 0.f; }
+        if (sx == w - 2) { sx = w - 3; a[3] = a[2] + a[3]; a[2] = a[1]; a[1] = a[0]; a[0] = 0.f; }
+        if (sx >= w - 1) { sx = w - 3; a[3] = 1.f - a[0]; a[2] = a[0]; a[1] = 0.f; a[0] = 0.f; }
+        xofs[dx] = sx;
+    }
+}
+
+/* src: w x h floats; dst: 4w x 4h floats */
+void rsr_oracle_bicubic4x(const float *src, int w, int h, float *dst)
+{
+    const int ow = w * 4, oh = h * 4;
+    int *xofs = (int *)malloc(sizeof(int) * (ow + oh));
+    int *yofs = xofs + ow;
+    float *alpha = (float *)malloc(sizeof(float) * 4 * (ow + oh));
+    float *beta = alpha + 4 * ow;
+    rsr_oracle_cubic_coeffs(w, ow, xofs, alpha);
+    rsr_oracle_cubic_coeffs(h, oh, yofs, beta);
+    float *rows = (float *)malloc(sizeof(float) * 4 * ow);
+    for (int dy = 0; dy < oh; dy++) {
+        const int sy = yofs[dy];
+        for (int k = 0; k < 4; k++) { /* horizontal pass of source rows sy-1 .. sy+2 */
+            const float *S = src + (size_t)(sy - 1 + k) * w;
+            float *r = rows + k * ow;
+            for (int dx = 0; dx < ow; dx++) {
+                const float *Sp = S + xofs[dx];
+                const float *a = alpha + dx * 4;
+                r[dx] = Sp[-1] * a[0] + Sp[0] * a[1] + Sp[1] * a[2] + Sp[2] * a[3];
+            }
+        }
+        const float *b = beta + dy * 4;
+        for (int dx = 0; dx < ow; dx++)
+            dst[(size_t)dy * ow + dx] = rows[dx] * b[0] + rows[ow + dx] * b[1] + rows[2 * ow + dx] * b[2] + rows[3 * ow + dx] * b[3];
+    }
+    free(rows); free(alpha); free(xofs);
+}
+
 /* ---- tile engine (src/realsr.cpp:525-838) ---------------------------------------------------------------- */
 
 static int imin(int a, int b) { return a < b ? a : b; }
@@ -417,7 +480,7 @@ static void reflect_pad(const float *src, int sh, int sw, float *dst, int top, i
 int rsr_oracle_process(rsr_oracle *o, const uint8_t *pixeldata, int w, int h, int channels, uint8_t *outdata,
                        int tilesize, int prepadding, int tta_mode, int num_threads)
 {
-    if (channels != 3) return -10;
+    if (channels != 3 && channels != 4) return -10;
 #ifdef _OPENMP
     if (num_threads > 0) omp_set_num_threads(num_threads);
 #endif
@@ -436,7 +499,7 @@ int rsr_oracle_process(rsr_oracle *o, const uint8_t *pixeldata, int w, int h, in
                 for (int y = 0; y < ch; y++)
                     for (int x = 0; x < cw; x++)
                         crop[((size_t)q * ch + y) * cw + x] =
-                            (float)pixeldata[((size_t)(in_y0 + y) * w + in_x0 + x) * 3 + q] * (1 / 255.f);
+                            (float)pixeldata[((size_t)(in_y0 + y) * w + in_x0 + x) * channels + q] * (1 / 255.f);
             /* reflect padding only where the tile touches the image border */
             const int pad_top = imax(P - yi * T, 0);
             const int pad_bottom = imax(imin((yi + 1) * T + P - h, P), 0);
@@ -508,15 +571,32 @@ int rsr_oracle_process(rsr_oracle *o, const uint8_t *pixeldata, int w, int h, in
                 if (r) { free(in0); free(res); return r; }
             }
             free(in0);
+            /* alpha: bicubic x4 of the un-padded tile region, raw 0..255 values, no +0.5 (see header) */
+            float *ares = NULL;
+            if (channels == 4) {
+                float *asrc = (float *)malloc(sizeof(float) * (size_t)tile_w_nopad * tile_h_nopad);
+                for (int y = 0; y < tile_h_nopad; y++)
+                    for (int x = 0; x < tile_w_nopad; x++)
+                        asrc[(size_t)y * tile_w_nopad + x] = (float)pixeldata[((size_t)(yi * T + y) * w + xi * T + x) * 4 + 3];
+                ares = (float *)malloc(sizeof(float) * (size_t)tw * th);
+                rsr_oracle_bicubic4x(asrc, tile_w_nopad, tile_h_nopad, ares);
+                free(asrc);
+            }
             /* to_pixels: (int) truncation, clamp to [0,255] (mat_pixel.cpp:158,:140-206) */
             for (int i = 0; i < th; i++) {
-                uint8_t *dst = outdata + ((size_t)(yi * scale * T + i) * w * scale + (size_t)xi * scale * T) * 3;
-                for (int j = 0; j < tw; j++)
+                uint8_t *dst = outdata + ((size_t)(yi * scale * T + i) * w * scale + (size_t)xi * scale * T) * channels;
+                for (int j = 0; j < tw; j++) {
                     for (int q = 0; q < 3; q++) {
                         int v = (int)res[((size_t)q * th + i) * tw + j];
-                        dst[j * 3 + q] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+                        dst[j * channels + q] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
                     }
+                    if (channels == 4) {
+                        int v = (int)ares[(size_t)i * tw + j];
+                        dst[j * 4 + 3] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+                    }
+                }
             }
+            free(ares);
             free(res);
         }
     }

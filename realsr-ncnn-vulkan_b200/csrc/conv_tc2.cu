@@ -246,7 +246,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                     if constexpr (MODE == CONV_LAST_U8) {
                         const int ii = yy - a.prepad_s, jx = x - a.prepad_s;
                         if (ii >= 0 && ii < td.crop_h && jx >= 0 && jx < td.crop_w) {
-                            uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + ii) * a.img_w + td.out_x0 + jx) * 3;
+                            uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + ii) * a.img_w + td.out_x0 + jx) * a.img_c;
 #pragma unroll
                             for (int j = 0; j < 3; j++) {
                                 int iv = (int)(o[j] * 255.f + 0.5f);

@@ -228,8 +228,8 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
 }
 
 // Runs the whole network on one batch of same-shape padded tiles (H x W network-input pixels each).
-int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, uint8_t* d_out, const std::vector<TileDesc>& tiles, int H, int W,
-              bool tta_out)
+int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, uint8_t* d_out, const std::vector<TileDesc>& tiles, int H,
+              int W, bool tta_out)
 {
     rsr_handle* h = c.h;
     Workspace* ws = c.ws;
@@ -269,7 +269,7 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, uint8_t* 
     // Conv_0 + preproc
     {
         FirstArgs f{};
-        f.img = d_img; f.img_w = img_w; f.img_h = img_h; f.tiles = d_tiles;
+        f.img = d_img; f.img_w = img_w; f.img_h = img_h; f.img_c = img_c; f.tiles = d_tiles;
         f.w = h->dm.w0; f.bias = h->dm.bias[0];
         f.H = H; f.W = W; f.B = B;
         f.d16 = D[0]; f.t32 = (float*)ws->t32.p; f.r32 = (float*)ws->r32.p; f.f32 = (float*)ws->f32.p;
@@ -327,7 +327,7 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, uint8_t* 
         ConvArgs a = base;
         a.H = 4 * H; a.W = 4 * W;
         a.mode = tta_out ? CONV_LAST_F32 : CONV_LAST_U8;
-        a.img_out = d_out; a.img_w = img_w * 4; a.img_h = img_h * 4;
+        a.img_out = d_out; a.img_w = img_w * 4; a.img_h = img_h * 4; a.img_c = img_c;
         a.prepad_s = h->prepadding * 4;
         a.tta_out = (float*)ws->tta.p;
         if ((r = conv(c, &mapU2, a, m.idx_last()))) return r;
@@ -335,7 +335,8 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, uint8_t* 
     return 0;
 }
 
-int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, int hh, uint8_t* d_out, long long* padded_out, long long* launches_out)
+int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, int hh, int ch, uint8_t* d_out, long long* padded_out,
+                      long long* launches_out)
 {
     const int T = h->tilesize, P = h->prepadding;
     const int xtiles = (w + T - 1) / T, ytiles = (hh + T - 1) / T;
@@ -364,7 +365,7 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
         if (!h->tta) {
             for (size_t i = 0; i < tl.size(); i += (size_t)mb) {
                 std::vector<TileDesc> batch(tl.begin() + i, tl.begin() + std::min(tl.size(), i + (size_t)mb));
-                if ((r = run_batch(c, d_in, w, hh, d_out, batch, H, W, false))) return r;
+                if ((r = run_batch(c, d_in, w, hh, ch, d_out, batch, H, W, false))) return r;
                 padded += (long long)batch.size() * H * W;
                 CK(cudaStreamSynchronize(ws->stream));  // `batch` (tile descriptors) must outlive the async copy
             }
@@ -387,7 +388,7 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
                     std::vector<TileDesc> batch;
                     for (size_t gi = 0; gi < n; gi++)
                         for (int v = half * 4; v < half * 4 + 4; v++) batch.push_back(all[gi * 8 + v]);
-                    if ((r = run_batch(c, d_in, w, hh, d_out, batch, half ? W : H, half ? H : W, true))) return r;
+                    if ((r = run_batch(c, d_in, w, hh, ch, d_out, batch, half ? W : H, half ? H : W, true))) return r;
                     CK(cudaStreamSynchronize(ws->stream));
                 }
                 // gather needs the 8 descs of every tile in slot order on the device
@@ -395,7 +396,7 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
                 CK(cudaMemcpyAsync(ws->tiles.p, all.data(), sizeof(TileDesc) * all.size(), cudaMemcpyHostToDevice, ws->stream));
                 TtaGatherArgs ga{};
                 ga.tta_out = (const float*)ws->tta.p; ga.tiles = (const TileDesc*)ws->tiles.p; ga.ngroups = (int)n;
-                ga.slot_stride = slot_stride; ga.img_out = d_out; ga.img_w = w * 4; ga.img_h = hh * 4; ga.prepad_s = P * 4;
+                ga.slot_stride = slot_stride; ga.img_out = d_out; ga.img_w = w * 4; ga.img_h = hh * 4; ga.img_c = ch; ga.prepad_s = P * 4;
                 int mw = 0, mh = 0;
                 for (size_t gi = 0; gi < n; gi++) { mw = std::max(mw, tl[i + gi].crop_w); mh = std::max(mh, tl[i + gi].crop_h); }
                 CK(launch_tta_gather(ga, mw, mh, ws->stream));
@@ -404,6 +405,12 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
                 padded += (long long)n * 8 * H * W;
             }
         }
+    }
+    if (ch == 4) {  // alpha: bicubic x4 per un-padded tile region, independent of the network
+        AlphaArgs aa{};
+        aa.img = d_in; aa.img_out = d_out; aa.img_w = w; aa.img_h = hh; aa.tilesize = T;
+        CK(launch_alpha_bicubic4x(aa, ws->stream));
+        c.launches++;
     }
     *padded_out = padded;
     *launches_out = c.launches;
@@ -425,7 +432,7 @@ int check_args(rsr_handle* h, const void* in, int w, int hh, int c, const void* 
     if (!h) return RSR_ERR_GENERIC;
     if (!h->loaded) return set_err(h, RSR_ERR_GENERIC, "rsr_process: no model loaded");
     if (!in || !out || w <= 0 || hh <= 0) return set_err(h, RSR_ERR_GENERIC, "rsr_process: bad image arguments");
-    if (c != 3) return set_err(h, RSR_ERR_GENERIC, "rsr_process: only 3-channel RGB images are supported (alpha path not implemented)");
+    if (c != 3 && c != 4) return set_err(h, RSR_ERR_GENERIC, "rsr_process: only 3-channel RGB and 4-channel RGBA images are supported");
     return 0;
 }
 
@@ -538,7 +545,7 @@ static int process_impl(rsr_handle* h, const uint8_t* in, int w, int hh, int c, 
     CK(cudaSetDevice(h->gpuid));
     Workspace* ws = acquire_ws(h);
     if (!ws) return set_err(h, RSR_ERR_CUDA, "cannot create stream/events");
-    const size_t in_bytes = (size_t)w * hh * 3, out_bytes = in_bytes * 16;
+    const size_t in_bytes = (size_t)w * hh * c, out_bytes = in_bytes * 16;
     const uint8_t* d_in = in;
     uint8_t* d_out = out;
     long long padded = 0, launches = 0;
@@ -552,7 +559,7 @@ static int process_impl(rsr_handle* h, const uint8_t* in, int w, int hh, int c, 
         }
         CK(cudaEventRecord(ws->ev0, ws->stream));
         if (host_buffers) CK(cudaMemcpyAsync(ws->img_in.p, in, in_bytes, cudaMemcpyHostToDevice, ws->stream));
-        if ((rr = process_on_device(h, ws, d_in, w, hh, d_out, &padded, &launches))) return rr;
+        if ((rr = process_on_device(h, ws, d_in, w, hh, c, d_out, &padded, &launches))) return rr;
         if (host_buffers) CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ws->stream));
         CK(cudaEventRecord(ws->ev1, ws->stream));
         CK(cudaStreamSynchronize(ws->stream));

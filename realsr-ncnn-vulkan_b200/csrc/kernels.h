@@ -54,6 +54,7 @@ struct ConvArgs {
     const TileDesc* tiles;
     uint8_t* img_out;
     int img_w, img_h;    // output image size (pixels)
+    int img_c;           // bytes per pixel of the output image (3 or 4)
     int prepad_s;        // prepadding*scale
     float* tta_out;
     int desc_mode;       // debug mask for timing experiments (0 in production): 1 no MMA, 2 no A loads, 4 no B loads, 8 no epilogue I/O
@@ -78,6 +79,7 @@ constexpr int CONV_P = 32;
 struct FirstArgs {
     const uint8_t* img;  // u8 HWC RGB source image on the device
     int img_w, img_h;
+    int img_c;           // bytes per pixel of the source image: 3 (RGB) or 4 (RGBA; alpha is ignored here)
     const TileDesc* tiles;
     const float* w;      // [64][3][3][3] fp32 (OIHW as in the .bin), bias [64]
     const float* bias;
@@ -101,8 +103,20 @@ struct TtaGatherArgs {
     size_t slot_stride;    // floats per slot
     uint8_t* img_out;
     int img_w, img_h;
+    int img_c;             // bytes per pixel of the output image (3 or 4)
     int prepad_s;
 };
 cudaError_t launch_tta_gather(const TtaGatherArgs& a, int max_crop_w, int max_crop_h, cudaStream_t stream);
+
+// Alpha channel of RGBA images: bicubic x4 (A = -0.75; ncnn layer/interp.cpp:178-249,:645-668, used by
+// src/realsr.cpp:129-140,:431-442) of the UN-PADDED tile region (realsr_preproc.comp:79-88), truncated to u8 like the
+// CPU branch's to_pixels (no +0.5), written into byte 3 of the RGBA output pixels.  One launch per image.
+struct AlphaArgs {
+    const uint8_t* img;    // RGBA source
+    uint8_t* img_out;      // RGBA result
+    int img_w, img_h;      // source size
+    int tilesize;
+};
+cudaError_t launch_alpha_bicubic4x(const AlphaArgs& a, cudaStream_t stream);
 
 }  // namespace rsr

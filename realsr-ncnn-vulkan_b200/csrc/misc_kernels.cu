@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(FIRST_THREADS) conv_first_kernel(const FirstAr
                 variant_to_base(td.variant, aa, bb, td.base_h, td.base_w, i, j);
                 const int X = reflect101(td.in_x0 + j, a.img_w);
                 const int Y = reflect101(td.in_y0 + i, a.img_h);
-                const uint8_t* px = a.img + ((size_t)Y * a.img_w + X) * 3;
+                const uint8_t* px = a.img + ((size_t)Y * a.img_w + X) * a.img_c;
                 v0 = (float)px[0] * (1 / 255.f);
                 v1 = (float)px[1] * (1 / 255.f);
                 v2 = (float)px[2] * (1 / 255.f);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) tta_gather_kernel(const TtaGatherArgs a)
     o[0] = (v0.x + v1.x + v2.x + v3.x + v4.x + v5.x + v6.x + v7.x) / 8;
     o[1] = (v0.y + v1.y + v2.y + v3.y + v4.y + v5.y + v6.y + v7.y) / 8;
     o[2] = (v0.z + v1.z + v2.z + v3.z + v4.z + v5.z + v6.z + v7.z) / 8;
-    uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + i) * a.img_w + td.out_x0 + j) * 3;
+    uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + i) * a.img_w + td.out_x0 + j) * a.img_c;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const int iv = (int)(o[c] * 255.f + 0.5f);
@@ -163,7 +163,65 @@ __global__ void __launch_bounds__(256) tta_gather_kernel(const TtaGatherArgs a)
     }
 }
 
+// cubic coefficients + source offset of output coordinate d (scale 1/4), with ncnn's border folding (interp.cpp:205-246)
+__device__ __forceinline__ int cubic_coeffs4(int d, int w, float (&a)[4])
+{
+    float fx = (float)((d + 0.5) * 0.25 - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    const float A = -0.75f;
+    const float fx0 = fx + 1, fx1 = fx, fx2 = 1 - fx;
+    a[0] = A * fx0 * fx0 * fx0 - 5 * A * fx0 * fx0 + 8 * A * fx0 - 4 * A;
+    a[1] = (A + 2) * fx1 * fx1 * fx1 - (A + 3) * fx1 * fx1 + 1;
+    a[2] = (A + 2) * fx2 * fx2 * fx2 - (A + 3) * fx2 * fx2 + 1;
+    a[3] = 1.f - a[0] - a[1] - a[2];
+    if (sx <= -1) { sx = 1; a[0] = 1.f - a[3]; a[1] = a[3]; a[2] = 0.f; a[3] = 0.f; }
+    if (sx == 0) { sx = 1; a[0] = a[0] + a[1]; a[1] = a[2]; a[2] = a[3]; a[3] = 0.f; }
+    if (sx == w - 2) { sx = w - 3; a[3] = a[2] + a[3]; a[2] = a[1]; a[1] = a[0]; a[0] = 0.f; }
+    if (sx >= w - 1) { sx = w - 3; a[3] = 1.f - a[0]; a[2] = a[0]; a[1] = 0.f; a[0] = 0.f; }
+    return sx;
+}
+
+__global__ void __launch_bounds__(256) alpha_bicubic4x_kernel(const AlphaArgs a)
+{
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;  // output pixel
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= a.img_w * 4 || Y >= a.img_h * 4) return;
+    const int T = a.tilesize;
+    // the tile this output pixel belongs to, and the tile's un-padded source region
+    const int xi = (X >> 2) / T, yi = (Y >> 2) / T;
+    const int tx0 = xi * T, ty0 = yi * T;
+    const int tw = min(tx0 + T, a.img_w) - tx0, th = min(ty0 + T, a.img_h) - ty0;
+    float ca[4], cb[4];
+    const int sx = cubic_coeffs4(X - tx0 * 4, tw, ca);
+    const int sy = cubic_coeffs4(Y - ty0 * 4, th, cb);
+    float rows[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        // rows sy-1 .. sy+2, columns sx-1 .. sx+2 of the tile; zero-weight taps may point outside: clamp the address only
+        const int yy = min(max(sy - 1 + k, 0), th - 1);
+        const uint8_t* S = a.img + ((size_t)(ty0 + yy) * a.img_w + tx0) * 4 + 3;
+        const float s0 = (float)S[(size_t)min(max(sx - 1, 0), tw - 1) * 4];
+        const float s1 = (float)S[(size_t)min(max(sx, 0), tw - 1) * 4];
+        const float s2 = (float)S[(size_t)min(max(sx + 1, 0), tw - 1) * 4];
+        const float s3 = (float)S[(size_t)min(max(sx + 2, 0), tw - 1) * 4];
+        // same operation order as ncnn (mul, then three fused multiply-adds), explicit so that nvcc cannot re-associate
+        rows[k] = __fmaf_rn(s3, ca[3], __fmaf_rn(s2, ca[2], __fmaf_rn(s1, ca[1], __fmul_rn(s0, ca[0]))));
+    }
+    const float v = __fmaf_rn(rows[3], cb[3], __fmaf_rn(rows[2], cb[2], __fmaf_rn(rows[1], cb[1], __fmul_rn(rows[0], cb[0]))));
+    const int iv = (int)v;
+    a.img_out[((size_t)Y * a.img_w * 4 + X) * 4 + 3] = (uint8_t)min(max(iv, 0), 255);
+}
+
 }  // namespace
+
+cudaError_t launch_alpha_bicubic4x(const AlphaArgs& a, cudaStream_t stream)
+{
+    dim3 block(32, 8);
+    dim3 grid((a.img_w * 4 + 31) / 32, (a.img_h * 4 + 7) / 8);
+    alpha_bicubic4x_kernel<<<grid, block, 0, stream>>>(a);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_conv_first(const FirstArgs& a, cudaStream_t stream)
 {

@@ -97,7 +97,7 @@ class RealSR:
     def process(self, inimage, outimage):
         """int RealSR::process(const ncnn::Mat& in, ncnn::Mat& out) const -- reference: src/realsr.cpp:145-523.
 
-        inimage: uint8 ndarray (h, w, 3), C-contiguous, RGB; outimage: preallocated uint8 ndarray (4h, 4w, 3),
+        inimage: uint8 ndarray (h, w, c), c = 3 (RGB) or 4 (RGBA), C-contiguous; outimage: preallocated uint8 ndarray (4h, 4w, c),
         written in place (the reference's caller allocates it too, src/main.cpp:276).  Returns 0 on success,
         a negative code otherwise (message in last_error())."""
         if inimage.dtype != np.uint8 or inimage.ndim != 3 or not inimage.flags.c_contiguous:

@@ -34,7 +34,7 @@ def engine(model, tta=False):
 def run(model, img, tilesize, tta=False):
     e = engine(model, tta)
     e.tilesize = tilesize
-    out = np.zeros((img.shape[0] * 4, img.shape[1] * 4, 3), dtype=np.uint8)
+    out = np.zeros((img.shape[0] * 4, img.shape[1] * 4, img.shape[2]), dtype=np.uint8)
     assert e.process(img, out) == 0, e.last_error()
     return out
 
@@ -54,7 +54,10 @@ def test_golden_vs_reference_cpu_path(case, models_dir):
     """CUDA path vs the committed outputs of the real reference CPU path (oracle/_ref), same tile size"""
     img, gold = golden(case["name"])
     out = run(case["model"], img, case["tilesize"], bool(case["tta"]))
-    check_contract(diff_stats(out, gold), natural=not case["name"].startswith(("noise", "cfg1_noise")))
+    check_contract(diff_stats(out[..., :3], gold[..., :3]), natural="noise" not in case["name"])
+    if img.shape[2] == 4:  # alpha: bicubic x4 in fp32 with the reference's operation order -> expected bit-exact, 1 LSB allowed
+        s = diff_stats(out[..., 3], gold[..., 3])
+        assert s["max"] <= 1 and s["frac_diff"] <= 0.001, s
 
 
 @pytest.mark.parametrize("idx,H,W", [(1, 37, 45), (2, 16, 30), (3, 17, 31), (4, 64, 61), (5, 33, 95), (346, 40, 40), (347, 35, 62), (350, 29, 47)])
@@ -84,6 +87,22 @@ def test_fresh_inputs_vs_oracle_port(w, h, tile, tta, models_dir):
     img = np.random.default_rng(w * 100 + h).integers(0, 256, (h, w, 3), dtype=np.uint8)
     ref = Oracle("models-DF2K_JPEG").process(img, tile, tta=tta)
     check_contract(diff_stats(run("models-DF2K_JPEG", img, tile, tta), ref), natural=False)
+
+
+@pytest.mark.parametrize("w,h,tile,tta", [(70, 45, 32, False), (40, 33, 200, True)])
+def test_rgba_vs_oracle_port(w, h, tile, tta, models_dir):
+    """RGBA incl. several tiles: alpha is up-scaled per un-padded tile region (the reference's GPU-shader semantics,
+    realsr_preproc.comp:79-88; its CPU branch is only defined for one tile), colour channels as for RGB"""
+    rng = np.random.default_rng(w + h)
+    img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img[..., 3] = np.clip((xx * 5 + yy * 7) % 256, 0, 255).astype(np.uint8)
+    img[: h // 3, : w // 3, 3] = 255
+    ref = Oracle("models-DF2K").process(img, tile, tta=tta)
+    out = run("models-DF2K", img, tile, tta)
+    check_contract(diff_stats(out[..., :3], ref[..., :3]), natural=False)
+    s = diff_stats(out[..., 3], ref[..., 3])
+    assert s["max"] <= 1 and s["frac_diff"] <= 0.001, s
 
 
 def test_constant_and_extreme_images(models_dir):
@@ -150,7 +169,7 @@ def test_errors_are_reported(models_dir):
     e = rb.RealSR(0)
     assert e.process(np.zeros((8, 8, 3), np.uint8), np.zeros((32, 32, 3), np.uint8)) != 0 and "no model" in e.last_error()
     g = engine("models-DF2K")
-    assert g.process(np.zeros((8, 8, 4), np.uint8), np.zeros((32, 32, 4), np.uint8)) != 0  # RGBA not implemented: loud
+    assert g.process(np.zeros((8, 8, 2), np.uint8), np.zeros((32, 32, 2), np.uint8)) != 0  # only RGB / RGBA
     assert g.kernel_launches() > 0
 
 
