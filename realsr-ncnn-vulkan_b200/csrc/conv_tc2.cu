@@ -85,7 +85,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
     if (threadIdx.x == 0) {
         for (int i = 0; i < NA_MAX; i++) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
         mbar_init(&bars->w_full, 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 2 * NEPI); }
+        for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], NEPI); }  // acc_empty: 4 warps per group x 2 CTAs
         mbar_fence_init();
         for (int i = 0; i < 3; i++) tma_prefetch_desc(&maps.m[i]);
         tma_prefetch_desc(&maps.w);
@@ -162,13 +162,17 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
             const uint32_t w_base = smem_u32(smW);
             for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
                 const int buf = ti & 1;
+                const bool ts_on = a.dbg_ts != nullptr && cluster_id == 0 && ti < 64 && leader;
+                if (ts_on) a.dbg_ts[ti * 8 + 0] = clock64();
                 mbar_wait(&bars->acc_empty[buf], ((ti >> 1) & 1) ^ 1);
                 tc_fence_after();
+                if (ts_on) a.dbg_ts[ti * 8 + 1] = clock64();
                 const uint32_t acc = tmem_base + buf * ACC_COLS;
                 for (int c = 0; c < nchunk; c++, ca++) {
                     const int sA = ca % NA;
                     mbar_wait(&bars->a_full[sA], (ca / NA) & 1);
                     tc_fence_after();
+                    if (ts_on && c == 0) a.dbg_ts[ti * 8 + 2] = clock64();
                     const int rem = a.cin - c * 64;
                     const int ksteps = rem >= 64 ? 4 : (rem >> 4);
                     const uint32_t a_base = smem_u32(smA + sA * A_STAGE);
@@ -190,180 +194,195 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                     if (leader) umma2_commit(&bars->a_empty[sA], 3);
                 }
                 if (leader) umma2_commit(&bars->acc_full[buf], 3);
+                if (ts_on) a.dbg_ts[ti * 8 + 3] = clock64();
             }
         }
     } else if (warp == 2) {
         // weight warp: its work (the one-time resident-weight fetch) happened in the prologue
     } else {
-        // ---------------- epilogue: warps 3..10; TMEM lane quarter = warp % 4; M-tile = (warp-3)/4 ----------------
+        // ---------------- epilogue: warps 3..10 in two groups of four ----------------
+        // Group g = (warp-3)/4 owns accumulator set g, i.e. every second work tile; inside a group warp q4 = warp % 4
+        // (its TMEM lane quarter) handles row q4 of both M-tiles.  Two tiles are therefore in the epilogue stage at any
+        // time and each group has two tile periods to drain its set (timestamps showed a single 8-warp epilogue taking
+        // 3-5 k clk per tile and stalling the 1-4 k clk MMA stream of the Cout=32 convs).
         const int q4 = warp & 3;
         const int ew = warp - 3;
-        const int mt = ew >> 2;
+        const int group = ew >> 2;
         uint32_t* stg = reinterpret_cast<uint32_t*>(smStage + ew * STAGE_BYTES);  // [32 rows][20 words]
         const int tr = lane >> 2, tc = lane & 3;
         const bool dbg_noepi = (a.desc_mode & 8) != 0;
-        const uint32_t acc_empty_leader[2] = {mapa_u32(smem_u32(&bars->acc_empty[0]), 0), mapa_u32(smem_u32(&bars->acc_empty[1]), 0)};
+        const uint32_t acc_empty_leader = mapa_u32(smem_u32(&bars->acc_empty[group]), 0);
         int ti = 0;
         for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
+            if ((ti & 1) != group) continue;
             const int b = t / tiles_per_img, rem = t - b * tiles_per_img;
             const int by = rem / tiles_x, tx = rem - by * tiles_x;
             const int x0 = tx * BW;
-            const int yy = by * BAND + (int)rank * BH + mt * 4 + q4;
-            const int buf = ti & 1;
-            const bool vrow = yy < a.H;
+            const int buf = group;
+            int yy[2];
+            size_t rowpix[2];
+            bool vrow[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                yy[i] = by * BAND + (int)rank * BH + i * 4 + q4;
+                vrow[i] = yy[i] < a.H && !dbg_noepi;
+                rowpix[i] = ((size_t)b * a.H + yy[i]) * a.W + x0;
+            }
             bool vcol[4];
 #pragma unroll
-            for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < a.W) && vrow && !dbg_noepi;
-            const size_t rowpix = ((size_t)b * a.H + yy) * a.W + x0;
+            for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < a.W);
+            // residual-stream operands of one (M-tile, 32-channel block), fetched one block ahead of use
             float4 res[2][4];
-            auto load_res = [&](int nb) {
+            auto load_res = [&](int i, int nb, float4 (&dst)[2][4]) {
                 if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
-                    const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix * 64 + nb * 32 + tc * 4;
+                    const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + nb * 32 + tc * 4;
 #pragma unroll
                     for (int hf = 0; hf < 2; hf++)
 #pragma unroll
                         for (int r = 0; r < 4; r++)
-                            if (vcol[r]) res[hf][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
+                            if (vcol[r] && vrow[i]) dst[hf][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
                 }
             };
-            load_res(0);
+            load_res(0, 0, res);
+            // (An L2 prefetch of the next tile's residual rows was tried and measured 5 % slower end to end: the Cout=64
+            // convs are HBM-bandwidth-bound in situ -- 1.44 GB per launch at 4.5 TB/s -- not latency-bound.)
+            const bool ts_on = a.dbg_ts != nullptr && cluster_id == 0 && ti < 64 && is_leader && (ew & 3) == 0 && lane == 0;
+            if (ts_on) a.dbg_ts[ti * 8 + 4] = clock64();
             mbar_wait(&bars->acc_full[buf], (ti >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS + mt * DCOLS;
-            if constexpr (NREAL == 16) {
-                uint32_t v[32], u[16];
-                tmem_ld32(taddr, v);
-                tmem_ld16(taddr + 32, u);
-                tmem_ld_wait();
-                float o[3];
+            if (ts_on) a.dbg_ts[ti * 8 + 5] = clock64();
 #pragma unroll
-                for (int j = 0; j < 3; j++)
-                    o[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 1) +
-                           __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 2) + s_bias[j];
-                const int x = x0 + lane;
-                if (lane < BW && x < a.W && vrow && !dbg_noepi) {
-                    const TileDesc td = a.tiles[b];
-                    if constexpr (MODE == CONV_LAST_U8) {
-                        const int ii = yy - a.prepad_s, jx = x - a.prepad_s;
-                        if (ii >= 0 && ii < td.crop_h && jx >= 0 && jx < td.crop_w) {
-                            uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + ii) * a.img_w + td.out_x0 + jx) * a.img_c;
+            for (int i = 0; i < 2; i++) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS + i * DCOLS;
+                if constexpr (NREAL == 16) {
+                    uint32_t v[32], u[16];
+                    tmem_ld32(taddr, v);
+                    tmem_ld16(taddr + 32, u);
+                    tmem_ld_wait();
+                    float o[3];
 #pragma unroll
-                            for (int j = 0; j < 3; j++) {
-                                int iv = (int)(o[j] * 255.f + 0.5f);
-                                dst[j] = (uint8_t)min(max(iv, 0), 255);
+                    for (int j = 0; j < 3; j++)
+                        o[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 1) +
+                               __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 2) + s_bias[j];
+                    const int x = x0 + lane;
+                    if (lane < BW && x < a.W && vrow[i]) {
+                        const TileDesc td = a.tiles[b];
+                        if constexpr (MODE == CONV_LAST_U8) {
+                            const int ii = yy[i] - a.prepad_s, jx = x - a.prepad_s;
+                            if (ii >= 0 && ii < td.crop_h && jx >= 0 && jx < td.crop_w) {
+                                uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + ii) * a.img_w + td.out_x0 + jx) * a.img_c;
+#pragma unroll
+                                for (int j = 0; j < 3; j++) {
+                                    int iv = (int)(o[j] * 255.f + 0.5f);
+                                    dst[j] = (uint8_t)min(max(iv, 0), 255);
+                                }
                             }
+                        } else {
+                            float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)a.H * a.W) + (size_t)yy[i] * a.W + x;
+                            *dst = make_float4(o[0], o[1], o[2], 0.f);
                         }
-                    } else {
-                        float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)a.H * a.W) + (size_t)yy * a.W + x;
-                        *dst = make_float4(o[0], o[1], o[2], 0.f);
                     }
-                }
-            } else if constexpr (MODE == CONV_STORE16) {
+                } else if constexpr (MODE == CONV_STORE16) {
 #pragma unroll
-                for (int nb = 0; nb < NREAL / 32; nb++) {
-                    float f[32];
-                    if constexpr (NREAL == 32) {  // D[0:32] + right neighbour's D[32:64] + second right neighbour's D[64:96]
-                        uint32_t v[32], u[32], w[32];
-                        tmem_ld32(taddr, v);
-                        tmem_ld32(taddr + 32, u);
-                        tmem_ld32(taddr + 64, w);
-                        tmem_ld_wait();
+                    for (int nb = 0; nb < NREAL / 32; nb++) {
+                        float f[32];
+                        if constexpr (NREAL == 32) {  // D[0:32] + right neighbour's D[32:64] + second right neighbour's D[64:96]
+                            uint32_t v[32], u[32], w[32];
+                            tmem_ld32(taddr, v);
+                            tmem_ld32(taddr + 32, u);
+                            tmem_ld32(taddr + 64, w);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            f[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
-                                   __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2) + s_bias[j];
-                    } else {  // D[nb*32..] + right neighbour's D[64 + nb*32..]
+                            for (int j = 0; j < 32; j++)
+                                f[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
+                                       __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2) + s_bias[j];
+                        } else {  // D[nb*32..] + right neighbour's D[64 + nb*32..]
+                            uint32_t v[32], u[32];
+                            tmem_ld32(taddr + nb * 32, v);
+                            tmem_ld32(taddr + 64 + nb * 32, u);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                f[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) + s_bias[nb * 32 + j];
+                        }
+                        if (a.act == 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) =
+                                make_uint4(pack_h2(f[8 * k + 0], f[8 * k + 1]), pack_h2(f[8 * k + 2], f[8 * k + 3]),
+                                           pack_h2(f[8 * k + 4], f[8 * k + 5]), pack_h2(f[8 * k + 6], f[8 * k + 7]));
+                        __syncwarp();
+                        __half* orow = a.out16 + rowpix[i] * a.out_cs + a.out_co + nb * 32 + tc * 8;
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const uint4 o = *reinterpret_cast<const uint4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
+                            if (vcol[r] && vrow[i]) *reinterpret_cast<uint4*>(orow + (size_t)(tr + 8 * r) * a.out_cs) = o;
+                        }
+                        __syncwarp();
+                    }
+                } else {
+                    // CONV_RDB_OUT / CONV_TRUNK (Cout = 64): fp32 math against the residual stream in the transposed domain
+#pragma unroll
+                    for (int nb = 0; nb < 2; nb++) {
                         uint32_t v[32], u[32];
                         tmem_ld32(taddr + nb * 32, v);
                         tmem_ld32(taddr + 64 + nb * 32, u);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; j++)
-                            f[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) + s_bias[nb * 32 + j];
-                    }
-                    if (a.act == 2) {
+                            v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1));
+                        float4 nxt[2][4];
+                        {   // prefetch the residual operands of the next (M-tile, 32-channel block)
+                            const int ni = nb == 1 ? i + 1 : i, nnb = nb ^ 1;
+                            if (ni < 2) load_res(ni, nnb, nxt);
+                        }
 #pragma unroll
-                        for (int j = 0; j < 32; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
-                    }
+                        for (int hf = 0; hf < 2; hf++) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) =
-                            make_uint4(pack_h2(f[8 * k + 0], f[8 * k + 1]), pack_h2(f[8 * k + 2], f[8 * k + 3]),
-                                       pack_h2(f[8 * k + 4], f[8 * k + 5]), pack_h2(f[8 * k + 6], f[8 * k + 7]));
-                    __syncwarp();
-                    __half* orow = a.out16 + rowpix * a.out_cs + a.out_co + nb * 32 + tc * 8;
+                            for (int k = 0; k < 4; k++)
+                                *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) = make_uint4(v[16 * hf + 4 * k], v[16 * hf + 4 * k + 1], v[16 * hf + 4 * k + 2], v[16 * hf + 4 * k + 3]);
+                            __syncwarp();
+                            const int ch0 = nb * 32 + hf * 16 + tc * 4;
+                            const float4 bb = *reinterpret_cast<const float4*>(&s_bias[ch0]);
+                            float4 acc4[4];
 #pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const uint4 o = *reinterpret_cast<const uint4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
-                        if (vcol[r]) *reinterpret_cast<uint4*>(orow + (size_t)(tr + 8 * r) * a.out_cs) = o;
-                    }
-                    __syncwarp();
-                }
-            } else {
-                // CONV_RDB_OUT / CONV_TRUNK (Cout = 64): fp32 math against the residual stream in the transposed domain
-#pragma unroll
-                for (int nb = 0; nb < 2; nb++) {
-                    uint32_t v[32], u[32];
-                    tmem_ld32(taddr + nb * 32, v);
-                    tmem_ld32(taddr + 64 + nb * 32, u);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1));
-                    float4 nxt[2][4];
-#pragma unroll
-                    for (int hf = 0; hf < 2; hf++) {
-#pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) = make_uint4(v[16 * hf + 4 * k], v[16 * hf + 4 * k + 1], v[16 * hf + 4 * k + 2], v[16 * hf + 4 * k + 3]);
-                        __syncwarp();
-                        const int ch0 = nb * 32 + hf * 16 + tc * 4;
-                        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[ch0]);
-                        float4 acc4[4];
-#pragma unroll
-                        for (int r = 0; r < 4; r++) acc4[r] = *reinterpret_cast<const float4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
-                        __syncwarp();
-                        if (hf == 0 && nb == 0) {  // prefetch the residual operands of the second 32-channel block
-                            const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix * 64 + 32 + tc * 4;
-#pragma unroll
-                            for (int h2 = 0; h2 < 2; h2++)
+                            for (int r = 0; r < 4; r++) acc4[r] = *reinterpret_cast<const float4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
+                            __syncwarp();
+                            float4 rr[4];
+                            if (MODE == CONV_RDB_OUT && a.rrdb_end) {
 #pragma unroll
                                 for (int r = 0; r < 4; r++)
-                                    if (vcol[r]) nxt[h2][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + h2 * 16);
-                        }
-                        float4 rr[4];
-                        if (MODE == CONV_RDB_OUT && a.rrdb_end) {
-#pragma unroll
-                            for (int r = 0; r < 4; r++)
-                                if (vcol[r]) rr[r] = *reinterpret_cast<const float4*>(a.r32 + (rowpix + tr + 8 * r) * 64 + ch0);
-                        }
-#pragma unroll
-                        for (int r = 0; r < 4; r++) {
-                            float4 o;
-                            if constexpr (MODE == CONV_RDB_OUT) {
-                                o.x = (acc4[r].x + bb.x) * 0.2f + res[hf][r].x;
-                                o.y = (acc4[r].y + bb.y) * 0.2f + res[hf][r].y;
-                                o.z = (acc4[r].z + bb.z) * 0.2f + res[hf][r].z;
-                                o.w = (acc4[r].w + bb.w) * 0.2f + res[hf][r].w;
-                                if (a.rrdb_end) {
-                                    o.x = o.x * 0.2f + rr[r].x; o.y = o.y * 0.2f + rr[r].y;
-                                    o.z = o.z * 0.2f + rr[r].z; o.w = o.w * 0.2f + rr[r].w;
-                                }
-                            } else {
-                                o.x = acc4[r].x + bb.x + res[hf][r].x; o.y = acc4[r].y + bb.y + res[hf][r].y;
-                                o.z = acc4[r].z + bb.z + res[hf][r].z; o.w = acc4[r].w + bb.w + res[hf][r].w;
+                                    if (vcol[r] && vrow[i]) rr[r] = *reinterpret_cast<const float4*>(a.r32 + (rowpix[i] + tr + 8 * r) * 64 + ch0);
                             }
-                            if (vcol[r]) {
-                                const size_t px = rowpix + tr + 8 * r;
+#pragma unroll
+                            for (int r = 0; r < 4; r++) {
+                                float4 o;
                                 if constexpr (MODE == CONV_RDB_OUT) {
-                                    if (a.rrdb_end) *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0) = o;
-                                    *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o;
+                                    o.x = (acc4[r].x + bb.x) * 0.2f + res[hf][r].x;
+                                    o.y = (acc4[r].y + bb.y) * 0.2f + res[hf][r].y;
+                                    o.z = (acc4[r].z + bb.z) * 0.2f + res[hf][r].z;
+                                    o.w = (acc4[r].w + bb.w) * 0.2f + res[hf][r].w;
+                                    if (a.rrdb_end) {
+                                        o.x = o.x * 0.2f + rr[r].x; o.y = o.y * 0.2f + rr[r].y;
+                                        o.z = o.z * 0.2f + rr[r].z; o.w = o.w * 0.2f + rr[r].w;
+                                    }
+                                } else {
+                                    o.x = acc4[r].x + bb.x + res[hf][r].x; o.y = acc4[r].y + bb.y + res[hf][r].y;
+                                    o.z = acc4[r].z + bb.z + res[hf][r].z; o.w = acc4[r].w + bb.w + res[hf][r].w;
                                 }
-                                *reinterpret_cast<uint2*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                                if (vcol[r] && vrow[i]) {
+                                    const size_t px = rowpix[i] + tr + 8 * r;
+                                    if constexpr (MODE == CONV_RDB_OUT) {
+                                        if (a.rrdb_end) *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0) = o;
+                                        *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o;
+                                    }
+                                    *reinterpret_cast<uint2*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                                }
                             }
                         }
-                    }
-                    if (nb == 0) {
 #pragma unroll
                         for (int h2 = 0; h2 < 2; h2++)
 #pragma unroll
@@ -371,10 +390,13 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                     }
                 }
             }
-            // accumulator set drained by this warp: tell the leader's MMA issuer (remote arrive from the peer CTA)
+            // accumulator set drained by this warp: tell the leader's MMA issuer.  Plain (CTA-scope release) remote arrive:
+            // only the TMEM reads have to be ordered (tcgen05 fence above); a cluster-scope release would also wait for
+            // this thread's global stores to drain.
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc_empty_leader[buf]);
+            if (lane == 0) mbar_arrive_remote(acc_empty_leader);
+            if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
         }
     }
 

@@ -10,6 +10,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -671,9 +672,27 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     a.tiles = d_td; a.tta_out = d_f;
     a.mode = npad == 16 ? CONV_LAST_F32 : CONV_STORE16;
     a.desc_mode = h->desc_mode;
-    if (h->conv_impl == 2) CK(launch_conv3x3_tc2(&map, a, npad, 0));
-    else CK(launch_conv3x3_tc(&map, a, npad, 0));
+    long long* d_ts = nullptr;
+    if (getenv("RSR_DBG_TS")) {
+        CK(cudaMalloc(&d_ts, 64 * 8 * sizeof(long long)));
+        CK(cudaMemset(d_ts, 0, 64 * 8 * sizeof(long long)));
+        a.dbg_ts = d_ts;
+    }
+    for (int rep = 0; rep < (d_ts ? 2 : 1); rep++) {
+        if (h->conv_impl == 2) CK(launch_conv3x3_tc2(&map, a, npad, 0));
+        else CK(launch_conv3x3_tc(&map, a, npad, 0));
+    }
     CK(cudaDeviceSynchronize());
+    if (d_ts) {  // bring-up: per-tile pipeline timestamps of cluster 0 (clock64 of the leader SM)
+        std::vector<long long> ts(64 * 8);
+        CK(cudaMemcpy(ts.data(), d_ts, ts.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const long long t0 = ts[0];
+        fprintf(stderr, "tile: mma_wait_start mma_acc_ready mma_a0_ready mma_issued | epi_wait_start epi_acc_full epi_done   (clk since first)\n");
+        for (int i = 0; i < 64 && ts[i * 8 + 0]; i++)
+            fprintf(stderr, "%3d: %8lld %8lld %8lld %8lld | %8lld %8lld %8lld\n", i, ts[i * 8 + 0] - t0, ts[i * 8 + 1] - t0, ts[i * 8 + 2] - t0,
+                    ts[i * 8 + 3] - t0, ts[i * 8 + 4] - t0, ts[i * 8 + 5] - t0, ts[i * 8 + 6] - t0);
+        cudaFree(d_ts);
+    }
     if (npad == 16) {
         std::vector<float> tmp(npx * 4);
         CK(cudaMemcpy(tmp.data(), d_f, npx * 16, cudaMemcpyDeviceToHost));

@@ -57,6 +57,7 @@ struct ConvArgs {
     int img_c;           // bytes per pixel of the output image (3 or 4)
     int prepad_s;        // prepadding*scale
     float* tta_out;
+    long long* dbg_ts;   // optional (bring-up): per-tile clock64 stamps of cluster 0, 8 slots per tile, see conv_tc2.cu
     int desc_mode;       // debug mask for timing experiments (0 in production): 1 no MMA, 2 no A loads, 4 no B loads, 8 no epilogue I/O
 };
 

@@ -179,6 +179,11 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// same with the default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) does
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA loads issued by either CTA of a pair; data lands in the issuing CTA's smem, completion bytes are signalled on the
 // mbarrier at cluster address `bar_cluster` (the leader CTA's barrier)
 __device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2, int c3)

@@ -146,12 +146,6 @@ __global__ void __launch_bounds__(128, 1) mma_bench(int iters, int mode, int nac
 }
 
 // ---- cta_group::2: one instruction drives the tensor cores of both SMs of a CTA pair (M = 256) -----------------------------
-__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc),
-                 "l"(b_desc), "r"(idesc), "r"(acc)
-                 : "memory");
-}
 template <int N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma2_bench(int iters, long long* out_cycles)
 {
@@ -336,15 +330,94 @@ void run_stream(const char* name, size_t span, int chunk, int depth, int ctas_pe
     cudaFree(d);
 }
 
+// ---- TMA tensor (tiled, SWIZZLE_128B) box streaming: the conv kernel's activation load pattern in isolation -------------
+#include <cuda.h>
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+__global__ void __launch_bounds__(128, 1) box_bench(const __grid_constant__ CUtensorMap map, int box_bytes, int box_rows, int depth, int W, int H, int B,
+                                                    int nrounds, long long* out_cycles)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bars[8];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < depth; i++) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int tiles_x = (W + 29) / 30, tiles_y = (H + box_rows - 3) / (box_rows - 2);
+        const int per_img = tiles_x * tiles_y, ntiles = per_img * B;
+        long long t0 = clock64();
+        int issued = 0, done = 0;
+        for (int r = 0; r < nrounds; r++)
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                if (issued - done >= depth) { mbar_wait(&bars[done % depth], (done / depth) & 1); done++; }
+                const int b = t / per_img, rem = t - b * per_img, ty = rem / tiles_x, tx = rem - ty * tiles_x;
+                const int s = issued % depth;
+                mbar_expect_tx(&bars[s], box_bytes);
+                tma_load_4d(smem + (size_t)s * (box_bytes + 1024), &map, &bars[s], 0, tx * 30 - 1, ty * (box_rows - 2) - 1, b);
+                issued++;
+            }
+        while (done < issued) { mbar_wait(&bars[done % depth], (done / depth) & 1); done++; }
+        out_cycles[blockIdx.x] = clock64() - t0;
+    }
+}
+void run_box(int box_rows, int depth)
+{
+    const int W = 420, H = 420, B = 8;
+    void* buf;
+    const size_t bytes = (size_t)B * H * W * 128;
+    CK(cudaMalloc(&buf, bytes));
+    CK(cudaMemset(buf, 1, bytes));
+    void* fnp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &q));
+    CUtensorMap map;
+    cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+    cuuint32_t box[4] = {64, 32, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (((EncodeTiledFn)fnp)(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, buf, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode failed\n"); exit(1); }
+    const int box_bytes = box_rows * 32 * 128;
+    const int smem = 1024 + depth * (box_bytes + 1024);
+    CK(cudaFuncSetAttribute(box_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    long long* d;
+    CK(cudaMalloc(&d, 148 * 8));
+    const int nrounds = 6;
+    box_bench<<<148, 128, smem>>>(map, box_bytes, box_rows, depth, W, H, B, 1, d);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    box_bench<<<148, 128, smem>>>(map, box_bytes, box_rows, depth, W, H, B, nrounds, d);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const int tiles = ((W + 29) / 30) * ((H + box_rows - 3) / (box_rows - 2)) * B;
+    const double moved = (double)tiles * box_bytes * nrounds, useful = (double)bytes * nrounds;
+    printf("TMA box {64ch,32px,%2d rows} depth %d: %.2f TB/s moved into smem, %.2f TB/s of distinct tensor bytes (%.3f ms)\n", box_rows, depth,
+           moved / (ms * 1e-3) / 1e12, useful / (ms * 1e-3) / 1e12, ms);
+    cudaFree(buf);
+    cudaFree(d);
+}
+
 int main()
 {
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, 0));
     printf("%s, %d SMs, clock %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
-    run_mma2<32>();
-    run_mma2<64>();
-    run_mma2<128>();
-    run_mma2<256>();
+    run_box(10, 2);
+    run_box(10, 3);
+    run_box(10, 4);
+    run_box(10, 5);
+    run_box(18, 2);
+    run_box(18, 3);
+    run_box(34, 1);
+    run_stream("HBM", (size_t)4096 << 20, 40 << 10, 4, 1);
 
     return 0;
 }
