@@ -235,12 +235,26 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
             float4 res[2][4];
             auto load_res = [&](int i, int nb, float4 (&dst)[2][4]) {
                 if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
-                    const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + nb * 32 + tc * 4;
+                    if (MODE == CONV_RDB_OUT && a.res16) {  // fp16 RDB input (already in the dense buffer): 128 B instead of 256 B per pixel
+                        const __half* base = a.res16 + rowpix[i] * 64 + nb * 32 + tc * 4;
 #pragma unroll
-                    for (int hf = 0; hf < 2; hf++)
+                        for (int hf = 0; hf < 2; hf++)
 #pragma unroll
-                        for (int r = 0; r < 4; r++)
-                            if (vcol[r] && vrow[i]) dst[hf][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
+                            for (int r = 0; r < 4; r++)
+                                if (vcol[r] && vrow[i]) {
+                                    const uint2 hv = *reinterpret_cast<const uint2*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
+                                    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
+                                    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
+                                    dst[hf][r] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                                }
+                    } else {
+                        const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + nb * 32 + tc * 4;
+#pragma unroll
+                        for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                            for (int r = 0; r < 4; r++)
+                                if (vcol[r] && vrow[i]) dst[hf][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
+                    }
                 }
             };
             load_res(0, 0, res);
@@ -377,7 +391,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                                     const size_t px = rowpix[i] + tr + 8 * r;
                                     if constexpr (MODE == CONV_RDB_OUT) {
                                         if (a.rrdb_end) *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0) = o;
-                                        *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o;
+                                        if (!a.res16) *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o;
                                     }
                                     *reinterpret_cast<uint2*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
                                 }

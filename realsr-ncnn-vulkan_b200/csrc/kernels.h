@@ -49,6 +49,8 @@ struct ConvArgs {
     float* t32;
     float* r32;
     const float* f32;
+    const __half* res16;  // CONV_RDB_OUT, optional: take the RDB input from this fp16 plane (64 ch/px) instead of T32 and do
+                          // not write T32 ("residual_fp16" engine option; the RRDB-level skip R32 stays fp32)
     int rrdb_end;
     // CONV_LAST_*
     const TileDesc* tiles;
