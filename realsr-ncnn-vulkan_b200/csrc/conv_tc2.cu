@@ -8,7 +8,7 @@
 // 75 (SS) / 52 (.ws) clk at N=64.  So here:
 //   * a cluster of 2 CTAs works on a 16 x 30-pixel band: CTA r owns rows 8r..8r+7 (2 M-tiles, its own 40 KB A box),
 //   * every MMA is N=128 where the tap grouping can fill it: Cout=64 -> taps (ky,0)+(ky,1) in one N=128 MMA, (ky,2) as
-//     N=64; Cout=32 -> all three taps of a kernel row in one N=128 MMA (96 useful columns); Cout=3 -> one N=64 MMA,
+//     N=64; Cout=32 -> all three taps of a kernel row in one N=96 MMA (no padding); Cout=3 -> one N=64 MMA,
 //   * each CTA streams only ITS half of every weight block (rows 64r..64r+63) -- weight traffic per SM halves,
 //   * 4 A stages (3 x 40 KB in flight per SM) instead of 2 x 72 KB.
 // Synchronisation: "full" barriers live in the leader CTA and collect the TMA bytes of both CTAs (cp.async.bulk.tensor
@@ -43,7 +43,7 @@ constexpr int SMEM_FIXED = 1024 /*align*/ + NEPI * STAGE_BYTES + 256 /*barriers*
 
 // this CTA's half of the weights of one (plane, ky): Cout=64 -> pair half (64 rows) + single half (32 rows);
 // Cout<=32 -> triple half (64 rows); Cout<=16 -> 32 rows
-__host__ __device__ constexpr int w_bytes_per_ky(int nreal) { return nreal == 64 ? 12288 : (nreal == 32 ? 8192 : 4096); }
+__host__ __device__ constexpr int w_bytes_per_ky(int nreal) { return nreal == 64 ? 12288 : (nreal == 32 ? 6144 : 4096); }
 
 struct Bars {
     uint64_t a_full[NA_MAX], a_empty[NA_MAX];
@@ -63,7 +63,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const int NA)
 {
     constexpr int NGROUPS = NREAL == 64 ? 2 : 1;           // MMA groups per kernel row (pair + single, or one triple)
-    constexpr int ROWS_PER_KY = NREAL == 64 ? 192 : (NREAL == 32 ? 128 : 64);  // weight rows per (plane, ky), see model.cpp
+    constexpr int ROWS_PER_KY = NREAL == 64 ? 192 : (NREAL == 32 ? 96 : 64);  // weight rows per (plane, ky), see model.cpp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nchunk = (a.cin + 63) >> 6;
@@ -115,7 +115,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                     uint8_t* dst = smW + (c * 3 + ky) * W_KY;
                     const int row0 = (c * 3 + ky) * ROWS_PER_KY;
                     if (NREAL == 16) tma2_load_2d(dst, &maps.w32, wbar, 0, row0 + (int)rank * 32);
-                    else tma2_load_2d(dst, &maps.w, wbar, 0, row0 + (int)rank * 64);
+                    else tma2_load_2d(dst, &maps.w, wbar, 0, row0 + (int)rank * (NREAL == 32 ? 48 : 64));  // maps.w box: 48 rows for Cout<=32
                     if (NREAL == 64) tma2_load_2d(dst + 8192, &maps.w32, wbar, 0, row0 + 128 + (int)rank * 32);
                 }
         } else if (is_leader && (a.desc_mode & 4) && lane == 0) {
@@ -153,7 +153,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (is_leader) {
             const bool leader = elect_one();
-            constexpr uint32_t idesc128 = umma_idesc_f16(256, 128);
+            constexpr uint32_t idesc128 = umma_idesc_f16(256, NREAL == 32 ? 96 : 128);  // Cout<=32: three 32-wide tap groups
             constexpr uint32_t idesc64 = umma_idesc_f16(256, 64);
             const uint64_t desc_hi = umma_desc_sw128(0, 1024, 0);
             int ca = 0, ti = 0;

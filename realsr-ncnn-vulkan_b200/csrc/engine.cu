@@ -519,7 +519,7 @@ int rsr_load(rsr_handle* h, const char* parampath, const char* modelpath)
     dm.wmap.resize(nconv);
     dm.wmap32.resize(nconv);
     for (int i = 1; i < nconv; i++) {
-        int rr = make_wmap(h, &dm.wmap[i], (uint8_t*)dm.blob + off_r[i], nrows[i], 64);
+        int rr = make_wmap(h, &dm.wmap[i], (uint8_t*)dm.blob + off_r[i], nrows[i], dm.cout_pad[i] == 32 ? 48 : 64);
         if (!rr) rr = make_wmap(h, &dm.wmap32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], 32);
         if (rr) return rr;
     }

@@ -311,7 +311,8 @@ int pack_conv_weight_rows(const ConvLayer& c, int cout_pad, std::vector<uint16_t
 {
     const int nchunk = (c.cin + 63) / 64;
     const int grp = cout_pad;                               // rows per tap group
-    const int rows_per_ky = cout_pad == 64 ? 192 : 4 * grp;  // 3 tap groups (+ one zero group when Cout < 64)
+    // 3 tap groups; Cout<=16 adds a zero group so that N=64; Cout<=32 runs as N=96 MMAs, no padding
+    const int rows_per_ky = cout_pad == 16 ? 64 : 3 * grp;
     const int rows = nchunk * 3 * rows_per_ky;
     out.assign((size_t)rows * 64, 0);
     for (int ch = 0; ch < nchunk; ch++)

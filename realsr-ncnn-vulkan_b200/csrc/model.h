@@ -51,8 +51,8 @@ int load_model(const std::string& parampath, const std::string& binpath, Model& 
 void pack_conv_weights(const ConvLayer& c, int cout_pad, std::vector<uint16_t>& out);
 
 // Weight rows for the CTA-pair kernel (conv_tc2.cu): plain row-major [rows][64] fp16 (TMA applies the swizzle), rows
-// grouped per (64-channel plane, ky): Cout=64 -> 192 rows [W(ky,0) | W(ky,1) | W(ky,2)]; Cout<=32 -> 128 rows
-// [W(ky,0) | W(ky,1) | W(ky,2) | 0] (32 each); Cout<=16 -> 64 rows (16 each).  Returns the number of rows.
+// grouped per (64-channel plane, ky): Cout=64 -> 192 rows [W(ky,0) | W(ky,1) | W(ky,2)]; Cout<=32 -> 96 rows
+// [W(ky,0) | W(ky,1) | W(ky,2)] (32 each); Cout<=16 -> 64 rows [16 | 16 | 16 | 0].  Returns the number of rows.
 int pack_conv_weight_rows(const ConvLayer& c, int cout_pad, std::vector<uint16_t>& out);
 
 }  // namespace rsr
