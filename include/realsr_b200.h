@@ -104,6 +104,11 @@ RSR_API int rsr_check_model(const char* parampath, const char* modelpath, int* n
 RSR_API long long rsr_debug_pack(const char* parampath, const char* modelpath, int conv_index, int* cin, int* cout, int* cout_pad,
                                  uint16_t* packed, long long capacity);
 
+/* Host-only: the same conv's weights as the plain row-major [rows][64] fp16 matrix the CTA-pair kernel fetches by TMA
+ * (rows grouped per (64-channel plane, ky): Cout=64 -> 192 rows, Cout<=32 -> 96, Cout<=16 -> 64; see model.h).
+ * Returns the number of rows (packed may be NULL), or a negative code. */
+RSR_API long long rsr_debug_pack_rows(const char* parampath, const char* modelpath, int conv_index, uint16_t* packed, long long capacity);
+
 #ifdef __cplusplus
 }
 #endif

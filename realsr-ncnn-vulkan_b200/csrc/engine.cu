@@ -641,6 +641,22 @@ long long rsr_debug_pack(const char* parampath, const char* modelpath, int conv_
     return (long long)out.size();
 }
 
+long long rsr_debug_pack_rows(const char* parampath, const char* modelpath, int conv_index, uint16_t* packed, long long capacity)
+{
+    if (!parampath || !modelpath) return RSR_ERR_GENERIC;
+    Model m;
+    if (load_model(parampath, modelpath, m)) return RSR_ERR_MODEL;
+    if (conv_index < 1 || conv_index >= (int)m.convs.size()) return RSR_ERR_GENERIC;
+    const ConvLayer& c = m.convs[conv_index];
+    std::vector<uint16_t> out;
+    const int rows = pack_conv_weight_rows(c, c.cout <= 16 ? 16 : (c.cout <= 32 ? 32 : 64), out);
+    if (packed) {
+        if ((long long)out.size() > capacity) return RSR_ERR_GENERIC;
+        memcpy(packed, out.data(), out.size() * 2);
+    }
+    return rows;
+}
+
 int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, int W, float* out32)
 {
     if (!h || !h->loaded) return RSR_ERR_GENERIC;

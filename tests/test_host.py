@@ -109,6 +109,30 @@ def test_weight_packing_matches_numpy(models_dir):
         assert np.array_equal(buf.view(np.float16).reshape(ref.shape).view(np.uint16), ref.view(np.uint16))
 
 
+def test_weight_rows_for_cta_pair_kernel(models_dir):
+    """row-major [rows][64] weight matrix of the cta_group::2 kernel: per (plane, ky) the three kx tap groups stacked along N"""
+    lib = rb.load_library()
+    lib.rsr_debug_pack_rows.restype = ctypes.c_longlong
+    p, b = model_paths("models-DF2K_JPEG")
+    convs = read_convs("models-DF2K_JPEG")
+    for idx in (1, 4, 5, 348, 350):
+        c = convs[idx]
+        grp = 16 if c["cout"] <= 16 else (32 if c["cout"] <= 32 else 64)
+        per_ky = 64 if grp == 16 else 3 * grp
+        nchunk = (c["cin"] + 63) // 64
+        rows = lib.rsr_debug_pack_rows(p.encode(), b.encode(), idx, None, ctypes.c_longlong(0))
+        assert rows == nchunk * 3 * per_ky
+        buf = np.zeros(rows * 64, dtype=np.uint16)
+        assert lib.rsr_debug_pack_rows(p.encode(), b.encode(), idx, buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(buf.size)) == rows
+        ref = np.zeros((nchunk, 3, per_ky, 64), dtype=np.float16)
+        for ch in range(nchunk):
+            k = min(64, c["cin"] - ch * 64)
+            for ky in range(3):
+                for kx in range(3):
+                    ref[ch, ky, kx * grp:kx * grp + c["cout"], :k] = c["w"][:, ch * 64:ch * 64 + k, ky, kx]
+        assert np.array_equal(buf.view(np.float16).reshape(ref.shape).view(np.uint16), ref.view(np.uint16))
+
+
 def test_fails_loudly_without_gpu_or_with_cpu_id(models_dir):
     """no CPU fallback: gpuid -1 (the reference's ncnn CPU mode) and a missing device are errors, not silent paths"""
     p, b = model_paths("models-DF2K")
