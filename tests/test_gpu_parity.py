@@ -221,3 +221,24 @@ def test_cpp_wrapper_cli_concurrent_jobs(tmp_path, models_dir):
     assert r.returncode == 0, r.stderr
     out = np.fromfile(fo, dtype=np.uint8).reshape(gold.shape)
     check_contract(diff_stats(out, gold), natural=True)
+
+
+def test_cli_directory_mode(tmp_path, models_dir):
+    """the reference's command line surface (src/main.cpp) on the B200 engine: dir -> dir, PNG in/out, RGB + RGBA, -t, -j"""
+    import os
+    from PIL import Image
+    import realsr_ncnn_vulkan_b200.cli as cli
+    ind, outd = tmp_path / "in", tmp_path / "out"
+    ind.mkdir(); outd.mkdir()
+    img, gold = golden("natural_48x40_df2k_t32")
+    rgba, gold_rgba = golden("rgba_noise_41x30_df2k_t200")
+    Image.fromarray(img).save(ind / "a.png")
+    Image.fromarray(rgba).save(ind / "b.png")
+    rc = cli.main(["-i", str(ind), "-o", str(outd), "-m", os.path.join(models_dir, "models-DF2K"), "-t", "32", "-j", "2:2:2", "-v"])
+    assert rc == 0
+    a = np.asarray(Image.open(outd / "a.png"))
+    check_contract(diff_stats(a, gold), natural=True)
+    b = np.asarray(Image.open(outd / "b.png"))
+    assert b.shape == gold_rgba.shape  # tile 32 here vs 200 in the golden: only shape / alpha-away-from-tile-borders are comparable
+    ref = run("models-DF2K", rgba, 32)
+    assert np.array_equal(b, ref)
