@@ -148,7 +148,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
                 const int s = ca % NA;
                 mbar_wait(&bars->a_empty[s], ((ca / NA) & 1) ^ 1);
                 if (leader) {
-                    if (a.desc_mode & 2) {  // timing experiment: no A traffic
+                    if (a.debug_mask & 2) {  // timing experiment: no A traffic
                         mbar_arrive(&bars->a_full[s]);
                     } else {
                         mbar_expect_tx(&bars->a_full[s], A_BYTES);
@@ -168,7 +168,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
                 const int s = cb % NB;
                 mbar_wait(&bars->b_empty[s], ((cb / NB) & 1) ^ 1);
                 if (leader) {
-                    if (a.desc_mode & 4) {  // timing experiment: no weight traffic
+                    if (a.debug_mask & 4) {  // timing experiment: no weight traffic
                         mbar_arrive(&bars->b_full[s]);
                     } else {
                         mbar_expect_tx(&bars->b_full[s], B_SLOT);
@@ -206,7 +206,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
                     const uint64_t da0 = desc_hi | (uint64_t)(((a_base + (uint32_t)(ky * P + kx) * 128u) & 0x3FFFFu) >> 4);
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++) {
-                        if (ks < ksteps && leader && !(a.desc_mode & 1)) {
+                        if (ks < ksteps && leader && !(a.debug_mask & 1)) {
                             const uint32_t accum = (c | tap | ks) ? 1u : 0u;
                             const uint64_t db = db0 + ks * 2;
                             // M-tile mt starts 128 rows = 16 KB further: +1024 in descriptor units of 16 B
@@ -234,7 +234,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a)
         const int half = ew >> 2;
         uint32_t* stg = reinterpret_cast<uint32_t*>(smStage + ew * STAGE_BYTES);  // [32 rows][20 words]
         const int tr = lane >> 2, tc = lane & 3;  // transposed domain: row (position) offset, 16-B chunk
-        const bool dbg_noepi = (a.desc_mode & 8) != 0;  // timing experiment: drain TMEM only
+        const bool dbg_noepi = (a.debug_mask & 8) != 0;  // timing experiment: drain TMEM only
         int ti = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ti++) {
             const int b = t / tiles_per_img, rem = t - b * tiles_per_img;

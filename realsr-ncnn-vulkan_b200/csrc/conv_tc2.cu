@@ -107,7 +107,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
     // Resident weights: every CTA fetches ITS half of all weight blocks once (before the grid dependency is resolved --
     // weights are constants, so this overlaps the previous conv's tail).  All bytes are counted on the leader's w_full.
     if (warp == 2) {
-        if (elect_one() && !(a.desc_mode & 4)) {
+        if (elect_one() && !(a.debug_mask & 4)) {
             const uint32_t wbar = mapa_u32(smem_u32(&bars->w_full), 0);
             if (is_leader) mbar_expect_tx(&bars->w_full, 2u * (uint32_t)(nchunk * 3 * W_KY));
             for (int c = 0; c < nchunk; c++)
@@ -118,7 +118,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                     else tma2_load_2d(dst, &maps.w, wbar, 0, row0 + (int)rank * (NREAL == 32 ? 48 : 64));  // maps.w box: 48 rows for Cout<=32
                     if (NREAL == 64) tma2_load_2d(dst + 8192, &maps.w32, wbar, 0, row0 + 128 + (int)rank * 32);
                 }
-        } else if (is_leader && (a.desc_mode & 4) && lane == 0) {
+        } else if (is_leader && (a.debug_mask & 4) && lane == 0) {
             mbar_arrive(&bars->w_full);
         }
     }
@@ -139,7 +139,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                 const int s = ca % NA;
                 mbar_wait(&bars->a_empty[s], ((ca / NA) & 1) ^ 1);
                 if (leader) {
-                    if (a.desc_mode & 2) {
+                    if (a.debug_mask & 2) {
                         if (is_leader) mbar_arrive(&bars->a_full[s]);
                     } else {
                         if (is_leader) mbar_expect_tx(&bars->a_full[s], 2 * A_BYTES);
@@ -184,7 +184,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                             const uint64_t da0 = desc_hi | (uint64_t)(((a_base + (uint32_t)(ky * P + g * 2) * 128u) & 0x3FFFFu) >> 4);
 #pragma unroll
                             for (int ks = 0; ks < 4; ks++) {
-                                if (ks < ksteps && leader && !(a.desc_mode & 1)) {
+                                if (ks < ksteps && leader && !(a.debug_mask & 1)) {
                                     const uint32_t accum = (c | ky | g | ks) ? 1u : 0u;
                                     umma2_f16(acc + 0 * DCOLS, da0 + ks * 2, db0 + ks * 2, idesc, accum);
                                     umma2_f16(acc + 1 * DCOLS, da0 + ks * 2 + 1024, db0 + ks * 2, idesc, accum);
@@ -210,7 +210,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
         const int group = ew >> 2;
         uint32_t* stg = reinterpret_cast<uint32_t*>(smStage + ew * STAGE_BYTES);  // [32 rows][20 words]
         const int tr = lane >> 2, tc = lane & 3;
-        const bool dbg_noepi = (a.desc_mode & 8) != 0;
+        const bool dbg_noepi = (a.debug_mask & 8) != 0;
         const uint32_t acc_empty_leader = mapa_u32(smem_u32(&bars->acc_empty[group]), 0);
         int ti = 0;
         for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {

@@ -84,7 +84,7 @@ struct rsr_handle {
     // 1024 bytes per pixel.  0 restores the fp32 RDB stream.  CTA-pair kernel only.
     int residual_fp16 = 1;
     int conv_impl = 2;  // 2 = CTA-pair kernel (conv_tc2.cu, default), 1 = single-CTA .ws kernel (conv_tc.cu, kept for A/B: tools/ab_impl.py)
-    int desc_mode = 0;  // measured on B200: SWIZZLE_128B is a function of the absolute smem address => base_offset 0 for row-shifted starts
+    int debug_mask = 0;  // timing experiments only (see include/realsr_b200.h)
     int time_convs = 0;
     // stats
     long long launches = 0;
@@ -206,7 +206,7 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
     a.wpk = dm.wpk[conv_idx];
     a.bias = dm.bias[conv_idx];
     a.cin = h->model.convs[conv_idx].cin;
-    a.desc_mode = h->desc_mode;
+    a.debug_mask = h->debug_mask;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->time_convs) {
         if (c.nconv_ev >= c.ws->conv_events.size()) {
@@ -600,7 +600,7 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
 {
     if (!h || !key) return RSR_ERR_GENERIC;
     if (!strcmp(key, "max_batch")) h->max_batch = value;
-    else if (!strcmp(key, "debug_mask") || !strcmp(key, "desc_mode")) h->desc_mode = (int)value;
+    else if (!strcmp(key, "debug_mask")) h->debug_mask = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
     else if (!strcmp(key, "conv_impl")) h->conv_impl = (int)value;
     else if (!strcmp(key, "residual_fp16")) h->residual_fp16 = (int)value;
@@ -694,7 +694,7 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     a.out16 = d_out; a.out_cs = npad; a.out_co = 0;
     a.tiles = d_td; a.tta_out = d_f;
     a.mode = npad == 16 ? CONV_LAST_F32 : CONV_STORE16;
-    a.desc_mode = h->desc_mode;
+    a.debug_mask = h->debug_mask;
     long long* d_ts = nullptr;
     if (getenv("RSR_DBG_TS")) {
         CK(cudaMalloc(&d_ts, 64 * 8 * sizeof(long long)));

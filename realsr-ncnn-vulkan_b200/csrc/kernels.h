@@ -60,7 +60,7 @@ struct ConvArgs {
     int prepad_s;        // prepadding*scale
     float* tta_out;
     long long* dbg_ts;   // optional (bring-up): per-tile clock64 stamps of cluster 0, 8 slots per tile, see conv_tc2.cu
-    int desc_mode;       // debug mask for timing experiments (0 in production): 1 no MMA, 2 no A loads, 4 no B loads, 8 no epilogue I/O
+    int debug_mask;       // debug mask for timing experiments (0 in production): 1 no MMA, 2 no A loads, 4 no B loads, 8 no epilogue I/O
 };
 
 // one tensor map per 64-channel input plane (chunk) of a conv

@@ -17,7 +17,7 @@ if os.environ.get("RSR_MAX_BATCH"):
 if os.environ.get("RSR_IMPL"):
     e.set_option("conv_impl", int(os.environ["RSR_IMPL"]))
 if os.environ.get("RSR_DEBUG"):
-    e.set_option("desc_mode", int(os.environ["RSR_DEBUG"]))
+    e.set_option("debug_mask", int(os.environ["RSR_DEBUG"]))
 if os.environ.get("RSR_TIME_CONVS"):
     e.set_option("time_convs", 1)
 img = np.random.default_rng(1000).integers(0, 256, (h, w, 3), dtype=np.uint8)
