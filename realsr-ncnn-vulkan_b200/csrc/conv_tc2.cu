@@ -231,33 +231,50 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
             bool vcol[4];
 #pragma unroll
             for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < a.W);
-            // residual-stream operands of one (M-tile, 32-channel block), fetched one block ahead of use
+            // residual operands.  fp32 modes (CONV_RDB_OUT with T32, CONV_TRUNK with F32): one (M-tile, 32-channel block) is
+            // fetched one block ahead of use.  CONV_RDB_OUT16: ALL fp16 x0 values this thread needs for the tile (4 blocks x
+            // 8 x 8 B = 64 registers) are requested here, before waiting for the MMAs -- per-tile timestamps showed the
+            // one-block-ahead scheme paying one memory latency (~3.7 k clk) per block, 15 k clk per tile against 7.5 k clk of
+            // MMAs.
+            constexpr bool RDB16 = MODE == CONV_RDB_OUT16;
+            constexpr bool RDB = MODE == CONV_RDB_OUT || RDB16;
             float4 res[2][4];
+            uint2 x0raw[2][2][2][4];  // [i][nb][hf][r], RDB16 only
             auto load_res = [&](int i, int nb, float4 (&dst)[2][4]) {
                 if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
-                    if (MODE == CONV_RDB_OUT && a.res16) {  // fp16 RDB input (already in the dense buffer): 128 B instead of 256 B per pixel
-                        const __half* base = a.res16 + rowpix[i] * 64 + nb * 32 + tc * 4;
+                    const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + nb * 32 + tc * 4;
 #pragma unroll
-                        for (int hf = 0; hf < 2; hf++)
+                    for (int hf = 0; hf < 2; hf++)
 #pragma unroll
-                            for (int r = 0; r < 4; r++)
-                                if (vcol[r] && vrow[i]) {
-                                    const uint2 hv = *reinterpret_cast<const uint2*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
-                                    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&hv.x));
-                                    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
-                                    dst[hf][r] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                                }
-                    } else {
-                        const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + nb * 32 + tc * 4;
-#pragma unroll
-                        for (int hf = 0; hf < 2; hf++)
-#pragma unroll
-                            for (int r = 0; r < 4; r++)
-                                if (vcol[r] && vrow[i]) dst[hf][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
-                    }
+                        for (int r = 0; r < 4; r++)
+                            if (vcol[r] && vrow[i]) dst[hf][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
                 }
             };
-            load_res(0, 0, res);
+            if constexpr (RDB16) {
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int nb = 0; nb < 2; nb++)
+#pragma unroll
+                        for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                            for (int r = 0; r < 4; r++)
+                                if (vcol[r] && vrow[i])
+                                    x0raw[i][nb][hf][r] = *reinterpret_cast<const uint2*>(a.res16 + (rowpix[i] + tr + 8 * r) * 64 + nb * 32 + hf * 16 + tc * 4);
+            } else {
+                load_res(0, 0, res);
+            }
+            if constexpr (RDB) {
+                if (a.rrdb_end) {  // the RRDB-level skip operands of THIS tile: pull the rows into L2 while the MMAs run
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+                        if (vrow[i]) {
+                            const int npx = min(BW, a.W - x0);
+                            const char* p1 = reinterpret_cast<const char*>(a.r32 + rowpix[i] * 64);
+                            for (int l = lane; l < npx * 2; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + (size_t)l * 128));
+                        }
+                }
+            }
             // (An L2 prefetch of the next tile's residual rows was tried and measured 5 % slower end to end: the Cout=64
             // convs are HBM-bandwidth-bound in situ -- 1.44 GB per launch at 4.5 TB/s -- not latency-bound.)
             const bool ts_on = a.dbg_ts != nullptr && cluster_id == 0 && ti < 64 && is_leader && (ew & 3) == 0 && lane == 0;
@@ -349,7 +366,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                         for (int j = 0; j < 32; j++)
                             v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1));
                         float4 nxt[2][4];
-                        {   // prefetch the residual operands of the next (M-tile, 32-channel block)
+                        if constexpr (!RDB16) {  // prefetch the residual operands of the next (M-tile, 32-channel block)
                             const int ni = nb == 1 ? i + 1 : i, nnb = nb ^ 1;
                             if (ni < 2) load_res(ni, nnb, nxt);
                         }
@@ -365,8 +382,16 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
 #pragma unroll
                             for (int r = 0; r < 4; r++) acc4[r] = *reinterpret_cast<const float4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
                             __syncwarp();
+                            if constexpr (RDB16) {
+#pragma unroll
+                                for (int r = 0; r < 4; r++) {
+                                    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&x0raw[i][nb][hf][r].x));
+                                    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&x0raw[i][nb][hf][r].y));
+                                    res[hf][r] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                                }
+                            }
                             float4 rr[4];
-                            if (MODE == CONV_RDB_OUT && a.rrdb_end) {
+                            if (RDB && a.rrdb_end) {
 #pragma unroll
                                 for (int r = 0; r < 4; r++)
                                     if (vcol[r] && vrow[i]) rr[r] = *reinterpret_cast<const float4*>(a.r32 + (rowpix[i] + tr + 8 * r) * 64 + ch0);
@@ -374,7 +399,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
 #pragma unroll
                             for (int r = 0; r < 4; r++) {
                                 float4 o;
-                                if constexpr (MODE == CONV_RDB_OUT) {
+                                if constexpr (RDB) {
                                     o.x = (acc4[r].x + bb.x) * 0.2f + res[hf][r].x;
                                     o.y = (acc4[r].y + bb.y) * 0.2f + res[hf][r].y;
                                     o.z = (acc4[r].z + bb.z) * 0.2f + res[hf][r].z;
@@ -389,18 +414,20 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                                 }
                                 if (vcol[r] && vrow[i]) {
                                     const size_t px = rowpix[i] + tr + 8 * r;
-                                    if constexpr (MODE == CONV_RDB_OUT) {
+                                    if constexpr (RDB) {
                                         if (a.rrdb_end) *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0) = o;
-                                        if (!a.res16) *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o;
+                                        if constexpr (!RDB16) *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o;
                                     }
                                     *reinterpret_cast<uint2*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
                                 }
                             }
                         }
+                        if constexpr (!RDB16) {
 #pragma unroll
-                        for (int h2 = 0; h2 < 2; h2++)
+                            for (int h2 = 0; h2 < 2; h2++)
 #pragma unroll
-                            for (int r = 0; r < 4; r++) res[h2][r] = nxt[h2][r];
+                                for (int r = 0; r < 4; r++) res[h2][r] = nxt[h2][r];
+                        }
                     }
                 }
             }
@@ -465,6 +492,7 @@ cudaError_t launch_conv3x3_tc2(const ConvMaps* in_map, const ConvArgs& a, int co
     if (cout_pad == 32 && a.mode == CONV_STORE16) return launch_nm<32, CONV_STORE16>(in_map, a, stream);
     if (cout_pad == 64 && a.mode == CONV_STORE16) return launch_nm<64, CONV_STORE16>(in_map, a, stream);
     if (cout_pad == 64 && a.mode == CONV_RDB_OUT) return launch_nm<64, CONV_RDB_OUT>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_RDB_OUT16) return launch_nm<64, CONV_RDB_OUT16>(in_map, a, stream);
     if (cout_pad == 64 && a.mode == CONV_TRUNK) return launch_nm<64, CONV_TRUNK>(in_map, a, stream);
     if (cout_pad == 16 && a.mode == CONV_LAST_U8) return launch_nm<16, CONV_LAST_U8>(in_map, a, stream);
     if (cout_pad == 16 && a.mode == CONV_LAST_F32) return launch_nm<16, CONV_LAST_F32>(in_map, a, stream);

@@ -297,7 +297,7 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c
             }
             ConvArgs a = base;  // x5 -> residual(s) -> x0 of the next RDB in the other buffer
             a.mode = CONV_RDB_OUT; a.rrdb_end = (rdb == 2);
-            if (h->residual_fp16 && h->conv_impl == 2) a.res16 = D[cur];
+            if (h->residual_fp16 && h->conv_impl == 2) { a.mode = CONV_RDB_OUT16; a.res16 = D[cur]; }
             a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
             if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, 4)))) return r;
             cur ^= 1;
@@ -696,6 +696,16 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     a.mode = npad == 16 ? CONV_LAST_F32 : CONV_STORE16;
     a.debug_mask = h->debug_mask;
     long long* d_ts = nullptr;
+    float* d_r32 = nullptr;
+    if (getenv("RSR_DBG_RDB") && npad == 64) {  // bring-up: time the Cout=64 conv with its real (CONV_RDB_OUT) epilogue
+        CK(cudaMalloc(&d_r32, npx * 64 * 4));
+        CK(cudaMemset(d_r32, 0, npx * 64 * 4));
+        a.mode = h->residual_fp16 ? CONV_RDB_OUT16 : CONV_RDB_OUT;
+        a.r32 = d_r32;
+        a.t32 = d_r32;
+        a.res16 = d_in;
+        a.rrdb_end = atoi(getenv("RSR_DBG_RDB")) > 1;
+    }
     if (getenv("RSR_DBG_TS")) {
         CK(cudaMalloc(&d_ts, 64 * 8 * sizeof(long long)));
         CK(cudaMemset(d_ts, 0, 64 * 8 * sizeof(long long)));
@@ -716,6 +726,7 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
                     ts[i * 8 + 3] - t0, ts[i * 8 + 4] - t0, ts[i * 8 + 5] - t0, ts[i * 8 + 6] - t0);
         cudaFree(d_ts);
     }
+    if (d_r32) cudaFree(d_r32);
     if (npad == 16) {
         std::vector<float> tmp(npx * 4);
         CK(cudaMemcpy(tmp.data(), d_f, npx * 16, cudaMemcpyDeviceToHost));

@@ -35,6 +35,7 @@ enum ConvMode {
     CONV_TRUNK = 2,     // out16 = fp16(acc + b + F32)
     CONV_LAST_U8 = 3,   // v = acc+b -> crop, v*255+0.5, (int) trunc, clamp -> u8 HWC output image
     CONV_LAST_F32 = 4,  // v = acc+b -> fp32 [slot][4H][4W][4] (TTA; averaged by tta_gather)
+    CONV_RDB_OUT16 = 5, // like CONV_RDB_OUT, but the RDB input is read from the fp16 plane `res16` and T32 is not written
 };
 
 struct ConvArgs {
