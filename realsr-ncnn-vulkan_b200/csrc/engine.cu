@@ -53,6 +53,8 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf d16[2], t32, r32, f32, u1, v1, u2, v2, tta, tiles, img_in, img_out;
+    TileDesc* h_tiles = nullptr;  // pinned staging for the tile descriptors of one process() call
+    size_t h_tiles_cap = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
 };
 
@@ -186,6 +188,7 @@ void free_ws(Workspace* w)
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto& e : w->conv_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (w->h_tiles) cudaFreeHost(w->h_tiles);
     if (w->ev0) cudaEventDestroy(w->ev0);
     if (w->ev1) cudaEventDestroy(w->ev1);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -234,13 +237,13 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
 }
 
 // Runs the whole network on one batch of same-shape padded tiles (H x W network-input pixels each).
-int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, uint8_t* d_out, const std::vector<TileDesc>& tiles, int H,
+// `d_tiles`: the batch's B descriptors, already on the device.
+int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, uint8_t* d_out, const TileDesc* d_tiles, int B, int H,
               int W, bool tta_out)
 {
     rsr_handle* h = c.h;
     Workspace* ws = c.ws;
     const Model& m = h->model;
-    const int B = (int)tiles.size();
     const size_t npx = (size_t)B * H * W;
     int r;
     if ((r = ensure(h, ws->d16[0], npx * 192 * 2))) return r;
@@ -252,11 +255,7 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c
     if ((r = ensure(h, ws->v1, npx * 4 * 64 * 2))) return r;
     if ((r = ensure(h, ws->u2, npx * 16 * 64 * 2))) return r;
     if ((r = ensure(h, ws->v2, npx * 16 * 64 * 2))) return r;
-    if ((r = ensure(h, ws->tiles, sizeof(TileDesc) * (size_t)B))) return r;
     cudaStream_t st = ws->stream;
-    // tile descriptors: pageable -> device through the stream (small); safe because `tiles` outlives the sync below
-    CK(cudaMemcpyAsync(ws->tiles.p, tiles.data(), sizeof(TileDesc) * (size_t)B, cudaMemcpyHostToDevice, st));
-    const TileDesc* d_tiles = (const TileDesc*)ws->tiles.p;
 
     // dense-block buffers: three 64-channel planes each (x0 | x1,x2 | x3,x4)
     __half* D[2] = {(__half*)ws->d16[0].p, (__half*)ws->d16[1].p};
@@ -362,19 +361,26 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
     BatchCtx c{h, ws};
     long long padded = 0;
     int r;
-    for (auto& g : groups) {
-        const int H = g.first.first, W = g.first.second;
-        std::vector<TileDesc>& tl = g.second;
+    // Every batch of the call is planned first, so that all tile descriptors go to the device in ONE copy from pinned memory
+    // and the batches then run back to back on the stream with no host synchronisation in between (same-stream order makes
+    // the reuse of the activation buffers safe).  Larger shapes first: the workspace is sized once.
+    struct Job { size_t off; int n, H, W; bool tta_out, gather; size_t slot_stride; int mw, mh; };
+    std::vector<TileDesc> flat;
+    std::vector<Job> jobs;
+    size_t max_tta_bytes = 0;
+    for (auto g = groups.rbegin(); g != groups.rend(); ++g) {
+        const int H = g->first.first, W = g->first.second;
+        std::vector<TileDesc>& tl = g->second;
         // workspace per padded pixel: 2x192 fp16 + 3x64 fp32 + (u1,v1) 4x64x2 fp16 + (u2,v2) 16x64x2 fp16 [+ TTA 16 float4 x2]
         const double bytes_per_tile = (double)H * W * (768.0 + 768.0 + 1024.0 + 4096.0 + (h->tta ? 512.0 : 0.0));
         long long mb = h->max_batch > 0 ? h->max_batch : (long long)(12e9 / bytes_per_tile);
         mb = std::max(1LL, std::min(mb, 64LL));
         if (!h->tta) {
             for (size_t i = 0; i < tl.size(); i += (size_t)mb) {
-                std::vector<TileDesc> batch(tl.begin() + i, tl.begin() + std::min(tl.size(), i + (size_t)mb));
-                if ((r = run_batch(c, d_in, w, hh, ch, d_out, batch, H, W, false))) return r;
-                padded += (long long)batch.size() * H * W;
-                CK(cudaStreamSynchronize(ws->stream));  // `batch` (tile descriptors) must outlive the async copy
+                const size_t n = std::min(tl.size(), i + (size_t)mb) - i;
+                jobs.push_back({flat.size(), (int)n, H, W, false, false, 0, 0, 0});
+                flat.insert(flat.end(), tl.begin() + i, tl.begin() + i + n);
+                padded += (long long)n * H * W;
             }
         } else {
             // 8 dihedral variants per tile (src/realsr.cpp:242-318): 0..3 keep the shape, 4..7 run transposed
@@ -382,35 +388,53 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
             for (size_t i = 0; i < tl.size(); i += (size_t)G) {
                 const size_t n = std::min(tl.size(), i + (size_t)G) - i;
                 const size_t slot_stride = (size_t)16 * H * W;  // float4 per slot
-                if ((r = ensure(h, ws->tta, n * 8 * slot_stride * sizeof(float4)))) return r;
-                std::vector<TileDesc> all(n * 8);
+                max_tta_bytes = std::max(max_tta_bytes, n * 8 * slot_stride * sizeof(float4));
+                for (int half = 0; half < 2; half++) {
+                    jobs.push_back({flat.size(), (int)n * 4, half ? W : H, half ? H : W, true, false, 0, 0, 0});
+                    for (size_t gi = 0; gi < n; gi++)
+                        for (int v = half * 4; v < half * 4 + 4; v++) {
+                            TileDesc t = tl[i + gi];
+                            t.variant = v;
+                            t.tta_slot = (int)(gi * 8 + v);
+                            flat.push_back(t);
+                        }
+                }
+                // the gather needs the 8 descriptors of every tile in slot order
+                int mw = 0, mh = 0;
+                for (size_t gi = 0; gi < n; gi++) { mw = std::max(mw, tl[i + gi].crop_w); mh = std::max(mh, tl[i + gi].crop_h); }
+                jobs.push_back({flat.size(), (int)n, H, W, true, true, slot_stride, mw, mh});
                 for (size_t gi = 0; gi < n; gi++)
                     for (int v = 0; v < 8; v++) {
                         TileDesc t = tl[i + gi];
                         t.variant = v;
                         t.tta_slot = (int)(gi * 8 + v);
-                        all[gi * 8 + v] = t;
+                        flat.push_back(t);
                     }
-                for (int half = 0; half < 2; half++) {
-                    std::vector<TileDesc> batch;
-                    for (size_t gi = 0; gi < n; gi++)
-                        for (int v = half * 4; v < half * 4 + 4; v++) batch.push_back(all[gi * 8 + v]);
-                    if ((r = run_batch(c, d_in, w, hh, ch, d_out, batch, half ? W : H, half ? H : W, true))) return r;
-                    CK(cudaStreamSynchronize(ws->stream));
-                }
-                // gather needs the 8 descs of every tile in slot order on the device
-                if ((r = ensure(h, ws->tiles, sizeof(TileDesc) * all.size()))) return r;
-                CK(cudaMemcpyAsync(ws->tiles.p, all.data(), sizeof(TileDesc) * all.size(), cudaMemcpyHostToDevice, ws->stream));
-                TtaGatherArgs ga{};
-                ga.tta_out = (const float*)ws->tta.p; ga.tiles = (const TileDesc*)ws->tiles.p; ga.ngroups = (int)n;
-                ga.slot_stride = slot_stride; ga.img_out = d_out; ga.img_w = w * 4; ga.img_h = hh * 4; ga.img_c = ch; ga.prepad_s = P * 4;
-                int mw = 0, mh = 0;
-                for (size_t gi = 0; gi < n; gi++) { mw = std::max(mw, tl[i + gi].crop_w); mh = std::max(mh, tl[i + gi].crop_h); }
-                CK(launch_tta_gather(ga, mw, mh, ws->stream));
-                c.launches++;
-                CK(cudaStreamSynchronize(ws->stream));
                 padded += (long long)n * 8 * H * W;
             }
+        }
+    }
+    if (flat.size() > ws->h_tiles_cap) {
+        if (ws->h_tiles) cudaFreeHost(ws->h_tiles);
+        ws->h_tiles = nullptr;
+        ws->h_tiles_cap = 0;
+        CK(cudaMallocHost((void**)&ws->h_tiles, sizeof(TileDesc) * flat.size()));
+        ws->h_tiles_cap = flat.size();
+    }
+    memcpy(ws->h_tiles, flat.data(), sizeof(TileDesc) * flat.size());
+    if ((r = ensure(h, ws->tiles, sizeof(TileDesc) * flat.size()))) return r;
+    if (max_tta_bytes && (r = ensure(h, ws->tta, max_tta_bytes))) return r;
+    CK(cudaMemcpyAsync(ws->tiles.p, ws->h_tiles, sizeof(TileDesc) * flat.size(), cudaMemcpyHostToDevice, ws->stream));
+    const TileDesc* d_tiles = (const TileDesc*)ws->tiles.p;
+    for (const Job& j : jobs) {
+        if (!j.gather) {
+            if ((r = run_batch(c, d_in, w, hh, ch, d_out, d_tiles + j.off, j.n, j.H, j.W, j.tta_out))) return r;
+        } else {
+            TtaGatherArgs ga{};
+            ga.tta_out = (const float*)ws->tta.p; ga.tiles = d_tiles + j.off; ga.ngroups = j.n;
+            ga.slot_stride = j.slot_stride; ga.img_out = d_out; ga.img_w = w * 4; ga.img_h = hh * 4; ga.img_c = ch; ga.prepad_s = P * 4;
+            CK(launch_tta_gather(ga, j.mw, j.mh, ws->stream));
+            c.launches++;
         }
     }
     if (ch == 4) {  // alpha: bicubic x4 per un-padded tile region, independent of the network
