@@ -58,7 +58,291 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b)
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Channel-split epilogue (option `epilogue_split`, template SPLIT): all 8 epilogue warps work on EVERY tile.  Warps w and
+// w+4 share a TMEM lane quarter (= one pixel row of each M-tile) and split the output channels in halves, each warp pulls
+// its share of BOTH M-tiles into registers, combines the horizontal taps, and hands the accumulator set back to the MMA
+// issuer right there -- before any bias / activation / residual math or store.  Why: per-tile timestamps
+// (profiles/r1_ts_1.txt) show the set-per-group scheme serialising MMA completion (~2 k clk) -> epilogue of that set
+// (~3 k clk) per accumulator set, so the Cout=32 convs run at 2.6 k clk per tile where MMAs / A loads need 1.4 k.  With
+// the early hand-back only the TMEM read (~0.3 k clk) stays on that chain.
 template <int NREAL, int MODE>
+__device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, const uint32_t tmem_base, uint8_t* smStage, const float* s_bias,
+                                               const uint32_t rank, const int cluster_id, const int nclusters, const int ntiles,
+                                               const int tiles_per_img, const int tiles_x, const int warp, const int lane)
+{
+    constexpr bool RDB16 = MODE == CONV_RDB_OUT16;
+    constexpr bool RDB = MODE == CONV_RDB_OUT || RDB16;
+    constexpr int NF = NREAL == 64 ? 32 : 16;  // accumulator values per M-tile and thread after the tap combination
+    const int q4 = warp & 3;
+    const int ew = warp - 3;
+    const int chh = ew >> 2;  // channel half owned by this warp (Cout=3: the M-tile it owns)
+    uint32_t* stg = reinterpret_cast<uint32_t*>(smStage + ew * STAGE_BYTES);  // [32 rows][20 words]
+    const int tr = lane >> 2, tc = lane & 3;
+    const bool dbg_noepi = (a.debug_mask & 8) != 0;
+    const uint32_t acc_empty_leader0 = mapa_u32(smem_u32(&bars->acc_empty[0]), 0);
+    const uint32_t acc_empty_leader1 = mapa_u32(smem_u32(&bars->acc_empty[1]), 0);
+    int ti = 0;
+    for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
+        const int b = t / tiles_per_img, rem = t - b * tiles_per_img;
+        const int by = rem / tiles_x, tx = rem - by * tiles_x;
+        const int x0 = tx * BW;
+        const int buf = ti & 1;
+        int yy[2];
+        size_t rowpix[2];
+        bool vrow[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            yy[i] = by * BAND + (int)rank * BH + i * 4 + q4;
+            vrow[i] = yy[i] < a.H && !dbg_noepi;
+            rowpix[i] = ((size_t)b * a.H + yy[i]) * a.W + x0;
+        }
+        bool vcol[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < a.W);
+
+        // ---- residual operands requested before the accumulators are waited for ----
+        uint2 x0raw[2][2][4];  // RDB16: [i][hf][r], channels chh*32 + hf*16 + tc*4 .. +3 of pixel tr + 8r
+        float4 res[2][4];      // fp32 modes: one M-tile ahead
+        auto load_res = [&](int i, float4 (&dst)[2][4]) {
+            if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
+                const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + chh * 32 + tc * 4;
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (vcol[r] && vrow[i]) dst[hf][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
+            }
+        };
+        if constexpr (RDB16) {
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (vcol[r] && vrow[i])
+                            x0raw[i][hf][r] = *reinterpret_cast<const uint2*>(a.res16 + (rowpix[i] + tr + 8 * r) * 64 + chh * 32 + hf * 16 + tc * 4);
+        } else {
+            load_res(0, res);
+        }
+        if constexpr (RDB) {
+            if (a.rrdb_end) {  // RRDB-level skip operands of THIS tile: pull this warp's half of each 256-B pixel into L2
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+                    if (vrow[i]) {
+                        const int npx = min(BW, a.W - x0);
+                        const char* p1 = reinterpret_cast<const char*>(a.r32 + rowpix[i] * 64 + chh * 32);
+                        for (int l = lane; l < npx; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + (size_t)l * 256));
+                    }
+            }
+        }
+        const bool ts_on = a.dbg_ts != nullptr && cluster_id == 0 && ti < 64 && rank == 0 && ew == 0 && lane == 0;
+        if (ts_on) a.dbg_ts[ti * 8 + 4] = clock64();
+        mbar_wait(&bars->acc_full[buf], (ti >> 1) & 1);
+        tc_fence_after();
+        if (ts_on) a.dbg_ts[ti * 8 + 5] = clock64();
+
+        // ---- accumulators of both M-tiles -> registers (taps combined), then give the set back ----
+        float f[2][NF];
+        float o3[3] = {0.f, 0.f, 0.f};
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS;
+        if constexpr (NREAL == 16) {
+            // Cout = 3: 16 + 16 + 16 columns per M-tile; the warp of group chh takes M-tile chh, the other one only signs off
+            uint32_t v[32], u[16];
+            tmem_ld32(taddr0 + chh * DCOLS, v);
+            tmem_ld16(taddr0 + chh * DCOLS + 32, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                o3[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 1) +
+                        __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 2);
+        } else if constexpr (NREAL == 32) {
+            // D[c] + right neighbour's D[32 + c] + second right neighbour's D[64 + c], c = chh*16 .. +15
+            uint32_t v[2][16], u[2][16], w[2][16];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                tmem_ld16(taddr0 + i * DCOLS + chh * 16, v[i]);
+                tmem_ld16(taddr0 + i * DCOLS + 32 + chh * 16, u[i]);
+                tmem_ld16(taddr0 + i * DCOLS + 64 + chh * 16, w[i]);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    f[i][j] = __uint_as_float(v[i][j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[i][j]), 1) +
+                              __shfl_down_sync(0xffffffffu, __uint_as_float(w[i][j]), 2);
+        } else {
+            // D[c] + right neighbour's D[64 + c], c = chh*32 .. +31
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                uint32_t v[32], u[32];
+                tmem_ld32(taddr0 + i * DCOLS + chh * 32, v);
+                tmem_ld32(taddr0 + i * DCOLS + 64 + chh * 32, u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j++) f[i][j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1);
+            }
+        }
+        // Plain (CTA-scope release) remote arrive: only the TMEM reads have to be ordered (tcgen05 fence); a cluster-scope
+        // release would also wait for this thread's global stores to drain.
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(buf ? acc_empty_leader1 : acc_empty_leader0);
+        if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
+
+        // ---- math + stores from registers ----
+        if constexpr (NREAL == 16) {
+            const int i = chh;
+            const int x = x0 + lane;
+            if (lane < BW && x < a.W && vrow[i]) {
+                const TileDesc td = a.tiles[b];
+                float o[3];
+#pragma unroll
+                for (int j = 0; j < 3; j++) o[j] = o3[j] + s_bias[j];
+                if constexpr (MODE == CONV_LAST_U8) {
+                    const int ii = yy[i] - a.prepad_s, jx = x - a.prepad_s;
+                    if (ii >= 0 && ii < td.crop_h && jx >= 0 && jx < td.crop_w) {
+                        uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + ii) * a.img_w + td.out_x0 + jx) * a.img_c;
+#pragma unroll
+                        for (int j = 0; j < 3; j++) {
+                            int iv = (int)(o[j] * 255.f + 0.5f);
+                            dst[j] = (uint8_t)min(max(iv, 0), 255);
+                        }
+                    }
+                } else {
+                    float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)a.H * a.W) + (size_t)yy[i] * a.W + x;
+                    *dst = make_float4(o[0], o[1], o[2], 0.f);
+                }
+            }
+        } else if constexpr (MODE == CONV_STORE16 && NREAL == 32) {
+            // 16 channels = 32 B per pixel: lanes 0..15 carry channels chh*16 .. +7 of 16 pixels, lanes 16..31 the other 8
+            const int p = lane & 15, tc2 = lane >> 4;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    float x = f[i][j] + s_bias[chh * 16 + j];
+                    if (a.act == 2) x = x > 0.f ? x : x * a.slope;
+                    f[i][j] = x;
+                }
+#pragma unroll
+                for (int k = 0; k < 2; k++)
+                    *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) =
+                        make_uint4(pack_h2(f[i][8 * k + 0], f[i][8 * k + 1]), pack_h2(f[i][8 * k + 2], f[i][8 * k + 3]),
+                                   pack_h2(f[i][8 * k + 4], f[i][8 * k + 5]), pack_h2(f[i][8 * k + 6], f[i][8 * k + 7]));
+                __syncwarp();
+                __half* orow = a.out16 + rowpix[i] * a.out_cs + a.out_co + chh * 16 + tc2 * 8;
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int px = p + 16 * r;
+                    const uint4 o = *reinterpret_cast<const uint4*>(stg + px * 20 + 4 * tc2);
+                    if (px < BW && x0 + px < a.W && vrow[i]) *reinterpret_cast<uint4*>(orow + (size_t)px * a.out_cs) = o;
+                }
+                __syncwarp();
+            }
+        } else if constexpr (MODE == CONV_STORE16) {
+            // Cout = 64: this warp's 32 channels = 64 B per pixel, 4 lanes per pixel
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    float x = f[i][j] + s_bias[chh * 32 + j];
+                    if (a.act == 2) x = x > 0.f ? x : x * a.slope;
+                    f[i][j] = x;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) =
+                        make_uint4(pack_h2(f[i][8 * k + 0], f[i][8 * k + 1]), pack_h2(f[i][8 * k + 2], f[i][8 * k + 3]),
+                                   pack_h2(f[i][8 * k + 4], f[i][8 * k + 5]), pack_h2(f[i][8 * k + 6], f[i][8 * k + 7]));
+                __syncwarp();
+                __half* orow = a.out16 + rowpix[i] * a.out_cs + a.out_co + chh * 32 + tc * 8;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint4 o = *reinterpret_cast<const uint4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
+                    if (vcol[r] && vrow[i]) *reinterpret_cast<uint4*>(orow + (size_t)(tr + 8 * r) * a.out_cs) = o;
+                }
+                __syncwarp();
+            }
+        } else {
+            // CONV_RDB_OUT / CONV_RDB_OUT16 / CONV_TRUNK (Cout = 64): fp32 math against the residual stream, transposed domain
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                float4 nxt[2][4];
+                if constexpr (!RDB16) {
+                    if (i == 0) load_res(1, nxt);
+                }
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        *reinterpret_cast<float4*>(stg + lane * 20 + 4 * k) =
+                            make_float4(f[i][16 * hf + 4 * k], f[i][16 * hf + 4 * k + 1], f[i][16 * hf + 4 * k + 2], f[i][16 * hf + 4 * k + 3]);
+                    __syncwarp();
+                    const int ch0 = chh * 32 + hf * 16 + tc * 4;
+                    const float4 bb = *reinterpret_cast<const float4*>(&s_bias[ch0]);
+                    float4 acc4[4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) acc4[r] = *reinterpret_cast<const float4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
+                    __syncwarp();
+                    if constexpr (RDB16) {
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&x0raw[i][hf][r].x));
+                            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&x0raw[i][hf][r].y));
+                            res[hf][r] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                        }
+                    }
+                    float4 rr[4];
+                    if (RDB && a.rrdb_end) {
+#pragma unroll
+                        for (int r = 0; r < 4; r++)
+                            if (vcol[r] && vrow[i]) rr[r] = *reinterpret_cast<const float4*>(a.r32 + (rowpix[i] + tr + 8 * r) * 64 + ch0);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        float4 o;
+                        if constexpr (RDB) {
+                            o.x = (acc4[r].x + bb.x) * 0.2f + res[hf][r].x;
+                            o.y = (acc4[r].y + bb.y) * 0.2f + res[hf][r].y;
+                            o.z = (acc4[r].z + bb.z) * 0.2f + res[hf][r].z;
+                            o.w = (acc4[r].w + bb.w) * 0.2f + res[hf][r].w;
+                            if (a.rrdb_end) {
+                                o.x = o.x * 0.2f + rr[r].x; o.y = o.y * 0.2f + rr[r].y;
+                                o.z = o.z * 0.2f + rr[r].z; o.w = o.w * 0.2f + rr[r].w;
+                            }
+                        } else {
+                            o.x = acc4[r].x + bb.x + res[hf][r].x; o.y = acc4[r].y + bb.y + res[hf][r].y;
+                            o.z = acc4[r].z + bb.z + res[hf][r].z; o.w = acc4[r].w + bb.w + res[hf][r].w;
+                        }
+                        if (vcol[r] && vrow[i]) {
+                            const size_t px = rowpix[i] + tr + 8 * r;
+                            if constexpr (RDB) {
+                                if (a.rrdb_end) *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0) = o;
+                                if constexpr (!RDB16) *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o;
+                            }
+                            *reinterpret_cast<uint2*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                        }
+                    }
+                }
+                if constexpr (!RDB16) {
+                    if (i == 0) {
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; h2++)
+#pragma unroll
+                            for (int r = 0; r < 4; r++) res[h2][r] = nxt[h2][r];
+                    }
+                }
+            }
+        }
+        if (ts_on) a.dbg_ts[ti * 8 + 7] = clock64();
+    }
+}
+
+template <int NREAL, int MODE, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const int NA)
 {
@@ -85,7 +369,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
     if (threadIdx.x == 0) {
         for (int i = 0; i < NA_MAX; i++) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
         mbar_init(&bars->w_full, 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], NEPI); }  // acc_empty: 4 warps per group x 2 CTAs
+        for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], SPLIT ? 2 * NEPI : NEPI); }  // acc_empty: 4 (SPLIT: 8) warps x 2 CTAs
         mbar_fence_init();
         for (int i = 0; i < 3; i++) tma_prefetch_desc(&maps.m[i]);
         tma_prefetch_desc(&maps.w);
@@ -199,6 +483,8 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
         }
     } else if (warp == 2) {
         // weight warp: its work (the one-time resident-weight fetch) happened in the prologue
+    } else if constexpr (SPLIT) {
+        epilogue_split<NREAL, MODE>(a, bars, tmem_base, smStage, s_bias, rank, cluster_id, nclusters, ntiles, tiles_per_img, tiles_x, warp, lane);
     } else {
         // ---------------- epilogue: warps 3..10 in two groups of four ----------------
         // Group g = (warp-3)/4 owns accumulator set g, i.e. every second work tile; inside a group warp q4 = warp % 4
@@ -446,8 +732,8 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
     if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
-template <int NREAL, int MODE>
-cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
+template <int NREAL, int MODE, bool SPLIT>
+cudaError_t launch_nms(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
 {
     static bool attr_done[64] = {};
     static int num_sms[64] = {};
@@ -456,7 +742,7 @@ cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t st
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     dev &= 63;
     if (!attr_done[dev]) {
-        e = cudaFuncSetAttribute(conv3x3_tc2_kernel<NREAL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+        e = cudaFuncSetAttribute(conv3x3_tc2_kernel<NREAL, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
         if (e != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         attr_done[dev] = true;
@@ -481,8 +767,14 @@ cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t st
     cfg.attrs = attr;
     static const int use_pdl = getenv("RSR_NOPDL") ? 0 : 1;  // bring-up switch
     cfg.numAttrs = use_pdl;
-    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<NREAL, MODE>, *in_map, a, na)) != cudaSuccess) return e;
+    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<NREAL, MODE, SPLIT>, *in_map, a, na)) != cudaSuccess) return e;
     return cudaGetLastError();
+}
+
+template <int NREAL, int MODE>
+cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
+{
+    return a.epi_split ? launch_nms<NREAL, MODE, true>(in_map, a, stream) : launch_nms<NREAL, MODE, false>(in_map, a, stream);
 }
 
 }  // namespace

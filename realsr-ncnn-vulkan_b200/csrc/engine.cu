@@ -80,6 +80,7 @@ struct rsr_handle {
     std::string err;
     // options
     long long max_batch = 0;  // 0 = auto
+    int epilogue_split = 0;   // CTA-pair kernel: channel-split epilogue (see conv_tc2.cu)
     // 1 (default): the RDB-level residual t = 0.2*x5 + x0 takes x0 from the fp16 dense buffer instead of an fp32 copy (the
     // RRDB-level skip stays fp32).  Measured on the goldens: max error unchanged (1 LSB natural / 2 LSB noise), off-by-one
     // bytes 1.8->2.1 %, 2.4->3.2 % (natural), 5.3 % faster: the Cout=64 conv is HBM-bound and this removes 384 of its
@@ -210,6 +211,7 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
     a.bias = dm.bias[conv_idx];
     a.cin = h->model.convs[conv_idx].cin;
     a.debug_mask = h->debug_mask;
+    a.epi_split = h->epilogue_split;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->time_convs) {
         if (c.nconv_ev >= c.ws->conv_events.size()) {
@@ -624,6 +626,7 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
 {
     if (!h || !key) return RSR_ERR_GENERIC;
     if (!strcmp(key, "max_batch")) h->max_batch = value;
+    else if (!strcmp(key, "epilogue_split")) h->epilogue_split = value ? 1 : 0;
     else if (!strcmp(key, "debug_mask")) h->debug_mask = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
     else if (!strcmp(key, "conv_impl")) h->conv_impl = (int)value;
@@ -719,6 +722,7 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     a.tiles = d_td; a.tta_out = d_f;
     a.mode = npad == 16 ? CONV_LAST_F32 : CONV_STORE16;
     a.debug_mask = h->debug_mask;
+    a.epi_split = h->epilogue_split;
     long long* d_ts = nullptr;
     float* d_r32 = nullptr;
     if (getenv("RSR_DBG_RDB") && npad == 64) {  // bring-up: time the Cout=64 conv with its real (CONV_RDB_OUT) epilogue
@@ -744,10 +748,11 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
         std::vector<long long> ts(64 * 8);
         CK(cudaMemcpy(ts.data(), d_ts, ts.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         const long long t0 = ts[0];
-        fprintf(stderr, "tile: mma_wait_start mma_acc_ready mma_a0_ready mma_issued | epi_wait_start epi_acc_full epi_done   (clk since first)\n");
+        fprintf(stderr, "tile: mma_wait_start mma_acc_ready mma_a0_ready mma_issued | epi_wait_start epi_acc_full epi_handback [epi_done]   (clk since first; "
+                        "epilogue_split=0: hand-back == done)\n");
         for (int i = 0; i < 64 && ts[i * 8 + 0]; i++)
-            fprintf(stderr, "%3d: %8lld %8lld %8lld %8lld | %8lld %8lld %8lld\n", i, ts[i * 8 + 0] - t0, ts[i * 8 + 1] - t0, ts[i * 8 + 2] - t0,
-                    ts[i * 8 + 3] - t0, ts[i * 8 + 4] - t0, ts[i * 8 + 5] - t0, ts[i * 8 + 6] - t0);
+            fprintf(stderr, "%3d: %8lld %8lld %8lld %8lld | %8lld %8lld %8lld %8lld\n", i, ts[i * 8 + 0] - t0, ts[i * 8 + 1] - t0, ts[i * 8 + 2] - t0,
+                    ts[i * 8 + 3] - t0, ts[i * 8 + 4] - t0, ts[i * 8 + 5] - t0, ts[i * 8 + 6] - t0, ts[i * 8 + 7] ? ts[i * 8 + 7] - t0 : 0LL);
         cudaFree(d_ts);
     }
     if (d_r32) cudaFree(d_r32);

@@ -1,0 +1,63 @@
+"""GPU tests of code paths that are compiled and shipped as OPT-IN options but have not yet had their first run on a
+B200 (written after the round's GPU budget was spent).  They only run with RSR_TEST_EXPERIMENTAL=1, so that the
+default `pytest -m gpu` stays a statement about validated code; tools/r2_first_call.sh runs them first thing next round."""
+import os
+
+import numpy as np
+import pytest
+
+import realsr_ncnn_vulkan_b200 as rb
+from common import diff_stats, golden, manifest, model_paths, read_convs
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get("RSR_TEST_EXPERIMENTAL"), reason="opt-in paths: set RSR_TEST_EXPERIMENTAL=1")]
+
+CASES = manifest()["cases"]
+
+
+def _engine(tta=False, **opts):
+    e = rb.RealSR(0, tta_mode=tta)
+    p, b = model_paths("models-DF2K")
+    assert e.load(p, b) == 0, e.last_error()
+    for k, v in opts.items():
+        assert e.set_option(k, v) == 0
+    return e
+
+
+@pytest.mark.parametrize("residual_fp16", [1, 0])
+def test_split_epilogue_is_bit_identical(models_dir, residual_fp16):
+    """epilogue_split=1 (channel-split epilogue, early accumulator hand-back) performs the same arithmetic in the same
+    order as the default epilogue: every layer output and the final image must be bit-identical to the default path"""
+    ref = _engine(residual_fp16=residual_fp16)
+    new = _engine(residual_fp16=residual_fp16, epilogue_split=1)
+    convs = read_convs("models-DF2K")
+    for idx, H, W in [(1, 37, 45), (2, 17, 31), (3, 64, 90), (4, 40, 61), (5, 33, 64), (346, 24, 30), (347, 50, 33), (350, 29, 47)]:
+        c = convs[idx]
+        x = (np.random.default_rng(idx).standard_normal((H, W, c["cin"])) * 0.5).astype(np.float16)
+        assert np.array_equal(ref.debug_conv(idx, x, c["cout"]), new.debug_conv(idx, x, c["cout"])), idx
+    rng = np.random.default_rng(7)
+    for (h, w, c, tile) in [(70, 93, 3, 32), (256, 256, 3, 200), (120, 90, 4, 64), (1080, 1920, 3, 400)]:
+        img = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        a = np.zeros((4 * h, 4 * w, c), np.uint8)
+        b = np.zeros_like(a)
+        ref.tilesize = new.tilesize = tile
+        assert ref.process(img, a) == 0 and new.process(img, b) == 0, new.last_error()
+        assert np.array_equal(a, b), (h, w, c, tile, diff_stats(a, b))
+
+
+def test_split_epilogue_tta_and_goldens(models_dir):
+    new = _engine(epilogue_split=1)
+    for name, natural in (("natural_48x40_df2k_t32", True), ("noise_50x33_df2k_t32", False), ("readme0_crop96x80_df2k_t64", True)):
+        case = [c for c in CASES if c["name"] == name][0]
+        img, gold = golden(name)
+        new.tilesize = case["tilesize"]
+        out = np.zeros_like(gold)
+        assert new.process(img, out) == 0, new.last_error()
+        s = diff_stats(out, gold)
+        assert (s["max"] <= 1 and s["frac_diff"] <= 0.05) if natural else (s["max"] <= 2 and s["n_gt1"] <= max(2, s["n"] // 10000)), s
+    a, b = _engine(tta=True), _engine(tta=True, epilogue_split=1)
+    img = np.random.default_rng(3).integers(0, 256, (45, 61, 3), dtype=np.uint8)
+    oa, ob = np.zeros((180, 244, 3), np.uint8), np.zeros((180, 244, 3), np.uint8)
+    a.tilesize = b.tilesize = 32
+    assert a.process(img, oa) == 0 and b.process(img, ob) == 0
+    assert np.array_equal(oa, ob)
