@@ -71,6 +71,17 @@ RSR_API int rsr_process(rsr_handle* h, const uint8_t* in, int w, int h_, int c, 
  * Used by bench.py to separate the compute stage from the PCIe copies; not part of the reference API. */
 RSR_API int rsr_process_device(rsr_handle* h, const uint8_t* d_in, int w, int h_, int c, uint8_t* d_out);
 
+/* Tile-granular sharding of ONE image over several handles (one per GPU) -- SURVEY 8e; the reference only shards whole
+ * images over GPUs (src/main.cpp:811-828).  Tiles are numbered row-major over the reference's tile grid
+ * (yi * xtiles + xi, src/realsr.cpp:170-171,:176-187 with the handle's current tilesize).
+ *   rsr_tile_count   : number of tiles of a w x h image.
+ *   rsr_process_tiles: rsr_process restricted to tiles [tile_first, tile_first + tile_count).  `in` is the WHOLE image;
+ *                      only the output regions of those tiles are written to `out` (the whole 4w x 4h x c buffer), so
+ *                      concurrent calls on different handles with disjoint ranges assemble the result in place with no
+ *                      exchange step.  The union over a partition of the grid is byte-identical to rsr_process. */
+RSR_API int rsr_tile_count(const rsr_handle* h, int w, int h_);
+RSR_API int rsr_process_tiles(rsr_handle* h, const uint8_t* in, int w, int h_, int c, uint8_t* out, int tile_first, int tile_count);
+
 /* Last error message of this handle ("" if none).  The pointer stays valid until the next failing call. */
 RSR_API const char* rsr_last_error(const rsr_handle* h);
 

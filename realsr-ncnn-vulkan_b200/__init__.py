@@ -5,3 +5,4 @@ of the reference's `class RealSR` (reference: src/realsr.h:13-42) on top of it. 
 so it is imported through the `realsr_ncnn_vulkan_b200` symlink at the repo root.
 """
 from .realsr import RealSR, RealSRError, lib_path, load_library  # noqa: F401
+from .sharded import process_sharded, split_tiles, tile_costs  # noqa: F401

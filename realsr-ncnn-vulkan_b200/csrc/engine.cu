@@ -343,8 +343,9 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c
     return 0;
 }
 
+// tiles [tile_first, tile_first + tile_count) of the reference's row-major tile grid; `done` (optional) receives their descriptors
 int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, int hh, int ch, uint8_t* d_out, long long* padded_out,
-                      long long* launches_out)
+                      long long* launches_out, int tile_first, int tile_count, std::vector<TileDesc>* done)
 {
     const int T = h->tilesize, P = h->prepadding;
     const int xtiles = (w + T - 1) / T, ytiles = (hh + T - 1) / T;
@@ -352,6 +353,8 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
     std::map<std::pair<int, int>, std::vector<TileDesc>> groups;
     for (int yi = 0; yi < ytiles; yi++)
         for (int xi = 0; xi < xtiles; xi++) {
+            const int tidx = yi * xtiles + xi;
+            if (tidx < tile_first || tidx >= tile_first + tile_count) continue;
             const int tw = std::min((xi + 1) * T, w) - xi * T, th = std::min((yi + 1) * T, hh) - yi * T;
             TileDesc t{};
             t.in_x0 = xi * T - P; t.in_y0 = yi * T - P;
@@ -359,6 +362,7 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
             t.crop_w = tw * 4; t.crop_h = th * 4;
             t.variant = 0; t.base_h = th + 2 * P; t.base_w = tw + 2 * P; t.tta_slot = 0;
             groups[{t.base_h, t.base_w}].push_back(t);
+            if (done) done->push_back(t);
         }
     BatchCtx c{h, ws};
     long long padded = 0;
@@ -442,6 +446,7 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
     if (ch == 4) {  // alpha: bicubic x4 per un-padded tile region, independent of the network
         AlphaArgs aa{};
         aa.img = d_in; aa.img_out = d_out; aa.img_w = w; aa.img_h = hh; aa.tilesize = T;
+        aa.tile_first = tile_first; aa.tile_count = tile_count;
         CK(launch_alpha_bicubic4x(aa, ws->stream));
         c.launches++;
     }
@@ -571,10 +576,17 @@ int rsr_set(rsr_handle* h, int scale, int tilesize, int prepadding)
     return 0;
 }
 
-static int process_impl(rsr_handle* h, const uint8_t* in, int w, int hh, int c, uint8_t* out, bool host_buffers)
+static int process_impl(rsr_handle* h, const uint8_t* in, int w, int hh, int c, uint8_t* out, bool host_buffers, int tile_first = 0,
+                        int tile_count = -1)
 {
     int r = check_args(h, in, w, hh, c, out);
     if (r) return r;
+    const int ntiles_img = ((w + h->tilesize - 1) / h->tilesize) * ((hh + h->tilesize - 1) / h->tilesize);
+    const bool whole = tile_count < 0;
+    if (whole) { tile_first = 0; tile_count = ntiles_img; }
+    if (tile_first < 0 || tile_count < 0 || tile_first + tile_count > ntiles_img)
+        return set_err(h, RSR_ERR_GENERIC, "rsr_process_tiles: tile range outside the image's tile grid");
+    if (tile_count == 0) return 0;
     CK(cudaSetDevice(h->gpuid));
     Workspace* ws = acquire_ws(h);
     if (!ws) return set_err(h, RSR_ERR_CUDA, "cannot create stream/events");
@@ -592,8 +604,19 @@ static int process_impl(rsr_handle* h, const uint8_t* in, int w, int hh, int c, 
         }
         CK(cudaEventRecord(ws->ev0, ws->stream));
         if (host_buffers) CK(cudaMemcpyAsync(ws->img_in.p, in, in_bytes, cudaMemcpyHostToDevice, ws->stream));
-        if ((rr = process_on_device(h, ws, d_in, w, hh, c, d_out, &padded, &launches))) return rr;
-        if (host_buffers) CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ws->stream));
+        std::vector<TileDesc> done;
+        if ((rr = process_on_device(h, ws, d_in, w, hh, c, d_out, &padded, &launches, tile_first, tile_count, whole ? nullptr : &done))) return rr;
+        if (host_buffers) {
+            if (whole) {
+                CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ws->stream));
+            } else {  // only this handle's tile regions travel back: other handles fill the rest of the caller's buffer
+                const size_t pitch = (size_t)w * 4 * c;
+                for (const TileDesc& t : done) {
+                    const size_t off = (size_t)t.out_y0 * pitch + (size_t)t.out_x0 * c;
+                    CK(cudaMemcpy2DAsync(out + off, pitch, d_out + off, pitch, (size_t)t.crop_w * c, (size_t)t.crop_h, cudaMemcpyDeviceToHost, ws->stream));
+                }
+            }
+        }
         CK(cudaEventRecord(ws->ev1, ws->stream));
         CK(cudaStreamSynchronize(ws->stream));
         float ms = 0;
@@ -615,6 +638,18 @@ int rsr_process(rsr_handle* h, const uint8_t* in, int w, int h_, int c, uint8_t*
 int rsr_process_device(rsr_handle* h, const uint8_t* d_in, int w, int h_, int c, uint8_t* d_out)
 {
     return process_impl(h, d_in, w, h_, c, d_out, false);
+}
+
+int rsr_tile_count(const rsr_handle* h, int w, int h_)
+{
+    if (!h || w <= 0 || h_ <= 0 || h->tilesize <= 0) return 0;
+    return ((w + h->tilesize - 1) / h->tilesize) * ((h_ + h->tilesize - 1) / h->tilesize);
+}
+
+int rsr_process_tiles(rsr_handle* h, const uint8_t* in, int w, int h_, int c, uint8_t* out, int tile_first, int tile_count)
+{
+    if (h && tile_count < 0) return set_err(h, RSR_ERR_GENERIC, "rsr_process_tiles: negative tile_count");
+    return process_impl(h, in, w, h_, c, out, true, tile_first, tile_count);
 }
 
 const char* rsr_last_error(const rsr_handle* h) { return h ? h->err.c_str() : "null handle"; }

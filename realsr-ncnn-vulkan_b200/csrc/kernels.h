@@ -121,6 +121,7 @@ struct AlphaArgs {
     uint8_t* img_out;      // RGBA result
     int img_w, img_h;      // source size
     int tilesize;
+    int tile_first, tile_count;  // only output pixels of tiles [tile_first, tile_first + tile_count) (row-major tile index) are written
 };
 cudaError_t launch_alpha_bicubic4x(const AlphaArgs& a, cudaStream_t stream);
 

@@ -190,6 +190,8 @@ __global__ void __launch_bounds__(256) alpha_bicubic4x_kernel(const AlphaArgs a)
     const int T = a.tilesize;
     // the tile this output pixel belongs to, and the tile's un-padded source region
     const int xi = (X >> 2) / T, yi = (Y >> 2) / T;
+    const int tidx = yi * ((a.img_w + T - 1) / T) + xi;
+    if (tidx < a.tile_first || tidx >= a.tile_first + a.tile_count) return;  // another handle's tile (rsr_process_tiles)
     const int tx0 = xi * T, ty0 = yi * T;
     const int tw = min(tx0 + T, a.img_w) - tx0, th = min(ty0 + T, a.img_h) - ty0;
     float ca[4], cb[4];

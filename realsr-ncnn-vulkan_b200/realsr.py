@@ -45,6 +45,10 @@ def load_library():
     lib.rsr_process.argtypes = [vp, vp, ci, ci, ci, vp]
     lib.rsr_process_device.restype = ci
     lib.rsr_process_device.argtypes = [vp, vp, ci, ci, ci, vp]
+    lib.rsr_tile_count.restype = ci
+    lib.rsr_tile_count.argtypes = [vp, ci, ci]
+    lib.rsr_process_tiles.restype = ci
+    lib.rsr_process_tiles.argtypes = [vp, vp, ci, ci, ci, vp, ci, ci]
     lib.rsr_last_error.restype = cc
     lib.rsr_last_error.argtypes = [vp]
     lib.rsr_kernel_launches.restype = ll
@@ -107,6 +111,22 @@ class RealSR:
             raise RealSRError("outimage must be a preallocated C-contiguous uint8 array of shape (4h, 4w, c)")
         self._push_params()
         return self._lib.rsr_process(self._h, inimage.ctypes.data, w, h, c, outimage.ctypes.data)
+
+    def tile_count(self, w, h):
+        """number of tiles of a w x h image at the current tilesize (reference tile grid, src/realsr.cpp:170-171)"""
+        self._push_params()
+        return int(self._lib.rsr_tile_count(self._h, int(w), int(h)))
+
+    def process_tiles(self, inimage, outimage, tile_first, tile_count):
+        """process() restricted to tiles [tile_first, tile_first + tile_count) (row-major over the tile grid): only their
+        regions of `outimage` are written.  Building block of sharded.process_sharded (one image over several GPUs)."""
+        if inimage.dtype != np.uint8 or inimage.ndim != 3 or not inimage.flags.c_contiguous:
+            raise RealSRError("inimage must be a C-contiguous uint8 HWC array")
+        h, w, c = inimage.shape
+        if outimage.dtype != np.uint8 or outimage.shape != (h * 4, w * 4, c) or not outimage.flags.c_contiguous:
+            raise RealSRError("outimage must be a preallocated C-contiguous uint8 array of shape (4h, 4w, c)")
+        self._push_params()
+        return self._lib.rsr_process_tiles(self._h, inimage.ctypes.data, w, h, c, outimage.ctypes.data, int(tile_first), int(tile_count))
 
     def process_ptr(self, in_ptr, w, h, c, out_ptr):
         """process() on raw HOST pointers (e.g. pinned torch tensors): same contract as the C ABI rsr_process."""

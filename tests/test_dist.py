@@ -55,3 +55,27 @@ def test_shard_items_balanced():
         parts = [rd.shard_items(n, w, r) for r in range(w)]
         assert sorted(sum(parts, [])) == list(range(n))
         assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_split_tiles_partitions_the_grid():
+    """tile-granular sharding of one image (sharded.split_tiles): contiguous, complete, disjoint, balanced"""
+    import realsr_ncnn_vulkan_b200 as rb
+    for (w, h, T, n) in [(1920, 1080, 400, 2), (1920, 1080, 400, 8), (3840, 2160, 200, 8), (3840, 2160, 200, 3), (256, 256, 200, 4),
+                         (100, 100, 200, 8), (1280, 720, 200, 5), (33, 977, 32, 7)]:
+        costs = rb.tile_costs(w, h, T, 10)
+        assert len(costs) == -(-w // T) * -(-h // T)
+        parts = rb.split_tiles(w, h, T, 10, n)
+        assert len(parts) == n
+        nxt = 0
+        for first, count in parts:
+            assert first == nxt and count >= 0
+            nxt = first + count
+        assert nxt == len(costs)
+        loads = [sum(costs[f:f + c]) for f, c in parts]
+        assert sum(loads) == sum(costs)
+        # no part carries more than its fair share plus one (largest) tile
+        assert max(loads) <= sum(costs) / n + max(costs)
+    # BASELINE configs[3] over 8 GPUs: 220 tiles, every GPU within 4 % of 1/8 of the work
+    costs = rb.tile_costs(3840, 2160, 200, 10)
+    loads = [sum(costs[f:f + c]) for f, c in rb.split_tiles(3840, 2160, 200, 10, 8)]
+    assert max(loads) / (sum(costs) / 8) < 1.04, loads

@@ -61,3 +61,21 @@ def test_split_epilogue_tta_and_goldens(models_dir):
     a.tilesize = b.tilesize = 32
     assert a.process(img, oa) == 0 and b.process(img, ob) == 0
     assert np.array_equal(oa, ob)
+
+
+@pytest.mark.parametrize("shape,tile,parts", [((150, 130, 3), 32, 3), ((90, 200, 4), 64, 2), ((1080, 1920, 3), 400, 4)])
+def test_tile_sharded_process_is_byte_identical(models_dir, shape, tile, parts):
+    """sharded.process_sharded: several handles (here all on GPU 0, one thread each) each run a contiguous tile range of
+    ONE image and copy only their regions back; the assembled buffer equals a plain process() call byte for byte"""
+    engines = [_engine() for _ in range(parts)]
+    for e in engines:
+        e.tilesize = tile
+    img = np.random.default_rng(11).integers(0, 256, shape, dtype=np.uint8)
+    ref = np.zeros((shape[0] * 4, shape[1] * 4, shape[2]), np.uint8)
+    out = np.full_like(ref, 0x5A)
+    assert engines[0].process(img, ref) == 0
+    assert rb.process_sharded(engines, img, out) == 0, [e.last_error() for e in engines]
+    assert np.array_equal(out, ref)
+    # ranges outside the grid are refused
+    n = engines[0].tile_count(shape[1], shape[0])
+    assert engines[0].process_tiles(img, out, n - 1, 2) != 0 and "tile range" in engines[0].last_error()
