@@ -29,9 +29,14 @@ constexpr int BW = P - 2;
 constexpr int BH = 8;                         // output rows per CTA
 constexpr int BAND = 2 * BH;                  // output rows per CTA pair
 constexpr int MT = BH * P / 128;              // 2 M-tiles per CTA
-constexpr int NA_MAX = 4;                     // A stages (run-time count: as many as fit next to the resident weights)
-constexpr int A_BYTES = (BH + 2) * P * 128;   // 40 KB
-constexpr int A_STAGE = A_BYTES + 1024;
+// K-block KB = input channels per A stage / per resident weight block: 64 (one SWIZZLE_128B box per 64-channel plane) or
+// 32 (option conv_impl=3: SWIZZLE_64B half-plane boxes -- the 96- and 160-channel convs stop fetching a half plane of
+// zero-weighted channels, and twice as many, half as large stages pipeline the 192-channel conv more finely).
+constexpr int NA_MAX = 8;                     // A stages (run-time count: as many as fit next to the resident weights; KB=64: <= 4)
+__host__ __device__ constexpr int na_max(int kb) { return kb == 64 ? 4 : 8; }
+__host__ __device__ constexpr int a_bytes(int kb) { return (BH + 2) * P * kb * 2; }   // 40 KB / 20 KB
+__host__ __device__ constexpr int a_slack(int kb) { return kb == 64 ? 1024 : 512; }    // zeroed rows behind the box (kx taps of the last positions)
+__host__ __device__ constexpr int a_stage(int kb) { return a_bytes(kb) + a_slack(kb); }
 constexpr int NEPI = 8;
 constexpr int NTHREADS = (3 + NEPI) * 32;
 constexpr int STAGE_BYTES = 32 * 20 * 4;
@@ -43,7 +48,7 @@ constexpr int SMEM_FIXED = 1024 /*align*/ + NEPI * STAGE_BYTES + 256 /*barriers*
 
 // this CTA's half of the weights of one (plane, ky): Cout=64 -> pair half (64 rows) + single half (32 rows);
 // Cout<=32 -> triple half (64 rows); Cout<=16 -> 32 rows
-__host__ __device__ constexpr int w_bytes_per_ky(int nreal) { return nreal == 64 ? 12288 : (nreal == 32 ? 6144 : 4096); }
+__host__ __device__ constexpr int w_bytes_per_ky(int nreal, int kb) { return (nreal == 64 ? 12288 : (nreal == 32 ? 6144 : 4096)) * kb / 64; }
 
 struct Bars {
     uint64_t a_full[NA_MAX], a_empty[NA_MAX];
@@ -342,16 +347,19 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
     }
 }
 
-template <int NREAL, int MODE, bool SPLIT>
+template <int NREAL, int MODE, bool SPLIT, int KB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const int NA)
 {
+    constexpr int A_BYTES = a_bytes(KB), A_STAGE = a_stage(KB);
+    constexpr int ROWB = KB * 2;                     // bytes per smem row of an operand tile (one pixel / one weight row)
+    constexpr int GOFF = 64 * ROWB;                  // Cout=64: offset of the single-tap group behind the 64 pair rows
     constexpr int NGROUPS = NREAL == 64 ? 2 : 1;           // MMA groups per kernel row (pair + single, or one triple)
     constexpr int ROWS_PER_KY = NREAL == 64 ? 192 : (NREAL == 32 ? 96 : 64);  // weight rows per (plane, ky), see model.cpp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int nchunk = (a.cin + 63) >> 6;
-    constexpr int W_KY = w_bytes_per_ky(NREAL);
+    const int nchunk = (a.cin + KB - 1) / KB;       // K-blocks
+    constexpr int W_KY = w_bytes_per_ky(NREAL, KB);
     uint8_t* smA = smem;
     uint8_t* smW = smem + NA * A_STAGE;                  // resident weights: [plane][ky] x W_KY bytes
     uint8_t* smStage = smW + nchunk * 3 * W_KY;
@@ -377,9 +385,12 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + NREAL) s_bias[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
     // rows behind each A box: read by the kx=2 taps of the last two (never stored) positions; keep them finite
-    if (threadIdx.x >= 96 && threadIdx.x < 96 + NA * 64) {  // NA <= 4
-        const int i = threadIdx.x - 96;
-        reinterpret_cast<uint4*>(smA + (i >> 6) * A_STAGE + A_BYTES)[i & 63] = make_uint4(0, 0, 0, 0);
+    {
+        constexpr int SL16 = a_slack(KB) / 16;  // uint4 per stage: 64 (KB=64, NA <= 4) or 32 (KB=32, NA <= 8): <= 256 threads
+        if (threadIdx.x >= 96 && threadIdx.x < 96 + NA * SL16) {
+            const int i = threadIdx.x - 96;
+            reinterpret_cast<uint4*>(smA + (i / SL16) * A_STAGE + A_BYTES)[i % SL16] = make_uint4(0, 0, 0, 0);
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     cluster_sync();  // barriers of both CTAs are initialised before anybody signals across
@@ -397,10 +408,12 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
             for (int c = 0; c < nchunk; c++)
                 for (int ky = 0; ky < 3; ky++) {
                     uint8_t* dst = smW + (c * 3 + ky) * W_KY;
-                    const int row0 = (c * 3 + ky) * ROWS_PER_KY;
-                    if (NREAL == 16) tma2_load_2d(dst, &maps.w32, wbar, 0, row0 + (int)rank * 32);
-                    else tma2_load_2d(dst, &maps.w, wbar, 0, row0 + (int)rank * (NREAL == 32 ? 48 : 64));  // maps.w box: 48 rows for Cout<=32
-                    if (NREAL == 64) tma2_load_2d(dst + 8192, &maps.w32, wbar, 0, row0 + 128 + (int)rank * 32);
+                    // weight rows are stored per (64-channel plane, ky); a 32-channel K-block is the left or right half of a row
+                    const int plane = KB == 64 ? c : (c >> 1), col = KB == 64 ? 0 : (c & 1) * 32;
+                    const int row0 = (plane * 3 + ky) * ROWS_PER_KY;
+                    if (NREAL == 16) tma2_load_2d(dst, &maps.w32, wbar, col, row0 + (int)rank * 32);
+                    else tma2_load_2d(dst, &maps.w, wbar, col, row0 + (int)rank * (NREAL == 32 ? 48 : 64));  // maps.w box: 48 rows for Cout<=32
+                    if (NREAL == 64) tma2_load_2d(dst + GOFF, &maps.w32, wbar, col, row0 + 128 + (int)rank * 32);
                 }
         } else if (is_leader && (a.debug_mask & 4) && lane == 0) {
             mbar_arrive(&bars->w_full);
@@ -427,7 +440,8 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                         if (is_leader) mbar_arrive(&bars->a_full[s]);
                     } else {
                         if (is_leader) mbar_expect_tx(&bars->a_full[s], 2 * A_BYTES);
-                        tma2_load_4d(smA + s * A_STAGE, &maps.m[c], mapa_u32(smem_u32(&bars->a_full[s]), 0), 0, tx * BW - 1,
+                        tma2_load_4d(smA + s * A_STAGE, &maps.m[KB == 64 ? c : (c >> 1)], mapa_u32(smem_u32(&bars->a_full[s]), 0),
+                                     KB == 64 ? 0 : (c & 1) * 32, tx * BW - 1,
                                      by * BAND + (int)rank * BH - 1, b);
                     }
                 }
@@ -439,7 +453,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
             const bool leader = elect_one();
             constexpr uint32_t idesc128 = umma_idesc_f16(256, NREAL == 32 ? 96 : 128);  // Cout<=32: three 32-wide tap groups
             constexpr uint32_t idesc64 = umma_idesc_f16(256, 64);
-            const uint64_t desc_hi = umma_desc_sw128(0, 1024, 0);
+            const uint64_t desc_hi = KB == 64 ? umma_desc_sw128(0, 1024, 0) : umma_desc_sw64(0, 512, 0);
             int ca = 0, ti = 0;
             mbar_wait(&bars->w_full, 0);
             tc_fence_after();
@@ -457,21 +471,21 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                     mbar_wait(&bars->a_full[sA], (ca / NA) & 1);
                     tc_fence_after();
                     if (ts_on && c == 0) a.dbg_ts[ti * 8 + 2] = clock64();
-                    const int rem = a.cin - c * 64;
-                    const int ksteps = rem >= 64 ? 4 : (rem >> 4);
+                    const int rem = a.cin - c * KB;
+                    const int ksteps = rem >= KB ? KB / 16 : (rem >> 4);
                     const uint32_t a_base = smem_u32(smA + sA * A_STAGE);
                     for (int ky = 0; ky < 3; ky++)
 #pragma unroll
                         for (int g = 0; g < NGROUPS; g++) {
                             const uint32_t idesc = (NREAL == 16 || g == 1) ? idesc64 : idesc128;
-                            const uint64_t db0 = desc_hi | (uint64_t)(((w_base + (uint32_t)((c * 3 + ky) * W_KY + g * 8192)) & 0x3FFFFu) >> 4);
-                            const uint64_t da0 = desc_hi | (uint64_t)(((a_base + (uint32_t)(ky * P + g * 2) * 128u) & 0x3FFFFu) >> 4);
+                            const uint64_t db0 = desc_hi | (uint64_t)(((w_base + (uint32_t)((c * 3 + ky) * W_KY + g * GOFF)) & 0x3FFFFu) >> 4);
+                            const uint64_t da0 = desc_hi | (uint64_t)(((a_base + (uint32_t)(ky * P + g * 2) * (uint32_t)ROWB) & 0x3FFFFu) >> 4);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ks++) {
+                            for (int ks = 0; ks < KB / 16; ks++) {
                                 if (ks < ksteps && leader && !(a.debug_mask & 1)) {
                                     const uint32_t accum = (c | ky | g | ks) ? 1u : 0u;
                                     umma2_f16(acc + 0 * DCOLS, da0 + ks * 2, db0 + ks * 2, idesc, accum);
-                                    umma2_f16(acc + 1 * DCOLS, da0 + ks * 2 + 1024, db0 + ks * 2, idesc, accum);
+                                    umma2_f16(acc + 1 * DCOLS, da0 + ks * 2 + (128 * ROWB) / 16, db0 + ks * 2, idesc, accum);  // second M-tile: 128 rows further
                                 }
                             }
                         }
@@ -732,8 +746,8 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
     if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
-template <int NREAL, int MODE, bool SPLIT>
-cudaError_t launch_nms(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
+template <int NREAL, int MODE, bool SPLIT, int KB>
+cudaError_t launch_nmsk(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
 {
     static bool attr_done[64] = {};
     static int num_sms[64] = {};
@@ -742,7 +756,7 @@ cudaError_t launch_nms(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t s
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     dev &= 63;
     if (!attr_done[dev]) {
-        e = cudaFuncSetAttribute(conv3x3_tc2_kernel<NREAL, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+        e = cudaFuncSetAttribute(conv3x3_tc2_kernel<NREAL, MODE, SPLIT, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
         if (e != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         attr_done[dev] = true;
@@ -754,12 +768,12 @@ cudaError_t launch_nms(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t s
     cfg.gridDim = dim3((unsigned)(2 * nclusters));
     cfg.blockDim = dim3(NTHREADS);
     // resident weights first, then as many 41 KB A stages as fit (2..4)
-    const int nchunk = (a.cin + 63) / 64;
-    const int wbytes = nchunk * 3 * w_bytes_per_ky(NREAL);
-    int na = (SMEM_MAX - SMEM_FIXED - wbytes) / A_STAGE;
-    if (na > NA_MAX) na = NA_MAX;
+    const int nchunk = (a.cin + KB - 1) / KB;
+    const int wbytes = nchunk * 3 * w_bytes_per_ky(NREAL, KB);
+    int na = (SMEM_MAX - SMEM_FIXED - wbytes) / a_stage(KB);
+    if (na > na_max(KB)) na = na_max(KB);
     if (na < 2) return cudaErrorInvalidValue;
-    cfg.dynamicSmemBytes = SMEM_FIXED + wbytes + na * A_STAGE;
+    cfg.dynamicSmemBytes = SMEM_FIXED + wbytes + na * a_stage(KB);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -767,14 +781,16 @@ cudaError_t launch_nms(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t s
     cfg.attrs = attr;
     static const int use_pdl = getenv("RSR_NOPDL") ? 0 : 1;  // bring-up switch
     cfg.numAttrs = use_pdl;
-    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<NREAL, MODE, SPLIT>, *in_map, a, na)) != cudaSuccess) return e;
+    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<NREAL, MODE, SPLIT, KB>, *in_map, a, na)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
 template <int NREAL, int MODE>
 cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
 {
-    return a.epi_split ? launch_nms<NREAL, MODE, true>(in_map, a, stream) : launch_nms<NREAL, MODE, false>(in_map, a, stream);
+    if (a.kblock == 32)
+        return a.epi_split ? launch_nmsk<NREAL, MODE, true, 32>(in_map, a, stream) : launch_nmsk<NREAL, MODE, false, 32>(in_map, a, stream);
+    return a.epi_split ? launch_nmsk<NREAL, MODE, true, 64>(in_map, a, stream) : launch_nmsk<NREAL, MODE, false, 64>(in_map, a, stream);
 }
 
 }  // namespace

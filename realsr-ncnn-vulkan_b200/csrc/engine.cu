@@ -63,6 +63,7 @@ struct DeviceModel {
     std::vector<float*> bias;   // per conv, padded to cout_pad
     std::vector<int> cout_pad;
     std::vector<CUtensorMap> wmap, wmap32;  // per conv: 2-D maps over its weight rows, box 64 / 32 rows (CTA-pair kernel)
+    std::vector<CUtensorMap> wmap_k32, wmap32_k32;  // same with 32-channel SWIZZLE_64B boxes (conv_impl 3)
     float* w0 = nullptr;        // Conv_0 fp32 weights [64][27]
     void* blob = nullptr;       // one allocation holding everything
 };
@@ -86,7 +87,8 @@ struct rsr_handle {
     // bytes 1.8->2.1 %, 2.4->3.2 % (natural), 5.3 % faster: the Cout=64 conv is HBM-bound and this removes 384 of its
     // 1024 bytes per pixel.  0 restores the fp32 RDB stream.  CTA-pair kernel only.
     int residual_fp16 = 1;
-    int conv_impl = 2;  // 2 = CTA-pair kernel (conv_tc2.cu, default), 1 = single-CTA .ws kernel (conv_tc.cu, kept for A/B: tools/ab_impl.py)
+    int conv_impl = 2;  // 2 = CTA-pair kernel (conv_tc2.cu, default), 1 = single-CTA .ws kernel (conv_tc.cu, kept for A/B: tools/ab_impl.py),
+                        // 3 = CTA-pair kernel with 32-channel K-blocks (SWIZZLE_64B boxes; opt-in until validated on a B200)
     int debug_mask = 0;  // timing experiments only (see include/realsr_b200.h)
     int time_convs = 0;
     // stats
@@ -126,30 +128,33 @@ int ensure(rsr_handle* h, DevBuf& b, size_t bytes)
     return 0;
 }
 
-int make_wmap(rsr_handle* h, CUtensorMap* m, const void* base, int rows, int box_rows)
+// box_c = 64: SWIZZLE_128B rows of 128 B; box_c = 32: SWIZZLE_64B half rows (conv_impl 3)
+int make_wmap(rsr_handle* h, CUtensorMap* m, const void* base, int rows, int box_rows, int box_c = 64)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[2] = {64, (cuuint64_t)rows};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight map");
     return 0;
 }
 
-int make_map(rsr_handle* h, CUtensorMap* m, const void* base, int C, int W, int H, int B, int box_rows = CONV_BH + 2)
+int make_map(rsr_handle* h, CUtensorMap* m, const void* base, int C, int W, int H, int B, int box_rows = CONV_BH + 2, int box_c = 64)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)CONV_P, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)CONV_P, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char b[160];
         snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d) for C=%d W=%d H=%d B=%d", (int)r, C, W, H, B);
@@ -225,10 +230,11 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
         c.nconv_ev++;
         CK(cudaEventRecord(e0, c.ws->stream));
     }
-    if (h->conv_impl == 2) {
+    if (h->conv_impl >= 2) {
         ConvMaps mm = *map;
-        mm.w = dm.wmap[conv_idx];
-        mm.w32 = dm.wmap32[conv_idx];
+        mm.w = h->conv_impl == 3 ? dm.wmap_k32[conv_idx] : dm.wmap[conv_idx];
+        mm.w32 = h->conv_impl == 3 ? dm.wmap32_k32[conv_idx] : dm.wmap32[conv_idx];
+        a.kblock = h->conv_impl == 3 ? 32 : 64;
         CK(launch_conv3x3_tc2(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
     } else {
         CK(launch_conv3x3_tc(map, a, dm.cout_pad[conv_idx], c.ws->stream));
@@ -263,14 +269,15 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c
     __half* D[2] = {(__half*)ws->d16[0].p, (__half*)ws->d16[1].p};
     const size_t plane = npx * 64;
     ConvMaps mapD[2], mapU1, mapV1, mapU2, mapV2;
-    const int brows = (h->conv_impl == 2 ? CONV2_BH : CONV_BH) + 2;
+    const int brows = (h->conv_impl >= 2 ? CONV2_BH : CONV_BH) + 2;
+    const int box_c = h->conv_impl == 3 ? 32 : 64;
     for (int i = 0; i < 2; i++)
         for (int pl = 0; pl < 3; pl++)
-            if ((r = make_map(h, &mapD[i].m[pl], D[i] + pl * plane, 64, W, H, B, brows))) return r;
-    if ((r = make_map(h, &mapU1.m[0], ws->u1.p, 64, 2 * W, 2 * H, B, brows))) return r;
-    if ((r = make_map(h, &mapV1.m[0], ws->v1.p, 64, 2 * W, 2 * H, B, brows))) return r;
-    if ((r = make_map(h, &mapU2.m[0], ws->u2.p, 64, 4 * W, 4 * H, B, brows))) return r;
-    if ((r = make_map(h, &mapV2.m[0], ws->v2.p, 64, 4 * W, 4 * H, B, brows))) return r;
+            if ((r = make_map(h, &mapD[i].m[pl], D[i] + pl * plane, 64, W, H, B, brows, box_c))) return r;
+    if ((r = make_map(h, &mapU1.m[0], ws->u1.p, 64, 2 * W, 2 * H, B, brows, box_c))) return r;
+    if ((r = make_map(h, &mapV1.m[0], ws->v1.p, 64, 2 * W, 2 * H, B, brows, box_c))) return r;
+    if ((r = make_map(h, &mapU2.m[0], ws->u2.p, 64, 4 * W, 4 * H, B, brows, box_c))) return r;
+    if ((r = make_map(h, &mapV2.m[0], ws->v2.p, 64, 4 * W, 4 * H, B, brows, box_c))) return r;
     for (ConvMaps* cm : {&mapU1, &mapV1, &mapU2, &mapV2}) cm->m[1] = cm->m[2] = cm->m[0];
 
     // Conv_0 + preproc
@@ -298,7 +305,7 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c
             }
             ConvArgs a = base;  // x5 -> residual(s) -> x0 of the next RDB in the other buffer
             a.mode = CONV_RDB_OUT; a.rrdb_end = (rdb == 2);
-            if (h->residual_fp16 && h->conv_impl == 2) { a.mode = CONV_RDB_OUT16; a.res16 = D[cur]; }
+            if (h->residual_fp16 && h->conv_impl >= 2) { a.mode = CONV_RDB_OUT16; a.res16 = D[cur]; }
             a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
             if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, 4)))) return r;
             cur ^= 1;
@@ -549,9 +556,13 @@ int rsr_load(rsr_handle* h, const char* parampath, const char* modelpath)
     dm.bias.assign(nconv, nullptr);
     dm.wmap.resize(nconv);
     dm.wmap32.resize(nconv);
+    dm.wmap_k32.resize(nconv);
+    dm.wmap32_k32.resize(nconv);
     for (int i = 1; i < nconv; i++) {
         int rr = make_wmap(h, &dm.wmap[i], (uint8_t*)dm.blob + off_r[i], nrows[i], dm.cout_pad[i] == 32 ? 48 : 64);
         if (!rr) rr = make_wmap(h, &dm.wmap32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], 32);
+        if (!rr) rr = make_wmap(h, &dm.wmap_k32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], dm.cout_pad[i] == 32 ? 48 : 64, 32);
+        if (!rr) rr = make_wmap(h, &dm.wmap32_k32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], 32, 32);
         if (rr) return rr;
     }
     for (int i = 0; i < nconv; i++) {
@@ -664,7 +675,10 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
     else if (!strcmp(key, "epilogue_split")) h->epilogue_split = value ? 1 : 0;
     else if (!strcmp(key, "debug_mask")) h->debug_mask = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
-    else if (!strcmp(key, "conv_impl")) h->conv_impl = (int)value;
+    else if (!strcmp(key, "conv_impl")) {
+        if (value < 1 || value > 3) return set_err(h, RSR_ERR_GENERIC, "conv_impl must be 1, 2 or 3");
+        h->conv_impl = (int)value;
+    }
     else if (!strcmp(key, "residual_fp16")) h->residual_fp16 = (int)value;
     else return set_err(h, RSR_ERR_GENERIC, std::string("unknown option ") + key);
     return 0;
@@ -746,9 +760,11 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     ConvMaps map;
     int r = 0;
     for (int pl = 0; pl < 3; pl++)
-        if ((r = make_map(h, &map.m[pl], d_in + (size_t)(pl < nplane ? pl : 0) * npx * 64, 64, W, H, 1, (h->conv_impl == 2 ? CONV2_BH : CONV_BH) + 2))) return r;
-    map.w = h->dm.wmap[conv_index];
-    map.w32 = h->dm.wmap32[conv_index];
+        if ((r = make_map(h, &map.m[pl], d_in + (size_t)(pl < nplane ? pl : 0) * npx * 64, 64, W, H, 1, (h->conv_impl >= 2 ? CONV2_BH : CONV_BH) + 2,
+                          h->conv_impl == 3 ? 32 : 64)))
+            return r;
+    map.w = h->conv_impl == 3 ? h->dm.wmap_k32[conv_index] : h->dm.wmap[conv_index];
+    map.w32 = h->conv_impl == 3 ? h->dm.wmap32_k32[conv_index] : h->dm.wmap32[conv_index];
     ConvArgs a{};
     a.wpk = h->dm.wpk[conv_index]; a.bias = h->dm.bias[conv_index]; a.cin = cl.cin;
     a.H = H; a.W = W; a.B = 1;
@@ -758,6 +774,7 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     a.mode = npad == 16 ? CONV_LAST_F32 : CONV_STORE16;
     a.debug_mask = h->debug_mask;
     a.epi_split = h->epilogue_split;
+    a.kblock = h->conv_impl == 3 ? 32 : 64;
     long long* d_ts = nullptr;
     float* d_r32 = nullptr;
     if (getenv("RSR_DBG_RDB") && npad == 64) {  // bring-up: time the Cout=64 conv with its real (CONV_RDB_OUT) epilogue
@@ -775,7 +792,7 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
         a.dbg_ts = d_ts;
     }
     for (int rep = 0; rep < (d_ts ? 2 : 1); rep++) {
-        if (h->conv_impl == 2) CK(launch_conv3x3_tc2(&map, a, npad, 0));
+        if (h->conv_impl >= 2) CK(launch_conv3x3_tc2(&map, a, npad, 0));
         else CK(launch_conv3x3_tc(&map, a, npad, 0));
     }
     CK(cudaDeviceSynchronize());

@@ -61,6 +61,7 @@ struct ConvArgs {
     int prepad_s;        // prepadding*scale
     float* tta_out;
     long long* dbg_ts;   // optional (bring-up): per-tile clock64 stamps of cluster 0, 8 slots per tile, see conv_tc2.cu
+    int kblock;           // CTA-pair kernel: input channels per A stage, 64 (default) or 32 (tensor maps must have 32-channel SWIZZLE_64B boxes)
     int epi_split;        // CTA-pair kernel: 1 = channel-split epilogue with early accumulator hand-back (conv_tc2.cu: epilogue_split)
     int debug_mask;       // debug mask for timing experiments (0 in production): 1 no MMA, 2 no A loads, 4 no B loads, 8 no epilogue I/O
 };

@@ -146,6 +146,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo
     d |= (uint64_t)2 << 61;
     return d;
 }
+// Same for SWIZZLE_64B (layout type 4): rows of 64 B (32 fp16 of K = two K=16 steps), 8-row groups `sbo` = 512 B apart.
+// UNVERIFIED on hardware at the time of writing (conv_impl=3, see conv_tc2.cu); the SWIZZLE_128B form above is verified.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(base_offset & 7u) << 49;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
 // kind::f16 instruction descriptor: D=F32 (bits[4,6)=1), A=B=F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N)
 {
