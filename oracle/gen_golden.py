@@ -72,6 +72,11 @@ def main():
         return np.ascontiguousarray(np.dstack([img, a]))
     cases.append(("rgba_noise_41x30_df2k_t200", rgba(noise(30, 41, 1006), 6), "models-DF2K", 200, 0))
     cases.append(("rgba_natural_36x28_jpeg_t200", rgba(natural(28, 36, 1007), 7), "models-DF2K_JPEG", 200, 0))
+    # smallest sizes for which the reference is defined: with w or h <= prepadding (10) ncnn's reflect border
+    # (copy_make_border, called at realsr.cpp:613,:764) reads outside the image -- the oracle port and the reference then
+    # disagree arbitrarily (probed: 10x10, 1x1), the engine clamps; 11 px is the first well-defined size
+    cases.append(("noise_12x11_df2k_tta_t32", noise(11, 12, 1008), "models-DF2K", 32, 1))
+    cases.append(("noise_45x11_jpeg_t32", noise(11, 45, 1009), "models-DF2K_JPEG", 32, 0))
     only_new = "--only-new" in sys.argv
     manifest = {"generator": "oracle/gen_golden.py", "reference_binary": "oracle/_ref/oracle_ref_avx2 (ncnn b4ba207, AVX2+FMA, OpenMP)",
                 "prepadding": 10, "cases": []}
