@@ -90,7 +90,8 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
     const uint32_t acc_empty_leader1 = mapa_u32(smem_u32(&bars->acc_empty[1]), 0);
     int ti = 0;
     for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
-        const int b = t / tiles_per_img, rem = t - b * tiles_per_img;
+        const int tt = a.reverse ? ntiles - 1 - t : t;  // serpentine layer order, see ConvArgs::reverse
+        const int b = tt / tiles_per_img, rem = tt - b * tiles_per_img;
         const int by = rem / tiles_x, tx = rem - by * tiles_x;
         const int x0 = tx * BW;
         const int buf = ti & 1;
@@ -430,7 +431,8 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
         const bool leader = elect_one();
         int ca = 0;
         for (int t = cluster_id; t < ntiles; t += nclusters) {
-            const int b = t / tiles_per_img, rem = t - b * tiles_per_img;
+            const int tt = a.reverse ? ntiles - 1 - t : t;  // serpentine layer order, see ConvArgs::reverse
+            const int b = tt / tiles_per_img, rem = tt - b * tiles_per_img;
             const int by = rem / tiles_x, tx = rem - by * tiles_x;
             for (int c = 0; c < nchunk; c++, ca++) {
                 const int s = ca % NA;
@@ -515,7 +517,8 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
         int ti = 0;
         for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
             if ((ti & 1) != group) continue;
-            const int b = t / tiles_per_img, rem = t - b * tiles_per_img;
+            const int tt = a.reverse ? ntiles - 1 - t : t;  // serpentine layer order, see ConvArgs::reverse
+            const int b = tt / tiles_per_img, rem = tt - b * tiles_per_img;
             const int by = rem / tiles_x, tx = rem - by * tiles_x;
             const int x0 = tx * BW;
             const int buf = group;

@@ -82,6 +82,7 @@ struct rsr_handle {
     // options
     long long max_batch = 0;  // 0 = auto
     int epilogue_split = 0;   // CTA-pair kernel: channel-split epilogue (see conv_tc2.cu)
+    int serpentine = 0;       // CTA-pair kernel: alternate the tile walk direction from conv to conv (L2 reuse, see ConvArgs::reverse)
     // 1 (default): the RDB-level residual t = 0.2*x5 + x0 takes x0 from the fp16 dense buffer instead of an fp32 copy (the
     // RRDB-level skip stays fp32).  Measured on the goldens: max error unchanged (1 LSB natural / 2 LSB noise), off-by-one
     // bytes 1.8->2.1 %, 2.4->3.2 % (natural), 5.3 % faster: the Cout=64 conv is HBM-bound and this removes 384 of its
@@ -217,6 +218,7 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
     a.cin = h->model.convs[conv_idx].cin;
     a.debug_mask = h->debug_mask;
     a.epi_split = h->epilogue_split;
+    a.reverse = h->serpentine ? (int)(c.launches & 1) : 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->time_convs) {
         if (c.nconv_ev >= c.ws->conv_events.size()) {
@@ -673,6 +675,7 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
     if (!h || !key) return RSR_ERR_GENERIC;
     if (!strcmp(key, "max_batch")) h->max_batch = value;
     else if (!strcmp(key, "epilogue_split")) h->epilogue_split = value ? 1 : 0;
+    else if (!strcmp(key, "serpentine")) h->serpentine = value ? 1 : 0;
     else if (!strcmp(key, "debug_mask")) h->debug_mask = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
     else if (!strcmp(key, "conv_impl")) {

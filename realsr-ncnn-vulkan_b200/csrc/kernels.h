@@ -61,6 +61,9 @@ struct ConvArgs {
     int prepad_s;        // prepadding*scale
     float* tta_out;
     long long* dbg_ts;   // optional (bring-up): per-tile clock64 stamps of cluster 0, 8 slots per tile, see conv_tc2.cu
+    int reverse;          // CTA-pair kernel: walk the work tiles from last to first.  The engine alternates it from one conv to the next
+                          // ("serpentine" option) so that a conv starts on the pixels the previous conv touched last -- the part of its
+                          // inputs (and of the previous conv's outputs) that is still in the 126 MB L2
     int kblock;           // CTA-pair kernel: input channels per A stage, 64 (default) or 32 (tensor maps must have 32-channel SWIZZLE_64B boxes)
     int epi_split;        // CTA-pair kernel: 1 = channel-split epilogue with early accumulator hand-back (conv_tc2.cu: epilogue_split)
     int debug_mask;       // debug mask for timing experiments (0 in production): 1 no MMA, 2 no A loads, 4 no B loads, 8 no epilogue I/O

@@ -45,6 +45,19 @@ def test_split_epilogue_is_bit_identical(models_dir, residual_fp16):
         assert np.array_equal(a, b), (h, w, c, tile, diff_stats(a, b))
 
 
+def test_serpentine_tile_order_is_bit_identical(models_dir):
+    """serpentine=1 only permutes the order in which a conv walks its work tiles (every second conv backwards)"""
+    ref, new = _engine(), _engine(serpentine=1)
+    rng = np.random.default_rng(9)
+    for (h, w, c, tile) in [(70, 93, 3, 32), (256, 256, 3, 200), (120, 90, 4, 64), (1080, 1920, 3, 400)]:
+        img = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        a = np.zeros((4 * h, 4 * w, c), np.uint8)
+        b = np.zeros_like(a)
+        ref.tilesize = new.tilesize = tile
+        assert ref.process(img, a) == 0 and new.process(img, b) == 0, new.last_error()
+        assert np.array_equal(a, b), (h, w, c, tile, diff_stats(a, b))
+
+
 def test_split_epilogue_tta_and_goldens(models_dir):
     new = _engine(epilogue_split=1)
     for name, natural in (("natural_48x40_df2k_t32", True), ("noise_50x33_df2k_t32", False), ("readme0_crop96x80_df2k_t64", True)):
