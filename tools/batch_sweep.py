@@ -7,6 +7,10 @@ sys.path.insert(0, ROOT)
 import realsr_ncnn_vulkan_b200 as rb
 e = rb.RealSR(0)
 assert e.load(os.path.join(ROOT, "models/models-DF2K/x4.param"), os.path.join(ROOT, "models/models-DF2K/x4.bin")) == 0
+for kv in os.environ.get("RSR_OPTS", "").split(","):  # e.g. RSR_OPTS=serpentine=1,epilogue_split=1
+    if "=" in kv:
+        k, v = kv.split("=")
+        assert e.set_option(k, int(v)) == 0, e.last_error()
 img = torch.from_numpy(np.random.default_rng(1000).integers(0, 256, (1080, 1920, 3), dtype=np.uint8)).cuda()
 out = torch.empty((4320, 7680, 3), dtype=torch.uint8, device="cuda")
 for tile, mbs in ((400, (0, 1, 2, 3, 4, 0)), (200, (0, 2, 3, 4, 6, 8, 16)), (256, (0, 2, 3, 4, 6))):
