@@ -72,7 +72,45 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b)
 // (profiles/r1_ts_1.txt) show the set-per-group scheme serialising MMA completion (~2 k clk) -> epilogue of that set
 // (~3 k clk) per accumulator set, so the Cout=32 convs run at 2.6 k clk per tile where MMAs / A loads need 1.4 k.  With
 // the early hand-back only the TMEM read (~0.3 k clk) stays on that chain.
-template <int NREAL, int MODE>
+// Where work tile `tt` lives: image b of its group, band by, column tile tx, the group's image size, pixel offset and maps.
+struct TileGeo {
+    int b, by, tx, H, W, desc0, g;
+    size_t pxoff;
+};
+template <bool MULTI>
+__device__ __forceinline__ TileGeo decode_tile(const ConvArgs& a, const int tt, const int tiles_per_img, const int tiles_x)
+{
+    TileGeo r;
+    if constexpr (MULTI) {
+        int g = 0;
+#pragma unroll
+        for (int k = 1; k < 4; k++)
+            if (k < a.ngroups && tt >= a.grp[k].tile_start) g = k;
+        // explicit selects: a dynamically indexed kernel parameter would be copied to local memory
+        const int H = g == 0 ? a.grp[0].H : g == 1 ? a.grp[1].H : g == 2 ? a.grp[2].H : a.grp[3].H;
+        const int W = g == 0 ? a.grp[0].W : g == 1 ? a.grp[1].W : g == 2 ? a.grp[2].W : a.grp[3].W;
+        const int tx_n = g == 0 ? a.grp[0].tiles_x : g == 1 ? a.grp[1].tiles_x : g == 2 ? a.grp[2].tiles_x : a.grp[3].tiles_x;
+        const int tpi = g == 0 ? a.grp[0].tiles_per_img : g == 1 ? a.grp[1].tiles_per_img : g == 2 ? a.grp[2].tiles_per_img : a.grp[3].tiles_per_img;
+        const int t0 = g == 0 ? a.grp[0].tile_start : g == 1 ? a.grp[1].tile_start : g == 2 ? a.grp[2].tile_start : a.grp[3].tile_start;
+        r.desc0 = g == 0 ? a.grp[0].desc0 : g == 1 ? a.grp[1].desc0 : g == 2 ? a.grp[2].desc0 : a.grp[3].desc0;
+        r.pxoff = (size_t)(g == 0 ? a.grp[0].px_off : g == 1 ? a.grp[1].px_off : g == 2 ? a.grp[2].px_off : a.grp[3].px_off);
+        const int lt = tt - t0;
+        r.b = lt / tpi;
+        const int rem = lt - r.b * tpi;
+        r.by = rem / tx_n;
+        r.tx = rem - r.by * tx_n;
+        r.H = H; r.W = W; r.g = g;
+    } else {
+        r.b = tt / tiles_per_img;
+        const int rem = tt - r.b * tiles_per_img;
+        r.by = rem / tiles_x;
+        r.tx = rem - r.by * tiles_x;
+        r.H = a.H; r.W = a.W; r.desc0 = 0; r.g = 0; r.pxoff = 0;
+    }
+    return r;
+}
+
+template <int NREAL, int MODE, bool MULTI>
 __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, const uint32_t tmem_base, uint8_t* smStage, const float* s_bias,
                                                const uint32_t rank, const int cluster_id, const int nclusters, const int ntiles,
                                                const int tiles_per_img, const int tiles_x, const int warp, const int lane)
@@ -91,8 +129,8 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
     int ti = 0;
     for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
         const int tt = a.reverse ? ntiles - 1 - t : t;  // serpentine layer order, see ConvArgs::reverse
-        const int b = tt / tiles_per_img, rem = tt - b * tiles_per_img;
-        const int by = rem / tiles_x, tx = rem - by * tiles_x;
+        const TileGeo geo = decode_tile<MULTI>(a, tt, tiles_per_img, tiles_x);
+        const int b = geo.b, by = geo.by, tx = geo.tx;
         const int x0 = tx * BW;
         const int buf = ti & 1;
         int yy[2];
@@ -101,12 +139,12 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
 #pragma unroll
         for (int i = 0; i < 2; i++) {
             yy[i] = by * BAND + (int)rank * BH + i * 4 + q4;
-            vrow[i] = yy[i] < a.H && !dbg_noepi;
-            rowpix[i] = ((size_t)b * a.H + yy[i]) * a.W + x0;
+            vrow[i] = yy[i] < geo.H && !dbg_noepi;
+            rowpix[i] = geo.pxoff + ((size_t)b * geo.H + yy[i]) * geo.W + x0;
         }
         bool vcol[4];
 #pragma unroll
-        for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < a.W);
+        for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < geo.W);
 
         // ---- residual operands requested before the accumulators are waited for ----
         uint2 x0raw[2][2][4];  // RDB16: [i][hf][r], channels chh*32 + hf*16 + tc*4 .. +3 of pixel tr + 8r
@@ -138,7 +176,7 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
 #pragma unroll
                 for (int i = 0; i < 2; i++)
                     if (vrow[i]) {
-                        const int npx = min(BW, a.W - x0);
+                        const int npx = min(BW, geo.W - x0);
                         const char* p1 = reinterpret_cast<const char*>(a.r32 + rowpix[i] * 64 + chh * 32);
                         for (int l = lane; l < npx; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + (size_t)l * 256));
                     }
@@ -203,8 +241,8 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
         if constexpr (NREAL == 16) {
             const int i = chh;
             const int x = x0 + lane;
-            if (lane < BW && x < a.W && vrow[i]) {
-                const TileDesc td = a.tiles[b];
+            if (lane < BW && x < geo.W && vrow[i]) {
+                const TileDesc td = a.tiles[geo.desc0 + b];
                 float o[3];
 #pragma unroll
                 for (int j = 0; j < 3; j++) o[j] = o3[j] + s_bias[j];
@@ -219,7 +257,7 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
                         }
                     }
                 } else {
-                    float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)a.H * a.W) + (size_t)yy[i] * a.W + x;
+                    float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)geo.H * geo.W) + (size_t)yy[i] * geo.W + x;
                     *dst = make_float4(o[0], o[1], o[2], 0.f);
                 }
             }
@@ -245,7 +283,7 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
                 for (int r = 0; r < 2; r++) {
                     const int px = p + 16 * r;
                     const uint4 o = *reinterpret_cast<const uint4*>(stg + px * 20 + 4 * tc2);
-                    if (px < BW && x0 + px < a.W && vrow[i]) *reinterpret_cast<uint4*>(orow + (size_t)px * a.out_cs) = o;
+                    if (px < BW && x0 + px < geo.W && vrow[i]) *reinterpret_cast<uint4*>(orow + (size_t)px * a.out_cs) = o;
                 }
                 __syncwarp();
             }
@@ -348,7 +386,7 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
     }
 }
 
-template <int NREAL, int MODE, bool SPLIT, int KB>
+template <int NREAL, int MODE, bool SPLIT, int KB, bool MULTI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const int NA)
 {
@@ -372,7 +410,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
     const bool is_leader = rank == 0;
     const int tiles_x = (a.W + BW - 1) / BW, bands_y = (a.H + BAND - 1) / BAND;
     const int tiles_per_img = tiles_x * bands_y;
-    const int ntiles = tiles_per_img * a.B;       // pair tiles
+    const int ntiles = MULTI ? a.ntiles_multi : tiles_per_img * a.B;  // pair tiles (MULTI: tiles_x / tiles_per_img come per group)
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
@@ -381,6 +419,10 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
         for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], SPLIT ? 2 * NEPI : NEPI); }  // acc_empty: 4 (SPLIT: 8) warps x 2 CTAs
         mbar_fence_init();
         for (int i = 0; i < 3; i++) tma_prefetch_desc(&maps.m[i]);
+        if constexpr (MULTI) {
+            for (int g = 1; g < a.ngroups; g++)
+                for (int i = 0; i < 3; i++) tma_prefetch_desc(&maps.mg[g - 1][i]);
+        }
         tma_prefetch_desc(&maps.w);
         tma_prefetch_desc(&maps.w32);
     }
@@ -432,8 +474,9 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
         int ca = 0;
         for (int t = cluster_id; t < ntiles; t += nclusters) {
             const int tt = a.reverse ? ntiles - 1 - t : t;  // serpentine layer order, see ConvArgs::reverse
-            const int b = tt / tiles_per_img, rem = tt - b * tiles_per_img;
-            const int by = rem / tiles_x, tx = rem - by * tiles_x;
+            const TileGeo geo = decode_tile<MULTI>(a, tt, tiles_per_img, tiles_x);
+            const int b = geo.b, by = geo.by, tx = geo.tx;
+            const CUtensorMap* gmaps = (MULTI && geo.g > 0) ? maps.mg[geo.g - 1] : maps.m;
             for (int c = 0; c < nchunk; c++, ca++) {
                 const int s = ca % NA;
                 mbar_wait(&bars->a_empty[s], ((ca / NA) & 1) ^ 1);
@@ -442,7 +485,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                         if (is_leader) mbar_arrive(&bars->a_full[s]);
                     } else {
                         if (is_leader) mbar_expect_tx(&bars->a_full[s], 2 * A_BYTES);
-                        tma2_load_4d(smA + s * A_STAGE, &maps.m[KB == 64 ? c : (c >> 1)], mapa_u32(smem_u32(&bars->a_full[s]), 0),
+                        tma2_load_4d(smA + s * A_STAGE, &gmaps[KB == 64 ? c : (c >> 1)], mapa_u32(smem_u32(&bars->a_full[s]), 0),
                                      KB == 64 ? 0 : (c & 1) * 32, tx * BW - 1,
                                      by * BAND + (int)rank * BH - 1, b);
                     }
@@ -500,7 +543,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
     } else if (warp == 2) {
         // weight warp: its work (the one-time resident-weight fetch) happened in the prologue
     } else if constexpr (SPLIT) {
-        epilogue_split<NREAL, MODE>(a, bars, tmem_base, smStage, s_bias, rank, cluster_id, nclusters, ntiles, tiles_per_img, tiles_x, warp, lane);
+        epilogue_split<NREAL, MODE, MULTI>(a, bars, tmem_base, smStage, s_bias, rank, cluster_id, nclusters, ntiles, tiles_per_img, tiles_x, warp, lane);
     } else {
         // ---------------- epilogue: warps 3..10 in two groups of four ----------------
         // Group g = (warp-3)/4 owns accumulator set g, i.e. every second work tile; inside a group warp q4 = warp % 4
@@ -518,8 +561,8 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
         for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
             if ((ti & 1) != group) continue;
             const int tt = a.reverse ? ntiles - 1 - t : t;  // serpentine layer order, see ConvArgs::reverse
-            const int b = tt / tiles_per_img, rem = tt - b * tiles_per_img;
-            const int by = rem / tiles_x, tx = rem - by * tiles_x;
+            const TileGeo geo = decode_tile<MULTI>(a, tt, tiles_per_img, tiles_x);
+            const int b = geo.b, by = geo.by, tx = geo.tx;
             const int x0 = tx * BW;
             const int buf = group;
             int yy[2];
@@ -528,12 +571,12 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
 #pragma unroll
             for (int i = 0; i < 2; i++) {
                 yy[i] = by * BAND + (int)rank * BH + i * 4 + q4;
-                vrow[i] = yy[i] < a.H && !dbg_noepi;
-                rowpix[i] = ((size_t)b * a.H + yy[i]) * a.W + x0;
+                vrow[i] = yy[i] < geo.H && !dbg_noepi;
+                rowpix[i] = geo.pxoff + ((size_t)b * geo.H + yy[i]) * geo.W + x0;
             }
             bool vcol[4];
 #pragma unroll
-            for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < a.W);
+            for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < geo.W);
             // residual operands.  fp32 modes (CONV_RDB_OUT with T32, CONV_TRUNK with F32): one (M-tile, 32-channel block) is
             // fetched one block ahead of use.  CONV_RDB_OUT16: ALL fp16 x0 values this thread needs for the tile (4 blocks x
             // 8 x 8 B = 64 registers) are requested here, before waiting for the MMAs -- per-tile timestamps showed the
@@ -572,7 +615,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
 #pragma unroll
                     for (int i = 0; i < 2; i++)
                         if (vrow[i]) {
-                            const int npx = min(BW, a.W - x0);
+                            const int npx = min(BW, geo.W - x0);
                             const char* p1 = reinterpret_cast<const char*>(a.r32 + rowpix[i] * 64);
                             for (int l = lane; l < npx * 2; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + (size_t)l * 128));
                         }
@@ -599,8 +642,8 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                         o[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 1) +
                                __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 2) + s_bias[j];
                     const int x = x0 + lane;
-                    if (lane < BW && x < a.W && vrow[i]) {
-                        const TileDesc td = a.tiles[b];
+                    if (lane < BW && x < geo.W && vrow[i]) {
+                        const TileDesc td = a.tiles[geo.desc0 + b];
                         if constexpr (MODE == CONV_LAST_U8) {
                             const int ii = yy[i] - a.prepad_s, jx = x - a.prepad_s;
                             if (ii >= 0 && ii < td.crop_h && jx >= 0 && jx < td.crop_w) {
@@ -612,7 +655,7 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
                                 }
                             }
                         } else {
-                            float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)a.H * a.W) + (size_t)yy[i] * a.W + x;
+                            float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)geo.H * geo.W) + (size_t)yy[i] * geo.W + x;
                             *dst = make_float4(o[0], o[1], o[2], 0.f);
                         }
                     }
@@ -749,8 +792,8 @@ conv3x3_tc2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, cons
     if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
-template <int NREAL, int MODE, bool SPLIT, int KB>
-cudaError_t launch_nmsk(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
+template <int NREAL, int MODE, bool SPLIT, int KB, bool MULTI>
+cudaError_t launch_nmskm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
 {
     static bool attr_done[64] = {};
     static int num_sms[64] = {};
@@ -759,12 +802,13 @@ cudaError_t launch_nmsk(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t 
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     dev &= 63;
     if (!attr_done[dev]) {
-        e = cudaFuncSetAttribute(conv3x3_tc2_kernel<NREAL, MODE, SPLIT, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+        e = cudaFuncSetAttribute(conv3x3_tc2_kernel<NREAL, MODE, SPLIT, KB, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
         if (e != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         attr_done[dev] = true;
     }
-    const long long ntiles = (long long)((a.W + BW - 1) / BW) * ((a.H + BAND - 1) / BAND) * a.B;
+    const long long ntiles = MULTI ? (long long)a.ntiles_multi : (long long)((a.W + BW - 1) / BW) * ((a.H + BAND - 1) / BAND) * a.B;
+    if (ntiles <= 0) return cudaErrorInvalidValue;
     long long nclusters = num_sms[dev] / 2;
     if (ntiles < nclusters) nclusters = ntiles;
     cudaLaunchConfig_t cfg = {};
@@ -784,16 +828,22 @@ cudaError_t launch_nmsk(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t 
     cfg.attrs = attr;
     static const int use_pdl = getenv("RSR_NOPDL") ? 0 : 1;  // bring-up switch
     cfg.numAttrs = use_pdl;
-    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<NREAL, MODE, SPLIT, KB>, *in_map, a, na)) != cudaSuccess) return e;
+    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_tc2_kernel<NREAL, MODE, SPLIT, KB, MULTI>, *in_map, a, na)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
 template <int NREAL, int MODE>
 cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
 {
+    if (a.ngroups > 0) {  // merged multi-shape launch (not for the TTA store mode: its slot stride is per shape)
+        if (MODE == CONV_LAST_F32 || a.ngroups > 4) return cudaErrorInvalidValue;
+        if (a.kblock == 32)
+            return a.epi_split ? launch_nmskm<NREAL, MODE, true, 32, true>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 32, true>(in_map, a, stream);
+        return a.epi_split ? launch_nmskm<NREAL, MODE, true, 64, true>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 64, true>(in_map, a, stream);
+    }
     if (a.kblock == 32)
-        return a.epi_split ? launch_nmsk<NREAL, MODE, true, 32>(in_map, a, stream) : launch_nmsk<NREAL, MODE, false, 32>(in_map, a, stream);
-    return a.epi_split ? launch_nmsk<NREAL, MODE, true, 64>(in_map, a, stream) : launch_nmsk<NREAL, MODE, false, 64>(in_map, a, stream);
+        return a.epi_split ? launch_nmskm<NREAL, MODE, true, 32, false>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 32, false>(in_map, a, stream);
+    return a.epi_split ? launch_nmskm<NREAL, MODE, true, 64, false>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 64, false>(in_map, a, stream);
 }
 
 }  // namespace

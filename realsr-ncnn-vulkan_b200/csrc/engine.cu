@@ -82,6 +82,7 @@ struct rsr_handle {
     // options
     long long max_batch = 0;  // 0 = auto
     int epilogue_split = 0;   // CTA-pair kernel: channel-split epilogue (see conv_tc2.cu)
+    int merge_shapes = 0;     // CTA-pair kernel, no TTA: one launch per layer over all shape groups of a job (see run_merged)
     int serpentine = 0;       // CTA-pair kernel: alternate the tile walk direction from conv to conv (L2 reuse, see ConvArgs::reverse)
     // 1 (default): the RDB-level residual t = 0.2*x5 + x0 takes x0 from the fp16 dense buffer instead of an fp32 copy (the
     // RRDB-level skip stays fp32).  Measured on the goldens: max error unchanged (1 LSB natural / 2 LSB noise), off-by-one
@@ -352,6 +353,148 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c
     return 0;
 }
 
+
+// ---- merged multi-shape launches ("merge_shapes" option, CTA-pair kernel, no TTA) -------------------------------------------
+// A frame's tiles come in up to four padded shapes (interior, right edge, bottom edge, corner).  run_batch launches every
+// layer once per shape; measured per-launch fill/drain (ncu launch list, profiles/README.md): 7.7 us for the Cout=32 convs and
+// 15 us for the Cout=64 conv, i.e. ~13 % of a 1080p step at 4 x 351 conv launches.  Here the shape groups of a job are
+// concatenated pixel-major in every activation buffer and each layer runs as ONE launch over all of them (ConvArgs::grp).
+struct Grp {
+    size_t off;     // first TileDesc of the group in the call's descriptor array
+    int n, H, W;    // tiles, padded tile size
+    size_t px_off;  // first pixel of the group in the (LR-resolution) activation buffers of the job
+};
+
+int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, uint8_t* d_out, const TileDesc* d_tiles_all,
+               const std::vector<Grp>& gs)
+{
+    rsr_handle* h = c.h;
+    Workspace* ws = c.ws;
+    const Model& m = h->model;
+    const int G = (int)gs.size();
+    if (G < 1 || G > 4) return set_err(h, RSR_ERR_GENERIC, "run_merged: 1..4 shape groups per job");
+    size_t npx = 0;
+    for (const Grp& g : gs) npx += (size_t)g.n * g.H * g.W;
+    int r;
+    if ((r = ensure(h, ws->d16[0], npx * 192 * 2))) return r;
+    if ((r = ensure(h, ws->d16[1], npx * 192 * 2))) return r;
+    if ((r = ensure(h, ws->r32, npx * 64 * 4))) return r;
+    if ((r = ensure(h, ws->t32, npx * 64 * 4))) return r;
+    if ((r = ensure(h, ws->f32, npx * 64 * 4))) return r;
+    if ((r = ensure(h, ws->u1, npx * 4 * 64 * 2))) return r;
+    if ((r = ensure(h, ws->v1, npx * 4 * 64 * 2))) return r;
+    if ((r = ensure(h, ws->u2, npx * 16 * 64 * 2))) return r;
+    if ((r = ensure(h, ws->v2, npx * 16 * 64 * 2))) return r;
+    cudaStream_t st = ws->stream;
+    __half* D[2] = {(__half*)ws->d16[0].p, (__half*)ws->d16[1].p};
+    const size_t plane = npx * 64;
+    const int brows = CONV2_BH + 2;
+    const int box_c = h->conv_impl == 3 ? 32 : 64;
+    ConvMaps mapD[2], mapU1, mapV1, mapU2, mapV2;
+    auto slot = [](ConvMaps& cm, int g, int pl) -> CUtensorMap* { return g == 0 ? &cm.m[pl] : &cm.mg[g - 1][pl]; };
+    for (int g = 0; g < G; g++) {
+        const Grp& gr = gs[g];
+        for (int i = 0; i < 2; i++)
+            for (int pl = 0; pl < 3; pl++)
+                if ((r = make_map(h, slot(mapD[i], g, pl), D[i] + pl * plane + gr.px_off * 64, 64, gr.W, gr.H, gr.n, brows, box_c))) return r;
+        struct { ConvMaps* cm; void* base; int s; } tails[4] = {{&mapU1, ws->u1.p, 2}, {&mapV1, ws->v1.p, 2}, {&mapU2, ws->u2.p, 4}, {&mapV2, ws->v2.p, 4}};
+        for (auto& t : tails) {
+            if ((r = make_map(h, slot(*t.cm, g, 0), (__half*)t.base + gr.px_off * (size_t)(t.s * t.s) * 64, 64, t.s * gr.W, t.s * gr.H, gr.n, brows, box_c)))
+                return r;
+            *slot(*t.cm, g, 1) = *slot(*t.cm, g, 0);
+            *slot(*t.cm, g, 2) = *slot(*t.cm, g, 0);
+        }
+    }
+    // Conv_0 + preproc, one (cheap, bandwidth-bound) launch per group
+    for (const Grp& gr : gs) {
+        FirstArgs f{};
+        f.img = d_img; f.img_w = img_w; f.img_h = img_h; f.img_c = img_c; f.tiles = d_tiles_all + gr.off;
+        f.w = h->dm.w0; f.bias = h->dm.bias[0];
+        f.H = gr.H; f.W = gr.W; f.B = gr.n;
+        f.d16 = D[0] + gr.px_off * 64;
+        f.t32 = (float*)ws->t32.p + gr.px_off * 64; f.r32 = (float*)ws->r32.p + gr.px_off * 64; f.f32 = (float*)ws->f32.p + gr.px_off * 64;
+        CK(launch_conv_first(f, st));
+        c.launches++;
+    }
+    // group table at scale s (1 for the body, 2 / 4 for the tail)
+    auto fill_groups = [&](ConvArgs& a, int s) {
+        a.H = a.W = a.B = 0;
+        a.ngroups = G;
+        int t0 = 0;
+        for (int g = 0; g < G; g++) {
+            ConvGroup& cg = a.grp[g];
+            cg.H = gs[g].H * s; cg.W = gs[g].W * s; cg.B = gs[g].n;
+            cg.tiles_x = (cg.W + CONV2_BW - 1) / CONV2_BW;
+            cg.tiles_per_img = cg.tiles_x * ((cg.H + CONV2_BAND - 1) / CONV2_BAND);
+            cg.tile_start = t0;
+            cg.desc0 = (int)gs[g].off;
+            cg.px_off = (long long)gs[g].px_off * s * s;
+            t0 += cg.tiles_per_img * cg.B;
+        }
+        a.ntiles_multi = t0;
+    };
+    ConvArgs base{};
+    base.t32 = (float*)ws->t32.p; base.r32 = (float*)ws->r32.p; base.f32 = (const float*)ws->f32.p;
+    base.tiles = d_tiles_all;
+    fill_groups(base, 1);
+    int cur = 0;
+    for (int rrdb = 0; rrdb < m.num_rrdb; rrdb++)
+        for (int rdb = 0; rdb < 3; rdb++) {
+            for (int k = 0; k < 4; k++) {
+                ConvArgs a = base;
+                a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_rdb(rrdb, rdb, k)].slope;
+                a.out16 = D[cur] + (1 + k / 2) * plane; a.out_cs = 64; a.out_co = 32 * (k & 1);
+                if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, k)))) return r;
+            }
+            ConvArgs a = base;
+            a.mode = CONV_RDB_OUT; a.rrdb_end = (rdb == 2);
+            if (h->residual_fp16) { a.mode = CONV_RDB_OUT16; a.res16 = D[cur]; }
+            a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
+            if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, 4)))) return r;
+            cur ^= 1;
+        }
+    {
+        ConvArgs a = base;
+        a.mode = CONV_TRUNK; a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
+        if ((r = conv(c, &mapD[cur], a, m.idx_trunk()))) return r;
+        cur ^= 1;
+    }
+    for (const Grp& gr : gs) {
+        CK(launch_upsample2x(D[cur] + gr.px_off * 64, 64, (__half*)ws->u1.p + gr.px_off * 4 * 64, gr.n, gr.H, gr.W, st));
+        c.launches++;
+    }
+    {
+        ConvArgs a = base;
+        fill_groups(a, 2);
+        a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_up1()].slope;
+        a.out16 = (__half*)ws->v1.p; a.out_cs = 64; a.out_co = 0;
+        if ((r = conv(c, &mapU1, a, m.idx_up1()))) return r;
+    }
+    for (const Grp& gr : gs) {
+        CK(launch_upsample2x((const __half*)ws->v1.p + gr.px_off * 4 * 64, 64, (__half*)ws->u2.p + gr.px_off * 16 * 64, gr.n, 2 * gr.H, 2 * gr.W, st));
+        c.launches++;
+    }
+    {
+        ConvArgs a = base;
+        fill_groups(a, 4);
+        a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_up2()].slope;
+        a.out16 = (__half*)ws->v2.p; a.out_cs = 64; a.out_co = 0;
+        if ((r = conv(c, &mapU2, a, m.idx_up2()))) return r;
+        a.slope = m.convs[m.idx_hr()].slope;
+        a.out16 = (__half*)ws->u2.p;  // u2 is dead after up2: reuse it for the HR conv output
+        if ((r = conv(c, &mapV2, a, m.idx_hr()))) return r;
+    }
+    {
+        ConvArgs a = base;
+        fill_groups(a, 4);
+        a.mode = CONV_LAST_U8;
+        a.img_out = d_out; a.img_w = img_w * 4; a.img_h = img_h * 4; a.img_c = img_c;
+        a.prepad_s = h->prepadding * 4;
+        if ((r = conv(c, &mapU2, a, m.idx_last()))) return r;
+    }
+    return 0;
+}
+
 // tiles [tile_first, tile_first + tile_count) of the reference's row-major tile grid; `done` (optional) receives their descriptors
 int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, int hh, int ch, uint8_t* d_out, long long* padded_out,
                       long long* launches_out, int tile_first, int tile_count, std::vector<TileDesc>* done)
@@ -382,8 +525,42 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
     struct Job { size_t off; int n, H, W; bool tta_out, gather; size_t slot_stride; int mw, mh; };
     std::vector<TileDesc> flat;
     std::vector<Job> jobs;
+    std::vector<std::vector<Grp>> mjobs;  // merge_shapes: every job = up to 4 shape groups, one launch per layer
+    const bool merged = h->merge_shapes && !h->tta && h->conv_impl >= 2;
+    if (merged) {
+        const double budget = 16e9;  // workspace bytes per job
+        std::vector<Grp> cur;
+        double cur_bytes = 0;
+        size_t cur_px = 0;
+        auto flush = [&]() {
+            if (!cur.empty()) mjobs.push_back(cur);
+            cur.clear(); cur_bytes = 0; cur_px = 0;
+        };
+        for (auto g = groups.rbegin(); g != groups.rend(); ++g) {
+            const int H = g->first.first, W = g->first.second;
+            const std::vector<TileDesc>& tl = g->second;
+            const double bpt = (double)H * W * (768.0 + 768.0 + 1024.0 + 4096.0);
+            size_t pos = 0;
+            while (pos < tl.size()) {
+                long long cap = (long long)((budget - cur_bytes) / bpt);
+                if (h->max_batch > 0) cap = std::min(cap, h->max_batch);
+                if (cur.size() == 4 || cap < 1) {
+                    if (cur.empty()) cap = 1;  // a single tile larger than the budget still has to run
+                    else { flush(); continue; }
+                }
+                const size_t take = std::min(tl.size() - pos, (size_t)cap);
+                cur.push_back({flat.size(), (int)take, H, W, cur_px});
+                flat.insert(flat.end(), tl.begin() + pos, tl.begin() + pos + take);
+                cur_px += take * (size_t)H * W;
+                cur_bytes += take * bpt;
+                padded += (long long)take * H * W;
+                pos += take;
+            }
+        }
+        flush();
+    }
     size_t max_tta_bytes = 0;
-    for (auto g = groups.rbegin(); g != groups.rend(); ++g) {
+    for (auto g = groups.rbegin(); !merged && g != groups.rend(); ++g) {
         const int H = g->first.first, W = g->first.second;
         std::vector<TileDesc>& tl = g->second;
         // workspace per padded pixel: 2x192 fp16 + 3x64 fp32 + (u1,v1) 4x64x2 fp16 + (u2,v2) 16x64x2 fp16 [+ TTA 16 float4 x2]
@@ -441,6 +618,8 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
     if (max_tta_bytes && (r = ensure(h, ws->tta, max_tta_bytes))) return r;
     CK(cudaMemcpyAsync(ws->tiles.p, ws->h_tiles, sizeof(TileDesc) * flat.size(), cudaMemcpyHostToDevice, ws->stream));
     const TileDesc* d_tiles = (const TileDesc*)ws->tiles.p;
+    for (const std::vector<Grp>& mj : mjobs)
+        if ((r = run_merged(c, d_in, w, hh, ch, d_out, d_tiles, mj))) return r;
     for (const Job& j : jobs) {
         if (!j.gather) {
             if ((r = run_batch(c, d_in, w, hh, ch, d_out, d_tiles + j.off, j.n, j.H, j.W, j.tta_out))) return r;
@@ -676,6 +855,7 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
     if (!strcmp(key, "max_batch")) h->max_batch = value;
     else if (!strcmp(key, "epilogue_split")) h->epilogue_split = value ? 1 : 0;
     else if (!strcmp(key, "serpentine")) h->serpentine = value ? 1 : 0;
+    else if (!strcmp(key, "merge_shapes")) h->merge_shapes = value ? 1 : 0;
     else if (!strcmp(key, "debug_mask")) h->debug_mask = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
     else if (!strcmp(key, "conv_impl")) {

@@ -38,6 +38,16 @@ enum ConvMode {
     CONV_RDB_OUT16 = 5, // like CONV_RDB_OUT, but the RDB input is read from the fp16 plane `res16` and T32 is not written
 };
 
+// One same-shape group of padded tiles inside a merged multi-shape launch (ConvArgs::ngroups > 0): the groups' activations
+// are concatenated pixel-major in every buffer, group g starting px_off pixels into it.
+struct ConvGroup {
+    int H, W, B;                 // this conv's input == output size of the group, tiles in the group
+    int tiles_x, tiles_per_img;  // work-tile grid of one image of the group (CTA-pair kernel: 30 x 16 px pair tiles)
+    int tile_start;              // first work tile of the group in the launch-wide numbering
+    int desc0;                   // index of the group's first TileDesc in ConvArgs::tiles
+    long long px_off;            // pixel offset of the group inside the activation buffers (already scaled for 2x / 4x layers)
+};
+
 struct ConvArgs {
     const __half* wpk;  // packed weights [chunk][tap][N][64] fp16, pre-swizzled smem image (see model.cpp)
     const float* bias;  // [N]
@@ -61,6 +71,12 @@ struct ConvArgs {
     int prepad_s;        // prepadding*scale
     float* tta_out;
     long long* dbg_ts;   // optional (bring-up): per-tile clock64 stamps of cluster 0, 8 slots per tile, see conv_tc2.cu
+    // CTA-pair kernel, merged multi-shape launch ("merge_shapes" option): up to 4 same-shape groups in ONE launch per layer, so
+    // that a frame pays the per-launch pipeline fill/drain (7.7 us for the Cout=32 convs, 15 us for the Cout=64 conv, measured)
+    // once per layer instead of once per layer and shape.  ngroups == 0: plain launch described by H, W, B above.
+    int ngroups;
+    int ntiles_multi;     // total work tiles of the merged launch
+    ConvGroup grp[4];
     int reverse;          // CTA-pair kernel: walk the work tiles from last to first.  The engine alternates it from one conv to the next
                           // ("serpentine" option) so that a conv starts on the pixels the previous conv touched last -- the part of its
                           // inputs (and of the previous conv's outputs) that is still in the 126 MB L2
@@ -74,12 +90,15 @@ struct alignas(64) ConvMaps {
     CUtensorMap m[3];
     CUtensorMap w;    // 2-D map over the conv's weight rows [rows][64], box 64 rows (CTA-pair kernel only)
     CUtensorMap w32;  // same tensor, box 32 rows
+    CUtensorMap mg[3][3];  // merged multi-shape launch: the planes of groups 1..3 (group 0 uses m[])
 };
 // conv3x3 s1 p1 as implicit GEMM on tcgen05 (conv_tc.cu). cout_pad in {16, 32, 64}.
 cudaError_t launch_conv3x3_tc(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
 // same contract, CTA-pair (cta_group::2) implementation (conv_tc2.cu); needs in_maps->w and 10-row activation boxes
 cudaError_t launch_conv3x3_tc2(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
 constexpr int CONV2_BH = 8;
+constexpr int CONV2_BW = 30;    // output columns per work tile of the CTA-pair kernel (CONV_P - 2)
+constexpr int CONV2_BAND = 16;  // output rows per work tile of the CTA-pair kernel (2 x CONV2_BH)
 // box dims the kernel expects from the tensor map: {64 ch, 32 px, CONV_BH+2 rows, 1}
 constexpr int CONV_BH = 16;
 constexpr int CONV_P = 32;

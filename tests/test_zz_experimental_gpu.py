@@ -58,6 +58,29 @@ def test_serpentine_tile_order_is_bit_identical(models_dir):
         assert np.array_equal(a, b), (h, w, c, tile, diff_stats(a, b))
 
 
+@pytest.mark.parametrize("opts", [dict(merge_shapes=1), dict(merge_shapes=1, epilogue_split=1, serpentine=1)],
+                         ids=["merge", "merge+split+serpentine"])
+def test_merged_shape_launches_are_bit_identical(models_dir, opts):
+    """merge_shapes=1 runs every layer as ONE launch over all shape groups of a frame (concatenated activation buffers,
+    per-group tensor maps): same per-tile arithmetic, so the image must equal the default path bit for bit"""
+    ref, new = _engine(), _engine(**opts)
+    rng = np.random.default_rng(13)
+    for (h, w, c, tile) in [(70, 93, 3, 32), (256, 256, 3, 200), (120, 90, 4, 64), (1080, 1920, 3, 400), (300, 500, 3, 200)]:
+        img = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        a = np.zeros((4 * h, 4 * w, c), np.uint8)
+        b = np.zeros_like(a)
+        ref.tilesize = new.tilesize = tile
+        assert ref.process(img, a) == 0 and new.process(img, b) == 0, new.last_error()
+        assert np.array_equal(a, b), (h, w, c, tile, diff_stats(a, b))
+    # the launch count drops to one per layer: 351 tensor-core convs + per-group Conv_0 / upsample launches
+    before = new.kernel_launches()
+    img = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    out = np.zeros((4320, 7680, 3), np.uint8)
+    new.tilesize = 400
+    assert new.process(img, out) == 0
+    assert new.kernel_launches() - before == 350 + 3 * 4
+
+
 def test_split_epilogue_tta_and_goldens(models_dir):
     new = _engine(epilogue_split=1)
     for name, natural in (("natural_48x40_df2k_t32", True), ("noise_50x33_df2k_t32", False), ("readme0_crop96x80_df2k_t64", True)):

@@ -8,6 +8,8 @@ RSR_TEST_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_zz_experimental_
 timeout 120 python tools/ab_option.py epilogue_split 0 1 2>&1 | tail -3; mark ab
 timeout 120 python tools/ab_option.py epilogue_split 0 1 200 2>&1 | tail -3; mark ab-t200
 timeout 120 python tools/ab_option.py serpentine 0 1 2>&1 | tail -3; mark ab-serpentine
+timeout 120 python tools/ab_option.py merge_shapes 0 1 2>&1 | tail -3; mark ab-merge
+timeout 120 python tools/ab_option.py merge_shapes 0 1 200 2>&1 | tail -3; mark ab-merge-t200
 timeout 120 python tools/ab_option.py conv_impl 2 3 2>&1 | tail -3; mark ab-kblock32
 for i in 2 4 5; do RSR_IMPL=3 RSR_DBG_RDB=1 timeout 60 python tools/ts_probe.py $i > gpurun_out/ts_k32_$i.log 2>&1; tail -3 gpurun_out/ts_k32_$i.log; done; mark ts-k32
 RSR_OPTS=serpentine=1,epilogue_split=1 timeout 200 python tools/batch_sweep.py 2>&1 | tail -20; mark batch-sweep-serpentine
