@@ -239,15 +239,16 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
 
         // ---- math + stores from registers ----
         if constexpr (NREAL == 16) {
-            const int i = chh;
+            const int yyi = chh ? yy[1] : yy[0];       // (selects, not a dynamic index: keeps yy / vrow in registers)
+            const bool vri = chh ? vrow[1] : vrow[0];
             const int x = x0 + lane;
-            if (lane < BW && x < geo.W && vrow[i]) {
+            if (lane < BW && x < geo.W && vri) {
                 const TileDesc td = a.tiles[geo.desc0 + b];
                 float o[3];
 #pragma unroll
                 for (int j = 0; j < 3; j++) o[j] = o3[j] + s_bias[j];
                 if constexpr (MODE == CONV_LAST_U8) {
-                    const int ii = yy[i] - a.prepad_s, jx = x - a.prepad_s;
+                    const int ii = yyi - a.prepad_s, jx = x - a.prepad_s;
                     if (ii >= 0 && ii < td.crop_h && jx >= 0 && jx < td.crop_w) {
                         uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + ii) * a.img_w + td.out_x0 + jx) * a.img_c;
 #pragma unroll
@@ -257,7 +258,7 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
                         }
                     }
                 } else {
-                    float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)geo.H * geo.W) + (size_t)yy[i] * geo.W + x;
+                    float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)geo.H * geo.W) + (size_t)yyi * geo.W + x;
                     *dst = make_float4(o[0], o[1], o[2], 0.f);
                 }
             }
