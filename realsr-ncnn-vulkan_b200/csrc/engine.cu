@@ -64,6 +64,7 @@ struct DeviceModel {
     std::vector<int> cout_pad;
     std::vector<CUtensorMap> wmap, wmap32;  // per conv: 2-D maps over its weight rows, box 64 / 32 rows (CTA-pair kernel)
     std::vector<CUtensorMap> wmap_k32, wmap32_k32;  // same with 32-channel SWIZZLE_64B boxes (conv_impl 3)
+    bool k32_ok = true;         // false: the driver refused the SWIZZLE_64B weight maps, conv_impl 3 is unavailable
     float* w0 = nullptr;        // Conv_0 fp32 weights [64][27]
     void* blob = nullptr;       // one allocation holding everything
 };
@@ -233,12 +234,15 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
         c.nconv_ev++;
         CK(cudaEventRecord(e0, c.ws->stream));
     }
+    if (h->conv_impl == 3 && !dm.k32_ok) return set_err(h, RSR_ERR_CUDA, "conv_impl 3: SWIZZLE_64B tensor maps are not available");
     if (h->conv_impl >= 2) {
         ConvMaps mm = *map;
         mm.w = h->conv_impl == 3 ? dm.wmap_k32[conv_idx] : dm.wmap[conv_idx];
         mm.w32 = h->conv_impl == 3 ? dm.wmap32_k32[conv_idx] : dm.wmap32[conv_idx];
         a.kblock = h->conv_impl == 3 ? 32 : 64;
-        CK(launch_conv3x3_tc2(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
+        // the validated round-1 kernel unless one of the opt-in variants is requested (conv_tc2x.cu)
+        const bool variant = a.epi_split || a.reverse || a.ngroups > 0 || a.kblock == 32;
+        CK((variant ? launch_conv3x3_tc2x : launch_conv3x3_tc2)(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
     } else {
         CK(launch_conv3x3_tc(map, a, dm.cout_pad[conv_idx], c.ws->stream));
     }
@@ -742,9 +746,13 @@ int rsr_load(rsr_handle* h, const char* parampath, const char* modelpath)
     for (int i = 1; i < nconv; i++) {
         int rr = make_wmap(h, &dm.wmap[i], (uint8_t*)dm.blob + off_r[i], nrows[i], dm.cout_pad[i] == 32 ? 48 : 64);
         if (!rr) rr = make_wmap(h, &dm.wmap32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], 32);
-        if (!rr) rr = make_wmap(h, &dm.wmap_k32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], dm.cout_pad[i] == 32 ? 48 : 64, 32);
-        if (!rr) rr = make_wmap(h, &dm.wmap32_k32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], 32, 32);
         if (rr) return rr;
+        // maps of the opt-in conv_impl=3: must never be able to fail a load of the default path
+        if (dm.k32_ok && (make_wmap(h, &dm.wmap_k32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], dm.cout_pad[i] == 32 ? 48 : 64, 32) ||
+                          make_wmap(h, &dm.wmap32_k32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], 32, 32))) {
+            dm.k32_ok = false;
+            set_err(h, 0, "");
+        }
     }
     for (int i = 0; i < nconv; i++) {
         if (i > 0) dm.wpk[i] = (__half*)((uint8_t*)dm.blob + off_w[i]);
@@ -860,6 +868,7 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
     else if (!strcmp(key, "conv_impl")) {
         if (value < 1 || value > 3) return set_err(h, RSR_ERR_GENERIC, "conv_impl must be 1, 2 or 3");
+        if (value == 3 && h->loaded && !h->dm.k32_ok) return set_err(h, RSR_ERR_CUDA, "conv_impl 3: SWIZZLE_64B tensor maps are not available");
         h->conv_impl = (int)value;
     }
     else if (!strcmp(key, "residual_fp16")) h->residual_fp16 = (int)value;
@@ -975,7 +984,7 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
         a.dbg_ts = d_ts;
     }
     for (int rep = 0; rep < (d_ts ? 2 : 1); rep++) {
-        if (h->conv_impl >= 2) CK(launch_conv3x3_tc2(&map, a, npad, 0));
+        if (h->conv_impl >= 2) CK(((a.epi_split || a.kblock == 32) ? launch_conv3x3_tc2x : launch_conv3x3_tc2)(&map, a, npad, 0));
         else CK(launch_conv3x3_tc(&map, a, npad, 0));
     }
     CK(cudaDeviceSynchronize());

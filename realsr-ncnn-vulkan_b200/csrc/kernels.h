@@ -96,6 +96,8 @@ struct alignas(64) ConvMaps {
 cudaError_t launch_conv3x3_tc(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
 // same contract, CTA-pair (cta_group::2) implementation (conv_tc2.cu); needs in_maps->w and 10-row activation boxes
 cudaError_t launch_conv3x3_tc2(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
+// conv_tc2x.cu: the same kernel with the opt-in variants (ConvArgs::epi_split / kblock / ngroups / reverse); conv_tc2.cu ignores those
+cudaError_t launch_conv3x3_tc2x(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
 constexpr int CONV2_BH = 8;
 constexpr int CONV2_BW = 30;    // output columns per work tile of the CTA-pair kernel (CONV_P - 2)
 constexpr int CONV2_BAND = 16;  // output rows per work tile of the CTA-pair kernel (2 x CONV2_BH)
