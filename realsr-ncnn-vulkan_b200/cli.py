@@ -211,8 +211,8 @@ def main(argv=None):
             try:
                 im = Image.fromarray(out)
                 if fmt == "jpg":
-                    if out.shape[2] == 4:  # the reference renames alpha outputs to png (main.cpp:279-288)
-                        path = os.path.splitext(path)[0] + ".png"
+                    if out.shape[2] == 4:  # the reference appends ".png" to the jpg name of alpha outputs (main.cpp:279-288)
+                        path = path + ".png"
                         sys.stderr.write("image %s has alpha channel ! %s will output %s\n" % (input_files[i], input_files[i], path))
                         im.save(path, "PNG")
                     else:

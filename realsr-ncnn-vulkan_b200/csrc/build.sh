@@ -20,3 +20,6 @@ echo "built $(realpath $OUT)"
 # reference's proc stage
 /usr/bin/g++ -O2 -std=c++11 -Wall -o ../realsr_raw_cli ../host/realsr_raw_cli.cpp -L.. -lrealsr_b200 -Wl,-rpath,'$ORIGIN' -lpthread
 echo "built $(realpath ../realsr_raw_cli)"
+# the reference-shaped C++ command line (PNG through zlib)
+/usr/bin/g++ -O2 -std=c++11 -Wall -o ../realsr-b200 ../host/realsr_cli.cpp -L.. -lrealsr_b200 -Wl,-rpath,'$ORIGIN' -lz -lpthread
+echo "built $(realpath ../realsr-b200)"

@@ -1,0 +1,249 @@
+// png_codec.h -- minimal PNG reader / writer on top of zlib, for the C++ command line (host/realsr_cli.cpp).
+//
+// The reference decodes with its vendored stb_image (src/main.cpp:243-263: auto channel count, gray -> RGB,
+// gray+alpha -> RGBA) and encodes with stb_image_write (src/main.cpp:383); those files are the reference's and are not
+// copied here.  This is an independent implementation of the PNG specification (ISO/IEC 15948): chunk parsing with
+// CRC check, zlib inflate, the five scanline filters, bit depths 1/2/4/8/16, colour types 0/2/3/4/6, tRNS, and Adam7
+// interlace on the read side; 8-bit RGB / RGBA with per-row filter selection (minimum sum of absolute differences) on
+// the write side.  Host plumbing only: no pixel of the super-resolution path is computed here.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+namespace rsrhost {
+
+inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+inline void put_be32(uint8_t* p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; }
+
+inline int paeth(int a, int b, int c)
+{
+    const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+// undo the scanline filters in place; `raw` holds h rows of (1 filter byte + stride bytes)
+inline bool png_unfilter(uint8_t* raw, size_t stride, int h, int bpp /* bytes per complete pixel, >= 1 */)
+{
+    std::vector<uint8_t> zero(stride, 0);
+    const uint8_t* prev = zero.data();
+    for (int y = 0; y < h; y++) {
+        uint8_t* row = raw + (size_t)y * (stride + 1);
+        const int ft = row[0];
+        uint8_t* cur = row + 1;
+        for (size_t i = 0; i < stride; i++) {
+            const int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= (size_t)bpp ? prev[i - bpp] : 0;
+            int add;
+            switch (ft) {
+            case 0: add = 0; break;
+            case 1: add = a; break;
+            case 2: add = b; break;
+            case 3: add = (a + b) >> 1; break;
+            case 4: add = paeth(a, b, c); break;
+            default: return false;
+            }
+            cur[i] = (uint8_t)(cur[i] + add);
+        }
+        prev = cur;
+    }
+    return true;
+}
+
+// Decodes `path`.  On success: w, h, c in {3, 4} (gray -> RGB, gray+alpha / tRNS -> RGBA, like the reference's load stage),
+// pixels tightly packed HWC 8 bit.
+inline bool png_decode_file(const std::string& path, int& w, int& h, int& c, std::vector<uint8_t>& pixels, std::string* why = nullptr)
+{
+    auto fail = [&](const char* m) { if (why) *why = m; return false; };
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) return fail("cannot open");
+    std::vector<uint8_t> f;
+    {
+        uint8_t buf[65536];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof buf, fp)) > 0) f.insert(f.end(), buf, buf + n);
+        fclose(fp);
+    }
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (f.size() < 8 || memcmp(f.data(), sig, 8)) return fail("not a PNG");
+    size_t pos = 8;
+    int depth = 0, ctype = -1, interlace = 0;
+    std::vector<uint8_t> idat, plte, trns;
+    bool have_ihdr = false, have_iend = false;
+    while (pos + 12 <= f.size()) {
+        const uint32_t len = be32(&f[pos]);
+        if (len > f.size() - pos - 12) return fail("truncated chunk");
+        const uint8_t* type = &f[pos + 4];
+        const uint8_t* data = &f[pos + 8];
+        const uint32_t crc = be32(&f[pos + 8 + len]);
+        if (crc32(crc32(0L, Z_NULL, 0), type, len + 4) != crc) return fail("chunk CRC mismatch");
+        if (!memcmp(type, "IHDR", 4)) {
+            if (len != 13) return fail("bad IHDR");
+            w = (int)be32(data); h = (int)be32(data + 4);
+            depth = data[8]; ctype = data[9]; interlace = data[12];
+            if (w <= 0 || h <= 0 || (long long)w * h > (1LL << 30) || data[10] || data[11] || interlace > 1) return fail("unsupported IHDR");
+            have_ihdr = true;
+        } else if (!memcmp(type, "PLTE", 4)) plte.assign(data, data + len);
+        else if (!memcmp(type, "tRNS", 4)) trns.assign(data, data + len);
+        else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), data, data + len);
+        else if (!memcmp(type, "IEND", 4)) { have_iend = true; break; }
+        pos += 12 + (size_t)len;
+    }
+    if (!have_ihdr || !have_iend || idat.empty()) return fail("missing IHDR / IDAT / IEND");
+    int nch;
+    switch (ctype) {
+    case 0: nch = 1; break;
+    case 2: nch = 3; break;
+    case 3: nch = 1; break;
+    case 4: nch = 2; break;
+    case 6: nch = 4; break;
+    default: return fail("bad colour type");
+    }
+    const bool depth_ok = (ctype == 0 && (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) ||
+                          (ctype == 3 && (depth == 1 || depth == 2 || depth == 4 || depth == 8)) ||
+                          ((ctype == 2 || ctype == 4 || ctype == 6) && (depth == 8 || depth == 16));
+    if (!depth_ok) return fail("bad bit depth");
+    if (ctype == 3 && plte.size() < 3) return fail("palette image without PLTE");
+    const int bits_pp = nch * depth;
+    const int bpp = bits_pp >= 8 ? bits_pp / 8 : 1;
+    // pass geometry: non-interlaced = one pass over everything; Adam7 = 7 sub-images
+    struct Pass { int x0, y0, dx, dy; };
+    static const Pass adam7[7] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    const Pass whole = {0, 0, 1, 1};
+    const int npass = interlace ? 7 : 1;
+    size_t raw_size = 0;
+    for (int p = 0; p < npass; p++) {
+        const Pass& ps = interlace ? adam7[p] : whole;
+        const int pw = (w - ps.x0 + ps.dx - 1) / ps.dx, ph = (h - ps.y0 + ps.dy - 1) / ps.dy;
+        if (pw > 0 && ph > 0) raw_size += (size_t)ph * (1 + ((size_t)pw * bits_pp + 7) / 8);
+    }
+    std::vector<uint8_t> raw(raw_size);
+    {
+        uLongf dl = (uLongf)raw_size;
+        const int zr = uncompress(raw.data(), &dl, idat.data(), (uLong)idat.size());
+        if (zr != Z_OK || dl != raw_size) return fail("inflate failed");
+    }
+    const bool has_alpha = ctype == 4 || ctype == 6 || !trns.empty();
+    c = has_alpha ? 4 : 3;
+    pixels.assign((size_t)w * h * c, 255);
+    size_t off = 0;
+    for (int p = 0; p < npass; p++) {
+        const Pass& ps = interlace ? adam7[p] : whole;
+        const int pw = (w - ps.x0 + ps.dx - 1) / ps.dx, ph = (h - ps.y0 + ps.dy - 1) / ps.dy;
+        if (pw <= 0 || ph <= 0) continue;
+        const size_t stride = ((size_t)pw * bits_pp + 7) / 8;
+        if (!png_unfilter(raw.data() + off, stride, ph, bpp)) return fail("bad filter type");
+        for (int y = 0; y < ph; y++) {
+            const uint8_t* row = raw.data() + off + (size_t)y * (stride + 1) + 1;
+            uint8_t* dst_row = pixels.data() + ((size_t)(ps.y0 + y * ps.dy) * w) * c;
+            for (int x = 0; x < pw; x++) {
+                // sample k of pixel x -> 8 bit (16 bit: high byte; < 8 bit gray: scaled to 0..255; palette: index)
+                int s[4] = {0, 0, 0, 0};
+                uint16_t s16[4] = {0, 0, 0, 0};
+                for (int k = 0; k < nch; k++) {
+                    if (depth == 8) s[k] = row[(size_t)x * nch + k];
+                    else if (depth == 16) {
+                        s16[k] = (uint16_t)((row[((size_t)x * nch + k) * 2] << 8) | row[((size_t)x * nch + k) * 2 + 1]);
+                        s[k] = s16[k] >> 8;
+                    } else {
+                        const size_t bit = (size_t)x * depth;
+                        const int v = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+                        s16[k] = (uint16_t)v;
+                        s[k] = ctype == 3 ? v : v * 255 / ((1 << depth) - 1);
+                    }
+                    if (depth == 8) s16[k] = (uint16_t)s[k];
+                }
+                uint8_t* d = dst_row + (size_t)(ps.x0 + x * ps.dx) * c;
+                int r, g, b, a = 255;
+                if (ctype == 3) {
+                    const size_t idx = (size_t)s[0];
+                    if (idx * 3 + 2 >= plte.size()) return fail("palette index out of range");
+                    r = plte[idx * 3]; g = plte[idx * 3 + 1]; b = plte[idx * 3 + 2];
+                    if (idx < trns.size()) a = trns[idx];
+                } else if (ctype == 0 || ctype == 4) {
+                    r = g = b = s[0];
+                    if (ctype == 4) a = s[1];
+                    else if (trns.size() >= 2 && s16[0] == (uint16_t)((trns[0] << 8) | trns[1])) a = 0;
+                } else {
+                    r = s[0]; g = s[1]; b = s[2];
+                    if (ctype == 6) a = s[3];
+                    else if (trns.size() >= 6 && s16[0] == (uint16_t)((trns[0] << 8) | trns[1]) && s16[1] == (uint16_t)((trns[2] << 8) | trns[3]) &&
+                             s16[2] == (uint16_t)((trns[4] << 8) | trns[5]))
+                        a = 0;
+                }
+                d[0] = (uint8_t)r; d[1] = (uint8_t)g; d[2] = (uint8_t)b;
+                if (c == 4) d[3] = (uint8_t)a;
+            }
+        }
+        off += (size_t)ph * (stride + 1);
+    }
+    return true;
+}
+
+// Writes 8-bit RGB (c = 3) or RGBA (c = 4), non-interlaced.  level: zlib 0..9 (1 = fast; a 33-MP result at level 6 costs
+// seconds per image and starves the GPUs).
+inline bool png_encode_file(const std::string& path, const uint8_t* pixels, int w, int h, int c, int level = 1)
+{
+    if ((c != 3 && c != 4) || w <= 0 || h <= 0) return false;
+    const size_t stride = (size_t)w * c;
+    std::vector<uint8_t> raw((stride + 1) * (size_t)h);
+    std::vector<uint8_t> cand(stride);
+    std::vector<uint8_t> zero(stride, 0);
+    for (int y = 0; y < h; y++) {
+        const uint8_t* cur = pixels + (size_t)y * stride;
+        const uint8_t* prev = y ? cur - stride : zero.data();
+        uint8_t* out = raw.data() + (size_t)y * (stride + 1);
+        // choose among None / Sub / Up / Paeth by the minimum sum of absolute (signed) residuals
+        int best = 0;
+        unsigned long long best_sum = ~0ULL;
+        for (int ft : {0, 1, 2, 4}) {
+            unsigned long long sum = 0;
+            for (size_t i = 0; i < stride; i++) {
+                const int a = i >= (size_t)c ? cur[i - c] : 0, b = prev[i], cc = i >= (size_t)c ? prev[i - c] : 0;
+                const int pred = ft == 0 ? 0 : ft == 1 ? a : ft == 2 ? b : paeth(a, b, cc);
+                const uint8_t v = (uint8_t)(cur[i] - pred);
+                sum += v < 128 ? v : 256 - v;
+                if (sum >= best_sum) break;
+            }
+            if (sum < best_sum) { best_sum = sum; best = ft; }
+        }
+        out[0] = (uint8_t)best;
+        for (size_t i = 0; i < stride; i++) {
+            const int a = i >= (size_t)c ? cur[i - c] : 0, b = prev[i], cc = i >= (size_t)c ? prev[i - c] : 0;
+            const int pred = best == 0 ? 0 : best == 1 ? a : best == 2 ? b : paeth(a, b, cc);
+            out[1 + i] = (uint8_t)(cur[i] - pred);
+        }
+    }
+    uLongf zl = compressBound((uLong)raw.size());
+    std::vector<uint8_t> z(zl);
+    if (compress2(z.data(), &zl, raw.data(), (uLong)raw.size(), level) != Z_OK) return false;
+    FILE* fp = fopen(path.c_str(), "wb");
+    if (!fp) return false;
+    auto chunk = [&](const char* type, const uint8_t* data, uint32_t len) {
+        uint8_t hdr[8];
+        put_be32(hdr, len);
+        memcpy(hdr + 4, type, 4);
+        uLong crc = crc32(crc32(0L, Z_NULL, 0), hdr + 4, 4);
+        if (len) crc = crc32(crc, data, len);
+        uint8_t tail[4];
+        put_be32(tail, (uint32_t)crc);
+        return fwrite(hdr, 1, 8, fp) == 8 && (!len || fwrite(data, 1, len, fp) == len) && fwrite(tail, 1, 4, fp) == 4;
+    };
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    uint8_t ihdr[13];
+    put_be32(ihdr, (uint32_t)w); put_be32(ihdr + 4, (uint32_t)h);
+    ihdr[8] = 8; ihdr[9] = c == 3 ? 2 : 6; ihdr[10] = ihdr[11] = ihdr[12] = 0;
+    bool ok = fwrite(sig, 1, 8, fp) == 8 && chunk("IHDR", ihdr, 13);
+    // IDAT chunks of at most 1 MiB
+    for (size_t p = 0; ok && p < zl; p += (1u << 20)) ok = chunk("IDAT", z.data() + p, (uint32_t)std::min<size_t>(1u << 20, zl - p));
+    ok = ok && chunk("IEND", nullptr, 0);
+    ok = (fclose(fp) == 0) && ok;
+    return ok;
+}
+
+}  // namespace rsrhost

@@ -1,0 +1,35 @@
+// png_tool.cpp -- exercises host/png_codec.h from the command line (used by tests/test_cpp_cli.py):
+//   png_tool decode in.png out.raw     -> prints "w h c", writes w*h*c bytes
+//   png_tool encode in.raw w h c out.png [zlib-level]
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "png_codec.h"
+
+int main(int argc, char** argv)
+{
+    if (argc == 4 && std::string(argv[1]) == "decode") {
+        int w, h, c;
+        std::vector<uint8_t> px;
+        std::string why;
+        if (!rsrhost::png_decode_file(argv[2], w, h, c, px, &why)) {
+            fprintf(stderr, "decode failed: %s\n", why.c_str());
+            return 1;
+        }
+        FILE* fp = fopen(argv[3], "wb");
+        if (!fp || fwrite(px.data(), 1, px.size(), fp) != px.size()) return 2;
+        fclose(fp);
+        printf("%d %d %d\n", w, h, c);
+        return 0;
+    }
+    if ((argc == 7 || argc == 8) && std::string(argv[1]) == "encode") {
+        const int w = atoi(argv[3]), h = atoi(argv[4]), c = atoi(argv[5]);
+        std::vector<uint8_t> px((size_t)w * h * c);
+        FILE* fp = fopen(argv[2], "rb");
+        if (!fp || fread(px.data(), 1, px.size(), fp) != px.size()) return 2;
+        fclose(fp);
+        return rsrhost::png_encode_file(argv[6], px.data(), w, h, c, argc == 8 ? atoi(argv[7]) : 1) ? 0 : 1;
+    }
+    fprintf(stderr, "usage: png_tool decode in.png out.raw | png_tool encode in.raw w h c out.png [level]\n");
+    return 64;
+}

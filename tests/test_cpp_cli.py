@@ -1,0 +1,192 @@
+"""CPU tests of the C++ host side: the PNG codec (host/png_codec.h) and the reference-shaped C++ command line
+(host/realsr_cli.cpp: flag surface and messages of /root/reference/src/main.cpp:422-879, file planning :606-659, the
+load -> proc -> save thread pipeline :179-416).  The CLI is linked against tests/stub/stub_realsr.c, a nearest-x4
+stand-in for the C ABI, so the whole pipeline runs without a GPU; the real library is exercised by the gpu tests."""
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+from PIL import Image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "realsr-ncnn-vulkan_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def bins(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("cppcli"))
+    subprocess.run(["gcc", "-shared", "-fPIC", "-O2", "-o", os.path.join(d, "librealsr_b200.so"), os.path.join(ROOT, "tests", "stub", "stub_realsr.c")], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++11", "-Wall", "-Werror", "-o", os.path.join(d, "realsr-b200"), os.path.join(HOST, "realsr_cli.cpp"),
+                    "-L" + d, "-lrealsr_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++11", "-Wall", "-Werror", "-o", os.path.join(d, "png_tool"), os.path.join(HOST, "png_tool.cpp"), "-lz"], check=True)
+    return d
+
+
+def decode(bins, path, tmp):
+    raw = os.path.join(tmp, "o.raw")
+    r = subprocess.run([os.path.join(bins, "png_tool"), "decode", path, raw], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    w, h, c = map(int, r.stdout.split())
+    return np.fromfile(raw, dtype=np.uint8).reshape(h, w, c)
+
+
+def expected(im):
+    """what the reference's load stage hands to the engine (main.cpp:243-263): RGB, or RGBA when the file carries alpha"""
+    alpha = im.mode in ("RGBA", "LA", "PA") or "transparency" in im.info
+    return np.asarray(im.convert("RGBA" if alpha else "RGB"))
+
+
+def test_png_decode_matches_pillow(bins, tmp_path):
+    rng = np.random.default_rng(5)
+    rgb = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    cases = {
+        "rgb": Image.fromarray(rgb),
+        "rgba": Image.fromarray(np.dstack([rgb, rng.integers(0, 256, (37, 53), dtype=np.uint8)])),
+        "gray": Image.fromarray(rgb[..., 0]),
+        "la": Image.fromarray(np.dstack([rgb[..., 0], rgb[..., 1]]), "LA"),
+        "pal": Image.fromarray(rgb).quantize(200),
+        "pal16": Image.fromarray(rgb).quantize(16),
+        "bilevel": Image.fromarray(rgb[..., 0] > 127),
+    }
+    for name, im in cases.items():
+        p = str(tmp_path / (name + ".png"))
+        im.save(p, optimize=(name == "pal16"))  # optimize packs small palettes to 4 bits per pixel
+        got = decode(bins, p, str(tmp_path))
+        assert np.array_equal(got, expected(Image.open(p))), name
+    # palette with transparency, 16-bit gray, 16-bit RGB
+    pal = Image.fromarray(rgb).quantize(64)
+    p = str(tmp_path / "paltr.png")
+    pal.save(p, transparency=3)
+    got = decode(bins, p, str(tmp_path))
+    assert got.shape[2] == 4 and np.array_equal(got, expected(Image.open(p)))
+    g16 = rng.integers(0, 65536, (20, 31), dtype=np.uint16)
+    p = str(tmp_path / "g16.png")
+    Image.fromarray(g16).save(p)
+    got = decode(bins, p, str(tmp_path))
+    assert np.array_equal(got, np.repeat((g16 >> 8).astype(np.uint8)[..., None], 3, 2))
+
+
+def _write_png(path, w, h, depth, ctype, raw, interlace=0):
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, interlace)) +
+                chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+
+
+def test_png_decode_adam7_and_all_filters(bins, tmp_path):
+    """hand-built files: Adam7 interlace (Pillow cannot write it) and every scanline filter type"""
+    rng = np.random.default_rng(6)
+    img = rng.integers(0, 256, (13, 19, 3), dtype=np.uint8)
+    h, w, _ = img.shape
+    raw = b""
+    for (x0, y0, dx, dy) in [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]:
+        sub = img[y0::dy, x0::dx]
+        if sub.size:
+            for row in sub:
+                raw += b"\x00" + row.tobytes()
+    p = str(tmp_path / "adam7.png")
+    _write_png(p, w, h, 8, 2, raw, interlace=1)
+    assert np.array_equal(decode(bins, p, str(tmp_path)), img)
+    assert np.array_equal(np.asarray(Image.open(p)), img)  # and Pillow agrees the file is well formed
+    # filters 0..4, one per row, computed here from the specification
+    def paeth(a, b, c):
+        pp = a + b - c
+        pa, pb, pc = abs(pp - a), abs(pp - b), abs(pp - c)
+        return a if pa <= pb and pa <= pc else (b if pb <= pc else c)
+    raw = b""
+    prev = np.zeros(w * 3, dtype=np.int32)
+    for y in range(h):
+        cur = img[y].reshape(-1).astype(np.int32)
+        ft = y % 5
+        out = bytearray([ft])
+        for i in range(w * 3):
+            a = cur[i - 3] if i >= 3 else 0
+            b = prev[i]
+            c = prev[i - 3] if i >= 3 else 0
+            pred = [0, a, b, (a + b) // 2, paeth(a, b, c)][ft]
+            out.append((cur[i] - pred) & 255)
+        raw += bytes(out)
+        prev = cur
+    p = str(tmp_path / "filters.png")
+    _write_png(p, w, h, 8, 2, raw)
+    assert np.array_equal(decode(bins, p, str(tmp_path)), img)
+    # corrupt CRC is refused
+    data = bytearray(open(p, "rb").read())
+    data[-20] ^= 0x55
+    bad = str(tmp_path / "bad.png")
+    open(bad, "wb").write(bytes(data))
+    r = subprocess.run([os.path.join(bins, "png_tool"), "decode", bad, str(tmp_path / "x.raw")], capture_output=True, text=True)
+    assert r.returncode != 0
+
+
+@pytest.mark.parametrize("c", [3, 4])
+def test_png_encode_roundtrip(bins, tmp_path, c):
+    rng = np.random.default_rng(7 + c)
+    yy, xx = np.mgrid[0:61, 0:47]
+    smooth = np.stack([(xx * 5 + yy * 2) % 256, (xx + yy * 3) % 256, (xx * yy) % 256, (xx * 7) % 256][:c], -1).astype(np.uint8)
+    for name, img in (("noise", rng.integers(0, 256, (61, 47, c), dtype=np.uint8)), ("smooth", smooth)):
+        raw, png = str(tmp_path / (name + ".raw")), str(tmp_path / (name + ".png"))
+        img.tofile(raw)
+        subprocess.run([os.path.join(bins, "png_tool"), "encode", raw, "47", "61", str(c), png], check=True)
+        back = np.asarray(Image.open(png))
+        assert back.shape == img.shape and np.array_equal(back, img), name
+        assert np.array_equal(decode(bins, png, str(tmp_path)), img)
+    assert os.path.getsize(str(tmp_path / "smooth.png")) < smooth.size // 3  # the filter heuristic does compress gradients
+
+
+def cli(bins, *args):
+    return subprocess.run([os.path.join(bins, "realsr-b200")] + list(args), capture_output=True, text=True)
+
+
+def test_cli_argument_validation(bins, tmp_path):
+    """same checks and messages as the reference (main.cpp:510-604, :661-733)"""
+    img = str(tmp_path / "a.png")
+    Image.fromarray(np.zeros((8, 8, 3), np.uint8)).save(img)
+    out = str(tmp_path / "o.png")
+    assert cli(bins).returncode != 0 and "Usage:" in cli(bins).stderr
+    assert "invalid scale argument" in cli(bins, "-i", img, "-o", out, "-s", "2").stderr
+    assert "invalid tilesize argument" in cli(bins, "-i", img, "-o", out, "-t", "16").stderr
+    assert "invalid tilesize argument" in cli(bins, "-i", img, "-o", out, "-t", "64,64", "-g", "0").stderr
+    assert "invalid thread count argument" in cli(bins, "-i", img, "-o", out, "-j", "0:2:2").stderr
+    assert "invalid jobs_proc thread count argument" in cli(bins, "-i", img, "-o", out, "-j", "1:2,2,2:2", "-g", "0,1").stderr
+    assert "invalid argument" in cli(bins, "-i", img, "-o", out, "-j", "4").stderr
+    assert "invalid outputpath extension type" in cli(bins, "-i", img, "-o", str(tmp_path / "o.bmp")).stderr
+    assert "invalid format argument" in cli(bins, "-i", str(tmp_path), "-o", str(tmp_path), "-f", "tiff").stderr
+    assert "must be either file or directory at the same time" in cli(bins, "-i", img, "-o", str(tmp_path)).stderr
+    assert "unknown model dir type" in cli(bins, "-i", img, "-o", out, "-m", "models-other").stderr
+    assert "no CPU mode" in cli(bins, "-i", img, "-o", out, "-g", "-1", "-m", "models-DF2K").stderr
+    assert "png only" in cli(bins, "-i", img, "-o", str(tmp_path / "o.jpg")).stderr
+    r = cli(bins, "-i", img, "-o", out, "-m", "missing/models-DF2K")
+    assert r.returncode != 0 and "load failed" in r.stderr
+
+
+def test_cli_pipeline_directory_mode(bins, tmp_path):
+    """dir -> dir through load/proc/save threads on two (stub) GPUs: sorted names, the collision rename, -v lines,
+    undecodable files reported and skipped, RGBA kept, every output = the engine's result for its input"""
+    din, dout = tmp_path / "in", tmp_path / "out"
+    din.mkdir(); dout.mkdir()
+    rng = np.random.default_rng(8)
+    imgs = {}
+    for i in range(11):
+        c = 4 if i % 4 == 3 else 3
+        im = rng.integers(0, 256, (9 + i, 14 - i % 3, c), dtype=np.uint8)
+        imgs["img%02d.png" % i] = im
+        Image.fromarray(im).save(str(din / ("img%02d.png" % i)))
+    (din / "img03.txt").write_text("not an image")  # same stem as img03.png -> collision rule, and undecodable
+    r = cli(bins, "-i", str(din), "-o", str(dout), "-m", "models-DF2K", "-g", "0,1", "-j", "2:3:2", "-t", "64,64", "-v")
+    assert r.returncode == 0, r.stderr
+    assert "both img03.txt and img03.png output img03.png ! img03.txt will output img03.txt.png" in r.stderr
+    assert "decode image %s failed" % str(din / "img03.txt") in r.stderr
+    assert r.stderr.count(" done\n") == 11
+    assert sorted(os.listdir(str(dout))) == sorted(imgs)
+    for name, im in imgs.items():
+        got = np.asarray(Image.open(str(dout / name)))
+        assert np.array_equal(got, np.repeat(np.repeat(im, 4, 0), 4, 1)), name
+    # file -> file
+    one = str(tmp_path / "one.png")
+    r = cli(bins, "-i", str(din / "img05.png"), "-o", one, "-m", "x/models-DF2K_JPEG")
+    assert r.returncode == 0 and np.array_equal(np.asarray(Image.open(one)), np.repeat(np.repeat(imgs["img05.png"], 4, 0), 4, 1))

@@ -148,3 +148,30 @@ def test_kblock32_kernel_same_contract(models_dir, split):
         assert e.process(img, out) == 0, e.last_error()
         s = diff_stats(out, gold)
         assert (s["max"] <= 1 and s["frac_diff"] <= 0.05) if natural else (s["max"] <= 2 and s["n_gt1"] <= max(2, s["n"] // 10000)), s
+
+
+def test_cpp_cli_png_pipeline(tmp_path, models_dir):
+    """the C++ command line (host/realsr_cli.cpp, PNG through host/png_codec.h) on the real library: file -> file equals
+    the engine's own output for the same input, dir -> dir with two proc threads writes every file"""
+    import subprocess
+    from PIL import Image
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "realsr-ncnn-vulkan_b200", "realsr-b200")
+    img, gold = golden("natural_48x40_df2k_t32")
+    src, dst = str(tmp_path / "a.png"), str(tmp_path / "b.png")
+    Image.fromarray(img).save(src)
+    mdir = os.path.join(root, "models", "models-DF2K")
+    r = subprocess.run([exe, "-i", src, "-o", dst, "-m", mdir, "-t", "32", "-v"], capture_output=True, text=True)
+    assert r.returncode == 0 and " done" in r.stderr, r.stderr
+    e = _engine()
+    e.tilesize = 32
+    ref = np.zeros_like(gold)
+    assert e.process(img, ref) == 0
+    assert np.array_equal(np.asarray(Image.open(dst)), ref)
+    din, dout = tmp_path / "in", tmp_path / "out"
+    din.mkdir(); dout.mkdir()
+    for i in range(5):
+        Image.fromarray(np.random.default_rng(i).integers(0, 256, (20 + i, 30, 3), dtype=np.uint8)).save(str(din / ("%d.png" % i)))
+    r = subprocess.run([exe, "-i", str(din), "-o", str(dout), "-m", mdir, "-j", "2:2:2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert sorted(os.listdir(str(dout))) == ["%d.png" % i for i in range(5)]
