@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opts", default="", help="engine options for A/B runs, e.g. epilogue_split=1,merge_shapes=1 (default: none; "
+                                               "recorded under config.engine_options)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,6 +188,12 @@ def main():
     if eng.load(p, b):
         raise SystemExit("rsr_load failed: " + eng.last_error())
     eng.scale, eng.tilesize, eng.prepadding = 4, TILE, 10
+    engine_options = {}
+    for kv in filter(None, args.opts.split(",")):
+        k, v = kv.split("=")
+        if eng.set_option(k, int(v)):
+            raise SystemExit("rsr_set_option failed: " + eng.last_error())
+        engine_options[k] = int(v)
 
     img = np.random.default_rng(1000 + rank).integers(0, 256, (IMG_H, IMG_W, 3), dtype=np.uint8)
     d_in = torch.from_numpy(img).cuda()
@@ -266,6 +274,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "configs[1]: one 1920x1080 RGB image per GPU per step, models-DF2K, scale 4, tile 400 (15 padded tiles, "
                                    "%d network-input px)" % padded,
+                       "engine_options": engine_options or "defaults",
                        "precision": "fp16 operands / fp32 accumulate on tcgen05, fp32 Conv_0 and fp32 residual stream",
                        "l2": "no flush needed: one step streams ~6 GB of activations through HBM, far above the 126 MB L2",
                        "timing": "CUDA events on the engine's stream around every call, summed over the K steps, max over ranks; "
