@@ -70,7 +70,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b)
 // Where work tile `tt` lives: image b of its group, band by, column tile tx, the group's image size, pixel offset and maps.
 struct TileGeo {
     int b, by, tx, H, W, desc0, g;
-    size_t pxoff;
+    size_t pxoff, aux;
 };
 template <bool MULTI>
 __device__ __forceinline__ TileGeo decode_tile(const ConvArgs& a, const int tt, const int tiles_per_img, const int tiles_x)
@@ -89,6 +89,7 @@ __device__ __forceinline__ TileGeo decode_tile(const ConvArgs& a, const int tt, 
         const int t0 = g == 0 ? a.grp[0].tile_start : g == 1 ? a.grp[1].tile_start : g == 2 ? a.grp[2].tile_start : a.grp[3].tile_start;
         r.desc0 = g == 0 ? a.grp[0].desc0 : g == 1 ? a.grp[1].desc0 : g == 2 ? a.grp[2].desc0 : a.grp[3].desc0;
         r.pxoff = (size_t)(g == 0 ? a.grp[0].px_off : g == 1 ? a.grp[1].px_off : g == 2 ? a.grp[2].px_off : a.grp[3].px_off);
+        r.aux = (size_t)(g == 0 ? a.grp[0].aux_off : g == 1 ? a.grp[1].aux_off : g == 2 ? a.grp[2].aux_off : a.grp[3].aux_off);
         const int lt = tt - t0;
         r.b = lt / tpi;
         const int rem = lt - r.b * tpi;
@@ -100,7 +101,7 @@ __device__ __forceinline__ TileGeo decode_tile(const ConvArgs& a, const int tt, 
         const int rem = tt - r.b * tiles_per_img;
         r.by = rem / tiles_x;
         r.tx = rem - r.by * tiles_x;
-        r.H = a.H; r.W = a.W; r.desc0 = 0; r.g = 0; r.pxoff = 0;
+        r.H = a.H; r.W = a.W; r.desc0 = 0; r.g = 0; r.pxoff = 0; r.aux = 0;
     }
     return r;
 }
@@ -253,7 +254,7 @@ __device__ __forceinline__ void epilogue_split(const ConvArgs& a, Bars* bars, co
                         }
                     }
                 } else {
-                    float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)geo.H * geo.W) + (size_t)yyi * geo.W + x;
+                    float4* dst = reinterpret_cast<float4*>(a.tta_out) + geo.aux + (size_t)td.tta_slot * ((size_t)geo.H * geo.W) + (size_t)yyi * geo.W + x;
                     *dst = make_float4(o[0], o[1], o[2], 0.f);
                 }
             }
@@ -651,7 +652,7 @@ conv3x3_tc2x_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, con
                                 }
                             }
                         } else {
-                            float4* dst = reinterpret_cast<float4*>(a.tta_out) + (size_t)td.tta_slot * ((size_t)geo.H * geo.W) + (size_t)yy[i] * geo.W + x;
+                            float4* dst = reinterpret_cast<float4*>(a.tta_out) + geo.aux + (size_t)td.tta_slot * ((size_t)geo.H * geo.W) + (size_t)yy[i] * geo.W + x;
                             *dst = make_float4(o[0], o[1], o[2], 0.f);
                         }
                     }
@@ -831,8 +832,8 @@ cudaError_t launch_nmskm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t
 template <int NREAL, int MODE>
 cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
 {
-    if (a.ngroups > 0) {  // merged multi-shape launch (not for the TTA store mode: its slot stride is per shape)
-        if (MODE == CONV_LAST_F32 || a.ngroups > 4) return cudaErrorInvalidValue;
+    if (a.ngroups > 0) {  // merged multi-shape launch
+        if (a.ngroups > 4) return cudaErrorInvalidValue;
         if (a.kblock == 32)
             return a.epi_split ? launch_nmskm<NREAL, MODE, true, 32, true>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 32, true>(in_map, a, stream);
         return a.epi_split ? launch_nmskm<NREAL, MODE, true, 64, true>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 64, true>(in_map, a, stream);

@@ -367,10 +367,21 @@ struct Grp {
     size_t off;     // first TileDesc of the group in the call's descriptor array
     int n, H, W;    // tiles, padded tile size
     size_t px_off;  // first pixel of the group in the (LR-resolution) activation buffers of the job
+    size_t tta_off; // TTA: float4 offset of the group's slots in the job's TTA buffer (both halves of a chunk share it)
+};
+struct GatherJob {  // TTA: inverse-transform + average of one chunk of tiles (8 result slots each)
+    size_t off;     // the chunk's 8n descriptors in slot order
+    int n, mw, mh;
+    size_t slot_stride, tta_off;
+};
+struct MJob {
+    std::vector<Grp> gs;
+    std::vector<GatherJob> gathers;
+    size_t tta_float4 = 0;
 };
 
 int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, uint8_t* d_out, const TileDesc* d_tiles_all,
-               const std::vector<Grp>& gs)
+               const std::vector<Grp>& gs, bool tta_out)
 {
     rsr_handle* h = c.h;
     Workspace* ws = c.ws;
@@ -433,6 +444,7 @@ int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_
             cg.tile_start = t0;
             cg.desc0 = (int)gs[g].off;
             cg.px_off = (long long)gs[g].px_off * s * s;
+            cg.aux_off = (long long)gs[g].tta_off;
             t0 += cg.tiles_per_img * cg.B;
         }
         a.ntiles_multi = t0;
@@ -491,9 +503,10 @@ int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_
     {
         ConvArgs a = base;
         fill_groups(a, 4);
-        a.mode = CONV_LAST_U8;
+        a.mode = tta_out ? CONV_LAST_F32 : CONV_LAST_U8;
         a.img_out = d_out; a.img_w = img_w * 4; a.img_h = img_h * 4; a.img_c = img_c;
         a.prepad_s = h->prepadding * 4;
+        a.tta_out = (float*)ws->tta.p;
         if ((r = conv(c, &mapU2, a, m.idx_last()))) return r;
     }
     return 0;
@@ -529,41 +542,76 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
     struct Job { size_t off; int n, H, W; bool tta_out, gather; size_t slot_stride; int mw, mh; };
     std::vector<TileDesc> flat;
     std::vector<Job> jobs;
-    std::vector<std::vector<Grp>> mjobs;  // merge_shapes: every job = up to 4 shape groups, one launch per layer
-    const bool merged = h->merge_shapes && !h->tta && h->conv_impl >= 2;
+    std::vector<MJob> mjobs;  // merge_shapes: every job = up to 4 shape groups, one launch per layer
+    const bool merged = h->merge_shapes && h->conv_impl >= 2;
+    size_t max_tta_bytes = 0;
     if (merged) {
         const double budget = 16e9;  // workspace bytes per job
-        std::vector<Grp> cur;
+        MJob cur;
         double cur_bytes = 0;
         size_t cur_px = 0;
         auto flush = [&]() {
-            if (!cur.empty()) mjobs.push_back(cur);
-            cur.clear(); cur_bytes = 0; cur_px = 0;
+            if (!cur.gs.empty()) {
+                max_tta_bytes = std::max(max_tta_bytes, cur.tta_float4 * sizeof(float4));
+                mjobs.push_back(cur);
+            }
+            cur = MJob();
+            cur_bytes = 0; cur_px = 0;
         };
+        const int per_tile = h->tta ? 8 : 1;   // network passes per tile
+        const size_t need = h->tta ? 2 : 1;    // group slots per chunk: TTA runs variants 0..3 as H x W and 4..7 as W x H
         for (auto g = groups.rbegin(); g != groups.rend(); ++g) {
             const int H = g->first.first, W = g->first.second;
             const std::vector<TileDesc>& tl = g->second;
-            const double bpt = (double)H * W * (768.0 + 768.0 + 1024.0 + 4096.0);
+            const double bpt = (double)per_tile * H * W * (768.0 + 768.0 + 1024.0 + 4096.0 + (h->tta ? 512.0 : 0.0));
             size_t pos = 0;
             while (pos < tl.size()) {
                 long long cap = (long long)((budget - cur_bytes) / bpt);
-                if (h->max_batch > 0) cap = std::min(cap, h->max_batch);
-                if (cur.size() == 4 || cap < 1) {
-                    if (cur.empty()) cap = 1;  // a single tile larger than the budget still has to run
+                if (h->max_batch > 0) cap = std::min(cap, std::max(1LL, h->max_batch / per_tile));
+                if (cur.gs.size() + need > 4 || cap < 1) {
+                    if (cur.gs.empty()) cap = 1;  // a single tile larger than the budget still has to run
                     else { flush(); continue; }
                 }
                 const size_t take = std::min(tl.size() - pos, (size_t)cap);
-                cur.push_back({flat.size(), (int)take, H, W, cur_px});
-                flat.insert(flat.end(), tl.begin() + pos, tl.begin() + pos + take);
-                cur_px += take * (size_t)H * W;
+                if (!h->tta) {
+                    cur.gs.push_back({flat.size(), (int)take, H, W, cur_px, 0});
+                    flat.insert(flat.end(), tl.begin() + pos, tl.begin() + pos + take);
+                    cur_px += take * (size_t)H * W;
+                } else {
+                    // 8 dihedral variants per tile (src/realsr.cpp:242-318): 0..3 keep the shape, 4..7 run transposed
+                    const size_t slot_stride = (size_t)16 * H * W;  // float4 per result slot
+                    for (int half = 0; half < 2; half++) {
+                        cur.gs.push_back({flat.size(), (int)take * 4, half ? W : H, half ? H : W, cur_px, cur.tta_float4});
+                        for (size_t gi = 0; gi < take; gi++)
+                            for (int v = half * 4; v < half * 4 + 4; v++) {
+                                TileDesc t = tl[pos + gi];
+                                t.variant = v;
+                                t.tta_slot = (int)(gi * 8 + v);
+                                flat.push_back(t);
+                            }
+                        cur_px += take * 4 * (size_t)H * W;
+                    }
+                    GatherJob gj{flat.size(), (int)take, 0, 0, slot_stride, cur.tta_float4};
+                    for (size_t gi = 0; gi < take; gi++) {
+                        gj.mw = std::max(gj.mw, tl[pos + gi].crop_w);
+                        gj.mh = std::max(gj.mh, tl[pos + gi].crop_h);
+                        for (int v = 0; v < 8; v++) {
+                            TileDesc t = tl[pos + gi];
+                            t.variant = v;
+                            t.tta_slot = (int)(gi * 8 + v);
+                            flat.push_back(t);
+                        }
+                    }
+                    cur.gathers.push_back(gj);
+                    cur.tta_float4 += take * 8 * slot_stride;
+                }
                 cur_bytes += take * bpt;
-                padded += (long long)take * H * W;
+                padded += (long long)take * per_tile * H * W;
                 pos += take;
             }
         }
         flush();
     }
-    size_t max_tta_bytes = 0;
     for (auto g = groups.rbegin(); !merged && g != groups.rend(); ++g) {
         const int H = g->first.first, W = g->first.second;
         std::vector<TileDesc>& tl = g->second;
@@ -622,8 +670,16 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
     if (max_tta_bytes && (r = ensure(h, ws->tta, max_tta_bytes))) return r;
     CK(cudaMemcpyAsync(ws->tiles.p, ws->h_tiles, sizeof(TileDesc) * flat.size(), cudaMemcpyHostToDevice, ws->stream));
     const TileDesc* d_tiles = (const TileDesc*)ws->tiles.p;
-    for (const std::vector<Grp>& mj : mjobs)
-        if ((r = run_merged(c, d_in, w, hh, ch, d_out, d_tiles, mj))) return r;
+    for (const MJob& mj : mjobs) {
+        if ((r = run_merged(c, d_in, w, hh, ch, d_out, d_tiles, mj.gs, h->tta != 0))) return r;
+        for (const GatherJob& gj : mj.gathers) {
+            TtaGatherArgs ga{};
+            ga.tta_out = (const float*)((const float4*)ws->tta.p + gj.tta_off); ga.tiles = d_tiles + gj.off; ga.ngroups = gj.n;
+            ga.slot_stride = gj.slot_stride; ga.img_out = d_out; ga.img_w = w * 4; ga.img_h = hh * 4; ga.img_c = ch; ga.prepad_s = P * 4;
+            CK(launch_tta_gather(ga, gj.mw, gj.mh, ws->stream));
+            c.launches++;
+        }
+    }
     for (const Job& j : jobs) {
         if (!j.gather) {
             if ((r = run_batch(c, d_in, w, hh, ch, d_out, d_tiles + j.off, j.n, j.H, j.W, j.tta_out))) return r;

@@ -46,6 +46,7 @@ struct ConvGroup {
     int tile_start;              // first work tile of the group in the launch-wide numbering
     int desc0;                   // index of the group's first TileDesc in ConvArgs::tiles
     long long px_off;            // pixel offset of the group inside the activation buffers (already scaled for 2x / 4x layers)
+    long long aux_off;           // CONV_LAST_F32: float4 offset of the group's first TTA slot inside ConvArgs::tta_out
 };
 
 struct ConvArgs {

@@ -81,6 +81,19 @@ def test_merged_shape_launches_are_bit_identical(models_dir, opts):
     assert new.kernel_launches() - before == 350 + 3 * 4
 
 
+def test_merged_shape_launches_tta_bit_identical(models_dir):
+    """merge_shapes with TTA: both orientations (variants 0..3 as H x W, 4..7 as W x H) of up to two shape chunks share
+    one launch per layer; result slots are addressed through the per-group TTA offset"""
+    a, b = _engine(tta=True), _engine(tta=True, merge_shapes=1)
+    rng = np.random.default_rng(17)
+    for (h, w, c, tile) in [(45, 61, 3, 32), (70, 50, 4, 32), (200, 330, 3, 200)]:
+        img = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        oa, ob = np.zeros((4 * h, 4 * w, c), np.uint8), np.zeros((4 * h, 4 * w, c), np.uint8)
+        a.tilesize = b.tilesize = tile
+        assert a.process(img, oa) == 0 and b.process(img, ob) == 0, b.last_error()
+        assert np.array_equal(oa, ob), (h, w, c, tile, diff_stats(oa, ob))
+
+
 def test_split_epilogue_tta_and_goldens(models_dir):
     new = _engine(epilogue_split=1)
     for name, natural in (("natural_48x40_df2k_t32", True), ("noise_50x33_df2k_t32", False), ("readme0_crop96x80_df2k_t64", True)):
