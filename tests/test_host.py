@@ -173,3 +173,19 @@ def test_cpp_wrapper_compiles_and_fails_loudly(tmp_path, models_dir):
     r = subprocess.run([str(exe), os.path.join(models_dir, "models-DF2K"), str(raw), "8", "8", str(tmp_path / "o.raw")], capture_output=True, text=True)
     if not has_gpu:
         assert r.returncode == 4 and "invalid gpu device" in r.stderr
+
+
+def test_options_and_tile_api_validate_without_gpu():
+    """rsr_set_option rejects unknown keys / out-of-range values; rsr_tile_count follows the reference tile grid;
+    rsr_process_tiles on a handle without a model is an error (no GPU needed for any of it)"""
+    e = rb.RealSR(0)
+    assert e.set_option("no_such_option", 1) != 0 and "unknown option" in e.last_error()
+    assert e.set_option("conv_impl", 7) != 0 and "conv_impl" in e.last_error()
+    for key in ("epilogue_split", "merge_shapes", "serpentine", "residual_fp16", "max_batch", "conv_impl"):
+        assert e.set_option(key, 1) == 0, key
+    e.tilesize = 400
+    assert e.tile_count(1920, 1080) == 15
+    e.tilesize = 200
+    assert e.tile_count(3840, 2160) == 220 and e.tile_count(1, 1) == 1
+    img, out = np.zeros((40, 40, 3), np.uint8), np.zeros((160, 160, 3), np.uint8)
+    assert e.process_tiles(img, out, 0, 1) != 0 and "no model" in e.last_error()
