@@ -1,9 +1,10 @@
-// png_tool.cpp -- exercises host/png_codec.h from the command line (used by tests/test_cpp_cli.py):
+// png_tool.cpp -- exercises host/png_codec.h and host/jpeg_codec.h (by file extension) from the command line (used by tests/test_cpp_cli.py):
 //   png_tool decode in.png out.raw     -> prints "w h c", writes w*h*c bytes
 //   png_tool encode in.raw w h c out.png [zlib-level]
 #include <stdio.h>
 #include <stdlib.h>
 
+#include "jpeg_codec.h"
 #include "png_codec.h"
 
 int main(int argc, char** argv)
@@ -12,7 +13,9 @@ int main(int argc, char** argv)
         int w, h, c;
         std::vector<uint8_t> px;
         std::string why;
-        if (!rsrhost::png_decode_file(argv[2], w, h, c, px, &why)) {
+        const std::string in = argv[2];
+        const bool jpg = in.size() > 4 && (in.substr(in.size() - 4) == ".jpg" || in.substr(in.size() - 5) == ".jpeg");
+        if (!(jpg ? rsrhost::jpeg_decode_file(in, w, h, c, px, &why) : rsrhost::png_decode_file(in, w, h, c, px, &why))) {
             fprintf(stderr, "decode failed: %s\n", why.c_str());
             return 1;
         }
@@ -28,7 +31,9 @@ int main(int argc, char** argv)
         FILE* fp = fopen(argv[2], "rb");
         if (!fp || fread(px.data(), 1, px.size(), fp) != px.size()) return 2;
         fclose(fp);
-        return rsrhost::png_encode_file(argv[6], px.data(), w, h, c, argc == 8 ? atoi(argv[7]) : 1) ? 0 : 1;
+        const std::string outp = argv[6];
+        if (outp.size() > 4 && outp.substr(outp.size() - 4) == ".jpg") return rsrhost::jpeg_encode_file(outp, px.data(), w, h, c, argc == 8 ? atoi(argv[7]) : 100) ? 0 : 1;
+        return rsrhost::png_encode_file(outp, px.data(), w, h, c, argc == 8 ? atoi(argv[7]) : 1) ? 0 : 1;
     }
     fprintf(stderr, "usage: png_tool decode in.png out.raw | png_tool encode in.raw w h c out.png [level]\n");
     return 64;

@@ -138,6 +138,47 @@ def test_png_encode_roundtrip(bins, tmp_path, c):
     assert os.path.getsize(str(tmp_path / "smooth.png")) < smooth.size // 3  # the filter heuristic does compress gradients
 
 
+def test_jpeg_decode_matches_libjpeg(bins, tmp_path):
+    """baseline JPEG reader vs Pillow (libjpeg-turbo): IDCT / upsampling / colour rounding differ by a few LSB at most"""
+    rng = np.random.default_rng(21)
+    yy, xx = np.mgrid[0:75, 0:101]
+    img = np.stack([np.sin(xx / 9.) * 80 + 128 + yy / 2, np.cos(yy / 7.) * 70 + 120 + xx / 3, ((xx * yy) % 200) + 20.], -1)
+    img = np.clip(img + rng.normal(0, 6, img.shape), 0, 255).astype(np.uint8)
+    cases = [("q95_444", img, dict(quality=95, subsampling=0)), ("q90_420", img, dict(quality=90, subsampling=2)),
+             ("q85_422", img, dict(quality=85, subsampling=1)), ("q75", img, dict(quality=75)), ("gray", img[..., 0], dict(quality=90)),
+             ("rst", img, dict(quality=90, subsampling=2, restart_marker_blocks=3)), ("odd", img[:33, :17], dict(quality=92, subsampling=2))]
+    for name, arr, kw in cases:
+        p = str(tmp_path / (name + ".jpg"))
+        try:
+            Image.fromarray(arr).save(p, **kw)
+        except TypeError:  # older Pillow without restart_marker_blocks
+            continue
+        got = decode(bins, p, str(tmp_path)).astype(int)
+        ref = np.asarray(Image.open(p).convert("RGB")).astype(int)
+        d = np.abs(got - ref)
+        assert got.shape == ref.shape and d.max() <= 4 and d.mean() < 0.35 and (d > 2).mean() < 0.002, (name, d.max(), d.mean())
+    # progressive files are refused, not mis-decoded
+    p = str(tmp_path / "prog.jpg")
+    Image.fromarray(img).save(p, quality=90, progressive=True)
+    r = subprocess.run([os.path.join(bins, "png_tool"), "decode", p, str(tmp_path / "x.raw")], capture_output=True, text=True)
+    assert r.returncode != 0 and "progressive" in r.stderr
+
+
+def test_jpeg_encode_quality_100(bins, tmp_path):
+    """baseline 4:4:4 writer at the reference's quality (stbi_write_jpg(..., 100), main.cpp:397): libjpeg reads it back
+    within rounding"""
+    rng = np.random.default_rng(22)
+    for name, img in (("noise", rng.integers(0, 256, (50, 70, 3), dtype=np.uint8)),
+                      ("flat", np.full((9, 9, 3), 200, np.uint8)), ("ramp", np.stack([np.tile(np.arange(64, dtype=np.uint8) * 4, (40, 1))] * 3, -1))):
+        raw, jpg = str(tmp_path / (name + ".raw")), str(tmp_path / (name + ".jpg"))
+        img.tofile(raw)
+        h, w, _ = img.shape
+        subprocess.run([os.path.join(bins, "png_tool"), "encode", raw, str(w), str(h), "3", jpg], check=True)
+        back = np.asarray(Image.open(jpg).convert("RGB")).astype(int)
+        d = np.abs(back - img.astype(int))
+        assert back.shape == img.shape and d.max() <= 4 and d.mean() < 0.8, (name, d.max(), d.mean())
+
+
 def cli(bins, *args):
     return subprocess.run([os.path.join(bins, "realsr-b200")] + list(args), capture_output=True, text=True)
 
@@ -159,7 +200,7 @@ def test_cli_argument_validation(bins, tmp_path):
     assert "must be either file or directory at the same time" in cli(bins, "-i", img, "-o", str(tmp_path)).stderr
     assert "unknown model dir type" in cli(bins, "-i", img, "-o", out, "-m", "models-other").stderr
     assert "no CPU mode" in cli(bins, "-i", img, "-o", out, "-g", "-1", "-m", "models-DF2K").stderr
-    assert "png only" in cli(bins, "-i", img, "-o", str(tmp_path / "o.jpg")).stderr
+    assert "jpg/png only" in cli(bins, "-i", img, "-o", str(tmp_path / "o.webp")).stderr
     r = cli(bins, "-i", img, "-o", out, "-m", "missing/models-DF2K")
     assert r.returncode != 0 and "load failed" in r.stderr
 
@@ -186,6 +227,18 @@ def test_cli_pipeline_directory_mode(bins, tmp_path):
     for name, im in imgs.items():
         got = np.asarray(Image.open(str(dout / name)))
         assert np.array_equal(got, np.repeat(np.repeat(im, 4, 0), 4, 1)), name
+    # jpg in, jpg out (-f jpg), and the reference's rule for alpha inputs: <name>.jpg.png (main.cpp:279-288)
+    dj, djo = tmp_path / "jin", tmp_path / "jout"
+    dj.mkdir(); djo.mkdir()
+    smooth = np.stack([np.tile(np.arange(40, dtype=np.uint8) * 6, (30, 1))] * 3, -1)
+    Image.fromarray(smooth).save(str(dj / "a.jpg"), quality=95, subsampling=0)
+    Image.fromarray(imgs["img03.png"]).save(str(dj / "b.png"))  # RGBA
+    r = cli(bins, "-i", str(dj), "-o", str(djo), "-m", "models-DF2K", "-f", "jpg")
+    assert r.returncode == 0, r.stderr
+    assert "has alpha channel" in r.stderr and sorted(os.listdir(str(djo))) == ["a.jpg", "b.jpg.png"]
+    up = np.repeat(np.repeat(np.asarray(Image.open(str(dj / "a.jpg")).convert("RGB")), 4, 0), 4, 1).astype(int)
+    assert np.abs(np.asarray(Image.open(str(djo / "a.jpg")).convert("RGB")).astype(int) - up).max() <= 6
+    assert np.array_equal(np.asarray(Image.open(str(djo / "b.jpg.png"))), np.repeat(np.repeat(imgs["img03.png"], 4, 0), 4, 1))
     # file -> file
     one = str(tmp_path / "one.png")
     r = cli(bins, "-i", str(din / "img05.png"), "-o", one, "-m", "x/models-DF2K_JPEG")
