@@ -1,10 +1,11 @@
-// jpeg_codec.h -- baseline JPEG reader / writer for the C++ command line (host/realsr_cli.cpp).
+// jpeg_codec.h -- JPEG reader (sequential + progressive) / baseline writer for the C++ command line (host/realsr_cli.cpp).
 //
 // The reference reads jpg through its vendored stb_image and writes with stbi_write_jpg(..., quality 100)
 // (src/main.cpp:243-263, :397); those files are not copied.  This is an independent implementation of ITU-T T.81:
-//   decode: baseline / extended sequential DCT (SOF0, SOF1), Huffman, 8-bit, 1 or 3 components (YCbCr, JFIF), any
-//           sampling factors up to 2x2 with the triangle ("fancy") chroma upsampling libjpeg applies, restart intervals;
-//           progressive (SOF2) and arithmetic-coded files are refused with a message;
+//   decode: sequential (SOF0, SOF1; interleaved or one scan per component) and progressive (SOF2: spectral selection and
+//           successive approximation, Annex G) DCT, Huffman, 8-bit, 1 or 3 components (YCbCr, JFIF), sampling factors up
+//           to 2x2 with the triangle ("fancy") chroma upsampling libjpeg applies, restart intervals; arithmetic-coded and
+//           lossless files are refused with a message;
 //   encode: baseline, 4:4:4, standard Huffman tables, the Annex K quantisation tables scaled libjpeg-style by a quality.
 // Host plumbing only: no pixel of the super-resolution path is computed here.
 #pragma once
@@ -142,7 +143,9 @@ inline void fdct8x8(const float* in, float* out)
 
 }  // namespace jpg
 
-// Decodes a baseline JPEG file to 8-bit RGB (c = 3; gray is expanded like the reference's load stage does).
+// Decodes a Huffman-coded 8-bit JPEG file (sequential or progressive) to 8-bit RGB (c = 3; gray is expanded like the
+// reference's load stage does).  All scans are decoded into per-block coefficient storage first (T.81 Annex G for the
+// progressive passes), dequantisation + IDCT follow once at the end.
 inline bool jpeg_decode_file(const std::string& path, int& w, int& h, int& c, std::vector<uint8_t>& pixels, std::string* why = nullptr)
 {
     using namespace jpg;
@@ -160,17 +163,24 @@ inline bool jpeg_decode_file(const std::string& path, int& w, int& h, int& c, st
     uint16_t qt[4][64] = {};
     bool qt_ok[4] = {};
     Huff hdc[4], hac[4];
-    struct Comp { int id, hs, vs, tq, td, ta, bw, bh; std::vector<uint8_t> plane; int pred; } comp[3];
+    struct Comp {
+        int id, hs, vs, tq, td, ta;
+        int bw, bh;    // plane size in pixels, padded to whole MCUs
+        int nbx, nby;  // blocks that carry image data (non-interleaved scans visit only these)
+        std::vector<int16_t> coef;  // [bh/8][bw/8][64], natural order
+        std::vector<uint8_t> plane;
+        int pred;
+    } comp[3];
     int ncomp = 0, restart = 0, hmax = 1, vmax = 1;
-    bool have_sof = false, adobe = false;
+    bool have_sof = false, progressive = false, adobe = false, saw_scan = false;
     int adobe_transform = -1;
     size_t pos = 2;
     while (pos + 4 <= f.size()) {
-        if (f[pos] != 0xFF) return fail("marker expected");
+        if (f[pos] != 0xFF) { pos++; continue; }  // tolerate stray bytes between segments
         while (pos < f.size() && f[pos] == 0xFF) pos++;  // fill bytes
         if (pos >= f.size()) break;
         const int marker = f[pos++];
-        if (marker == 0xD8 || (marker >= 0xD0 && marker <= 0xD7) || marker == 0x01) continue;
+        if (marker == 0x00 || marker == 0xD8 || (marker >= 0xD0 && marker <= 0xD7) || marker == 0x01) continue;
         if (marker == 0xD9) break;
         if (pos + 2 > f.size()) return fail("truncated segment");
         const size_t len = ((size_t)f[pos] << 8) | f[pos + 1];
@@ -200,8 +210,10 @@ inline bool jpeg_decode_file(const std::string& path, int& w, int& h, int& c, st
                 (tc ? hac[th] : hdc[th]).build(&d[i + 1], &d[i + 17], total);
                 i += 17 + total;
             }
-        } else if (marker == 0xC0 || marker == 0xC1) {  // SOF0 / SOF1
+        } else if (marker == 0xC0 || marker == 0xC1 || marker == 0xC2) {  // SOF0 / SOF1 / SOF2
+            if (have_sof) return fail("more than one frame");
             if (n < 6 || d[0] != 8) return fail("only 8-bit JPEG is supported");
+            progressive = marker == 0xC2;
             h = (d[1] << 8) | d[2];
             w = (d[3] << 8) | d[4];
             ncomp = d[5];
@@ -212,82 +224,214 @@ inline bool jpeg_decode_file(const std::string& path, int& w, int& h, int& c, st
                 comp[k].vs = d[7 + 3 * k] & 15;
                 comp[k].tq = d[8 + 3 * k];
                 if (comp[k].hs < 1 || comp[k].hs > 2 || comp[k].vs < 1 || comp[k].vs > 2 || comp[k].tq > 3) return fail("unsupported sampling factors");
+                if (ncomp == 1) comp[k].hs = comp[k].vs = 1;  // a single component is never subsampled against itself
                 hmax = std::max(hmax, comp[k].hs);
                 vmax = std::max(vmax, comp[k].vs);
             }
+            const int mx = (w + 8 * hmax - 1) / (8 * hmax), my = (h + 8 * vmax - 1) / (8 * vmax);
+            for (int k = 0; k < ncomp; k++) {
+                comp[k].bw = mx * comp[k].hs * 8;
+                comp[k].bh = my * comp[k].vs * 8;
+                const int cw = (w * comp[k].hs + hmax - 1) / hmax, chh = (h * comp[k].vs + vmax - 1) / vmax;
+                comp[k].nbx = (cw + 7) / 8;
+                comp[k].nby = (chh + 7) / 8;
+                comp[k].coef.assign((size_t)(comp[k].bw / 8) * (comp[k].bh / 8) * 64, 0);
+            }
             have_sof = true;
-        } else if (marker == 0xC2) return fail("progressive JPEG is not supported by the C++ command line (use the Python CLI)");
-        else if (marker >= 0xC3 && marker <= 0xCF && marker != 0xC4 && marker != 0xC8 && marker != 0xCC) return fail("unsupported JPEG process");
+        } else if (marker >= 0xC3 && marker <= 0xCF && marker != 0xC4 && marker != 0xC8 && marker != 0xCC) return fail("unsupported JPEG process (lossless / arithmetic)");
         else if (marker == 0xDD) { if (n >= 2) restart = (d[0] << 8) | d[1]; }
         else if (marker == 0xEE && n >= 12 && !memcmp(d, "Adobe", 5)) { adobe = true; adobe_transform = d[11]; }
-        else if (marker == 0xDA) {  // SOS: header, then the entropy-coded segment
+        else if (marker == 0xDA) {  // SOS: scan header, then the entropy-coded segment
             if (!have_sof) return fail("SOS before SOF");
-            if (n < 1 || d[0] != ncomp || n < (size_t)(1 + 2 * ncomp + 3)) return fail("non-interleaved scans are not supported");
-            for (int k = 0; k < ncomp; k++) {
+            const int ns = n ? d[0] : 0;
+            if (ns < 1 || ns > ncomp || n < (size_t)(1 + 2 * ns + 3)) return fail("bad scan header");
+            int sc[3];
+            for (int k = 0; k < ns; k++) {
                 int ci = -1;
                 for (int j = 0; j < ncomp; j++)
                     if (comp[j].id == d[1 + 2 * k]) ci = j;
                 if (ci < 0) return fail("bad scan component");
+                sc[k] = ci;
                 comp[ci].td = d[2 + 2 * k] >> 4;
                 comp[ci].ta = d[2 + 2 * k] & 15;
-                if (comp[ci].td > 3 || comp[ci].ta > 3 || !hdc[comp[ci].td].present || !hac[comp[ci].ta].present || !qt_ok[comp[ci].tq]) return fail("missing table");
+                if (comp[ci].td > 3 || comp[ci].ta > 3) return fail("bad table index");
             }
-            const int mcu_w = 8 * hmax, mcu_h = 8 * vmax;
-            const int mx = (w + mcu_w - 1) / mcu_w, my = (h + mcu_h - 1) / mcu_h;
-            for (int k = 0; k < ncomp; k++) {
-                if (ncomp == 1) { comp[k].hs = comp[k].vs = 1; }
-                comp[k].bw = (ncomp == 1 ? (w + 7) / 8 : mx * comp[k].hs) * 8;
-                comp[k].bh = (ncomp == 1 ? (h + 7) / 8 : my * comp[k].vs) * 8;
-                comp[k].plane.assign((size_t)comp[k].bw * comp[k].bh, 0);
-                comp[k].pred = 0;
+            const int Ss = d[1 + 2 * ns], Se = d[2 + 2 * ns], Ah = d[3 + 2 * ns] >> 4, Al = d[3 + 2 * ns] & 15;
+            if (!progressive && (Ss != 0 || Se != 63 || Ah || Al)) return fail("bad sequential scan parameters");
+            if (progressive && (Ss > Se || Se > 63 || (Ss == 0 && Se != 0) || (Ss > 0 && ns != 1) || Al > 13)) return fail("bad progressive scan parameters");
+            for (int k = 0; k < ns; k++) {
+                const Comp& cc = comp[sc[k]];
+                if ((Ss == 0 && Ah == 0 && !hdc[cc.td].present) || ((Se > 0) && !hac[cc.ta].present)) return fail("missing Huffman table");
             }
-            if (ncomp == 1) hmax = vmax = 1;
-            const int nmx = ncomp == 1 ? (w + 7) / 8 : mx, nmy = ncomp == 1 ? (h + 7) / 8 : my;
             BitReader br;
             br.p = &f[pos + len];
             br.end = f.data() + f.size();
-            int mcus_left = restart;
-            for (int yy = 0; yy < nmy; yy++)
-                for (int xx = 0; xx < nmx; xx++) {
-                    if (restart && mcus_left == 0) {  // expect RSTn: realign, reset predictors
-                        br.reset();
-                        while (br.p + 1 < br.end && !(br.p[0] == 0xFF && br.p[1] >= 0xD0 && br.p[1] <= 0xD7)) br.p++;
-                        if (br.p + 1 < br.end) br.p += 2;
-                        for (int k = 0; k < ncomp; k++) comp[k].pred = 0;
-                        mcus_left = restart;
+            for (int k = 0; k < ncomp; k++) comp[k].pred = 0;
+            int eobrun = 0;
+            // one block of the scan; returns false on a corrupt stream
+            auto decode_block = [&](Comp& cc, int16_t* blk) -> bool {
+                if (!progressive) {
+                    const int t = decode_symbol(br, hdc[cc.td]);
+                    if (t < 0 || t > 11) return false;
+                    cc.pred += extend(br.get(t), t);
+                    blk[0] = (int16_t)cc.pred;
+                    for (int i = 1; i < 64;) {
+                        const int rs = decode_symbol(br, hac[cc.ta]);
+                        if (rs < 0) return false;
+                        const int r = rs >> 4, s = rs & 15;
+                        if (s == 0) {
+                            if (r == 15) { i += 16; continue; }
+                            break;
+                        }
+                        i += r;
+                        if (i > 63) return false;
+                        blk[kZigzag[i]] = (int16_t)extend(br.get(s), s);
+                        i++;
                     }
-                    for (int k = 0; k < ncomp; k++)
-                        for (int by = 0; by < comp[k].vs; by++)
-                            for (int bx = 0; bx < comp[k].hs; bx++) {
-                                float blk[64] = {};
-                                const int t = decode_symbol(br, hdc[comp[k].td]);
-                                if (t < 0 || t > 11) return fail("bad DC code");
-                                comp[k].pred += extend(br.get(t), t);
-                                blk[0] = (float)comp[k].pred * qt[comp[k].tq][0];
-                                for (int i = 1; i < 64;) {
-                                    const int rs = decode_symbol(br, hac[comp[k].ta]);
-                                    if (rs < 0) return fail("bad AC code");
-                                    const int r = rs >> 4, s = rs & 15;
-                                    if (s == 0) {
-                                        if (r == 15) { i += 16; continue; }
-                                        break;
-                                    }
-                                    i += r;
-                                    if (i > 63) return fail("AC run past the block");
-                                    const int z = kZigzag[i];
-                                    blk[z] = (float)extend(br.get(s), s) * qt[comp[k].tq][z];
-                                    i++;
-                                }
-                                const int px = (xx * comp[k].hs + bx) * 8, py = (yy * comp[k].vs + by) * 8;
-                                idct8x8(blk, &comp[k].plane[(size_t)py * comp[k].bw + px], comp[k].bw);
-                            }
-                    if (restart) mcus_left--;
+                    return true;
                 }
-            break;  // baseline: one interleaved scan holds the image
+                if (Ss == 0) {  // DC scan
+                    if (Ah == 0) {
+                        const int t = decode_symbol(br, hdc[cc.td]);
+                        if (t < 0 || t > 11) return false;
+                        cc.pred += extend(br.get(t), t);
+                        blk[0] = (int16_t)(cc.pred * (1 << Al));
+                    } else if (br.get(1)) {
+                        blk[0] = (int16_t)(blk[0] | (1 << Al));
+                    }
+                    return true;
+                }
+                if (Ah == 0) {  // AC first pass (G.1.2.2)
+                    if (eobrun > 0) { eobrun--; return true; }
+                    for (int k = Ss; k <= Se;) {
+                        const int rs = decode_symbol(br, hac[cc.ta]);
+                        if (rs < 0) return false;
+                        const int r = rs >> 4, s = rs & 15;
+                        if (s == 0) {
+                            if (r < 15) {
+                                eobrun = (1 << r) - 1;
+                                if (r) eobrun += br.get(r);
+                                break;
+                            }
+                            k += 16;
+                            continue;
+                        }
+                        k += r;
+                        if (k > 63) return false;
+                        blk[kZigzag[k]] = (int16_t)(extend(br.get(s), s) * (1 << Al));
+                        k++;
+                    }
+                    return true;
+                }
+                // AC refinement pass (G.1.2.3): correction bits for already-nonzero coefficients interleave with the
+                // placement of newly nonzero ones
+                const int p1 = 1 << Al, m1 = -(1 << Al);
+                int k = Ss;
+                if (eobrun == 0) {
+                    while (k <= Se) {
+                        const int rs = decode_symbol(br, hac[cc.ta]);
+                        if (rs < 0) return false;
+                        int r = rs >> 4;
+                        const int s = rs & 15;
+                        int val = 0;
+                        if (s == 0) {
+                            if (r < 15) {
+                                eobrun = 1 << r;
+                                if (r) eobrun += br.get(r);
+                                break;
+                            }
+                        } else {
+                            if (s != 1) return false;
+                            val = br.get(1) ? p1 : m1;
+                        }
+                        while (k <= Se) {
+                            int16_t& cf = blk[kZigzag[k]];
+                            if (cf != 0) {
+                                if (br.get(1) && (cf & p1) == 0) cf = (int16_t)(cf + (cf > 0 ? p1 : m1));
+                            } else {
+                                if (r == 0) {
+                                    if (val) cf = (int16_t)val;
+                                    k++;
+                                    break;
+                                }
+                                r--;
+                            }
+                            k++;
+                        }
+                    }
+                }
+                if (eobrun > 0) {
+                    for (; k <= Se; k++) {
+                        int16_t& cf = blk[kZigzag[k]];
+                        if (cf != 0 && br.get(1) && (cf & p1) == 0) cf = (int16_t)(cf + (cf > 0 ? p1 : m1));
+                    }
+                    eobrun--;
+                }
+                return true;
+            };
+            auto restart_if_due = [&](int& left) {
+                if (restart && left == 0) {  // RSTn expected: byte-align, skip to it, reset the predictors
+                    br.reset();
+                    while (br.p + 1 < br.end && !(br.p[0] == 0xFF && br.p[1] >= 0xD0 && br.p[1] <= 0xD7)) br.p++;
+                    if (br.p + 1 < br.end) br.p += 2;
+                    for (int k = 0; k < ncomp; k++) comp[k].pred = 0;
+                    eobrun = 0;
+                    left = restart;
+                }
+            };
+            int left = restart;
+            if (ns == 1) {  // non-interleaved: the component's own block raster
+                Comp& cc = comp[sc[0]];
+                const int rowblocks = cc.bw / 8;
+                for (int y = 0; y < cc.nby; y++)
+                    for (int x = 0; x < cc.nbx; x++) {
+                        restart_if_due(left);
+                        if (!decode_block(cc, &cc.coef[((size_t)y * rowblocks + x) * 64])) return fail("corrupt entropy-coded data");
+                        if (restart) left--;
+                    }
+            } else {
+                const int mx = comp[0].bw / (8 * comp[0].hs), my = comp[0].bh / (8 * comp[0].vs);
+                for (int yy = 0; yy < my; yy++)
+                    for (int xx = 0; xx < mx; xx++) {
+                        restart_if_due(left);
+                        for (int k = 0; k < ns; k++) {
+                            Comp& cc = comp[sc[k]];
+                            const int rowblocks = cc.bw / 8;
+                            for (int by = 0; by < cc.vs; by++)
+                                for (int bx = 0; bx < cc.hs; bx++)
+                                    if (!decode_block(cc, &cc.coef[((size_t)(yy * cc.vs + by) * rowblocks + xx * cc.hs + bx) * 64]))
+                                        return fail("corrupt entropy-coded data");
+                        }
+                        if (restart) left--;
+                    }
+            }
+            saw_scan = true;
+            // continue at the next marker after the entropy-coded segment
+            size_t q = (size_t)(br.p - f.data());
+            if (q < pos + len) q = pos + len;
+            while (q + 1 < f.size() && !(f[q] == 0xFF && f[q + 1] != 0x00 && !(f[q + 1] >= 0xD0 && f[q + 1] <= 0xD7) && f[q + 1] != 0xFF)) q++;
+            pos = q;
+            continue;
         }
         pos += len;
     }
-    if (!have_sof || comp[0].plane.empty()) return fail("no image data");
+    if (!have_sof || !saw_scan) return fail("no image data");
+    // dequantise + IDCT every block
+    for (int k = 0; k < ncomp; k++) {
+        Comp& cc = comp[k];
+        if (!qt_ok[cc.tq]) return fail("missing quantisation table");
+        cc.plane.assign((size_t)cc.bw * cc.bh, 0);
+        const int rowblocks = cc.bw / 8;
+        for (int y = 0; y < cc.bh / 8; y++)
+            for (int x = 0; x < rowblocks; x++) {
+                const int16_t* cf = &cc.coef[((size_t)y * rowblocks + x) * 64];
+                float blk[64];
+                for (int i = 0; i < 64; i++) blk[i] = (float)cf[i] * qt[cc.tq][i];
+                idct8x8(blk, &cc.plane[(size_t)y * 8 * cc.bw + x * 8], cc.bw);
+            }
+        cc.coef.clear();
+        cc.coef.shrink_to_fit();
+    }
     // colour: full-resolution planes (triangle upsampling for subsampled chroma), then YCbCr -> RGB (JFIF)
     c = 3;
     pixels.resize((size_t)w * h * 3);

@@ -7,9 +7,9 @@
 // threads, jobs_proc[i] per GPU sharing that GPU's RealSR object -> queue of 8 -> save threads; sentinel shutdown).
 // Differences: `-g` takes CUDA ordinals and `-g -1` (ncnn CPU mode) is refused; one proc count is broadcast to all
 // GPUs (BASELINE configs[2] uses `-j 4:8:4` with 8 GPUs, which the reference itself rejects, main.cpp:560-564); auto
-// tile size is 400; codecs: PNG (host/png_codec.h on zlib) and baseline JPEG (host/jpeg_codec.h), both written for this
-// repo -- the reference's stb / libwebp files are not copied; WebP and progressive JPEG go through the Python CLI
-// (`python -m realsr_ncnn_vulkan_b200.cli`, Pillow).  Host plumbing only: every pixel goes through RealSR::process.
+// tile size is 400; codecs: PNG (host/png_codec.h on zlib) and JPEG (host/jpeg_codec.h: sequential + progressive reader,
+// baseline writer), both written for this repo -- the reference's stb / libwebp files are not copied; WebP goes through
+// the Python CLI (`python -m realsr_ncnn_vulkan_b200.cli`, Pillow).  Host plumbing only: every pixel goes through RealSR::process.
 #include <dirent.h>
 #include <stdio.h>
 #include <stdlib.h>

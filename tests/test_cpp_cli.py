@@ -139,7 +139,8 @@ def test_png_encode_roundtrip(bins, tmp_path, c):
 
 
 def test_jpeg_decode_matches_libjpeg(bins, tmp_path):
-    """baseline JPEG reader vs Pillow (libjpeg-turbo): IDCT / upsampling / colour rounding differ by a few LSB at most"""
+    """JPEG reader (sequential and progressive) vs Pillow (libjpeg-turbo): IDCT / upsampling / colour rounding differ by a
+    few LSB at most"""
     rng = np.random.default_rng(21)
     yy, xx = np.mgrid[0:75, 0:101]
     img = np.stack([np.sin(xx / 9.) * 80 + 128 + yy / 2, np.cos(yy / 7.) * 70 + 120 + xx / 3, ((xx * yy) % 200) + 20.], -1)
@@ -157,11 +158,24 @@ def test_jpeg_decode_matches_libjpeg(bins, tmp_path):
         ref = np.asarray(Image.open(p).convert("RGB")).astype(int)
         d = np.abs(got - ref)
         assert got.shape == ref.shape and d.max() <= 4 and d.mean() < 0.35 and (d > 2).mean() < 0.002, (name, d.max(), d.mean())
-    # progressive files are refused, not mis-decoded
-    p = str(tmp_path / "prog.jpg")
-    Image.fromarray(img).save(p, quality=90, progressive=True)
-    r = subprocess.run([os.path.join(bins, "png_tool"), "decode", p, str(tmp_path / "x.raw")], capture_output=True, text=True)
-    assert r.returncode != 0 and "progressive" in r.stderr
+    # progressive (spectral selection + successive approximation), with and without restart intervals / subsampling
+    big = np.asarray(Image.fromarray(img).resize((517, 389), Image.BICUBIC))
+    for name, arr, kw in [("p420", img, dict(quality=90, subsampling=2, progressive=True)), ("p444", img, dict(quality=97, subsampling=0, progressive=True)),
+                          ("pgray", img[..., 0], dict(quality=80, progressive=True)), ("pbig", big, dict(quality=85, progressive=True)),
+                          ("prst", big, dict(quality=85, progressive=True, restart_marker_blocks=5)),
+                          ("p422", big, dict(quality=70, subsampling=1, progressive=True)), ("opt", big, dict(quality=88, optimize=True))]:
+        p = str(tmp_path / (name + ".jpg"))
+        Image.fromarray(arr).save(p, **kw)
+        got = decode(bins, p, str(tmp_path)).astype(int)
+        ref = np.asarray(Image.open(p).convert("RGB")).astype(int)
+        d = np.abs(got - ref)
+        assert got.shape == ref.shape and d.max() <= 4 and d.mean() < 0.35 and (d > 2).mean() < 0.002, (name, d.max(), d.mean())
+    # a truncated file is an error, not a crash
+    data = open(p, "rb").read()
+    bad = str(tmp_path / "trunc.jpg")
+    open(bad, "wb").write(data[:200])
+    r = subprocess.run([os.path.join(bins, "png_tool"), "decode", bad, str(tmp_path / "x.raw")], capture_output=True, text=True)
+    assert r.returncode == 1 and "decode failed" in r.stderr
 
 
 def test_jpeg_encode_quality_100(bins, tmp_path):
