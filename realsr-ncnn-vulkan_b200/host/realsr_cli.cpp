@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>
+#include <new>
 #include <queue>
 #include <string>
 #include <thread>
@@ -273,8 +274,15 @@ int main(int argc, char** argv)
                     if (fread(magic, 1, 2, fp) != 2) magic[0] = magic[1] = 0;
                     fclose(fp);
                 }
-                const bool ok = (magic[0] == 0xFF && magic[1] == 0xD8) ? rsrhost::jpeg_decode_file(v.inpath, v.w, v.h, v.c, v.in, &why)
-                                                                        : rsrhost::png_decode_file(v.inpath, v.w, v.h, v.c, v.in, &why);
+                bool ok = false;
+                try {
+                    ok = (magic[0] == 0xFF && magic[1] == 0xD8) ? rsrhost::jpeg_decode_file(v.inpath, v.w, v.h, v.c, v.in, &why)
+                                                                : rsrhost::png_decode_file(v.inpath, v.w, v.h, v.c, v.in, &why);
+                    if (ok) v.out.resize((size_t)v.w * scale * v.h * scale * v.c);
+                } catch (const std::bad_alloc&) {  // a header announcing more pixels than the host can hold
+                    ok = false;
+                    why = "out of memory";
+                }
                 if (!ok) {
                     fprintf(stderr, "decode image %s failed\n", v.inpath.c_str());
                     if (verbose && !why.empty()) fprintf(stderr, "  (%s)\n", why.c_str());
@@ -286,7 +294,6 @@ int main(int argc, char** argv)
                     fprintf(stderr, "image %s has alpha channel ! %s will output %s\n", v.inpath.c_str(), v.inpath.c_str(), out2.c_str());
                     v.outpath = out2;
                 }
-                v.out.resize((size_t)v.w * scale * v.h * scale * v.c);
                 toproc.put(std::move(v));
             }
         });
