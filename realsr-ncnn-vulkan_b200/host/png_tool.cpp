@@ -1,6 +1,6 @@
 // png_tool.cpp -- exercises host/png_codec.h and host/jpeg_codec.h (by file extension) from the command line (used by tests/test_cpp_cli.py):
 //   png_tool decode in.png out.raw     -> prints "w h c", writes w*h*c bytes
-//   png_tool encode in.raw w h c out.png [zlib-level]
+//   png_tool encode in.raw w h c out.png [zlib-level [threads]]
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -25,15 +25,15 @@ int main(int argc, char** argv)
         printf("%d %d %d\n", w, h, c);
         return 0;
     }
-    if ((argc == 7 || argc == 8) && std::string(argv[1]) == "encode") {
+    if (argc >= 7 && argc <= 9 && std::string(argv[1]) == "encode") {
         const int w = atoi(argv[3]), h = atoi(argv[4]), c = atoi(argv[5]);
         std::vector<uint8_t> px((size_t)w * h * c);
         FILE* fp = fopen(argv[2], "rb");
         if (!fp || fread(px.data(), 1, px.size(), fp) != px.size()) return 2;
         fclose(fp);
         const std::string outp = argv[6];
-        if (outp.size() > 4 && outp.substr(outp.size() - 4) == ".jpg") return rsrhost::jpeg_encode_file(outp, px.data(), w, h, c, argc == 8 ? atoi(argv[7]) : 100) ? 0 : 1;
-        return rsrhost::png_encode_file(outp, px.data(), w, h, c, argc == 8 ? atoi(argv[7]) : 1) ? 0 : 1;
+        if (outp.size() > 4 && outp.substr(outp.size() - 4) == ".jpg") return rsrhost::jpeg_encode_file(outp, px.data(), w, h, c, argc >= 8 ? atoi(argv[7]) : 100) ? 0 : 1;
+        return rsrhost::png_encode_file(outp, px.data(), w, h, c, argc >= 8 ? atoi(argv[7]) : 1, argc >= 9 ? atoi(argv[8]) : 1) ? 0 : 1;
     }
     fprintf(stderr, "usage: png_tool decode in.png out.raw | png_tool encode in.raw w h c out.png [level]\n");
     return 64;

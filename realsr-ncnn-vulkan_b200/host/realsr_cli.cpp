@@ -316,6 +316,9 @@ int main(int argc, char** argv)
                 }
             });
     // ---- save stage (main.cpp:339-416) ----
+    // a 33-MP PNG costs ~1.4 core-seconds even in the fast mode: every save thread compresses its image in parallel row bands
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int png_threads = std::max(1, std::min(8, (hw > 0 ? hw : 8) / std::max(1, jobs_save)));
     for (int k = 0; k < jobs_save; k++)
         savers.emplace_back([&] {
             for (;;) {
@@ -323,7 +326,7 @@ int main(int argc, char** argv)
                 tosave.get(v);
                 if (v.id == END_ID) break;
                 const std::string ext = file_ext(v.outpath);
-                const bool ok = (ext == "png" || ext == "PNG") ? rsrhost::png_encode_file(v.outpath, v.out.data(), v.w * scale, v.h * scale, v.c)
+                const bool ok = (ext == "png" || ext == "PNG") ? rsrhost::png_encode_file(v.outpath, v.out.data(), v.w * scale, v.h * scale, v.c, 1, png_threads)
                                                                : rsrhost::jpeg_encode_file(v.outpath, v.out.data(), v.w * scale, v.h * scale, v.c, 100);
                 if (ok) {
                     if (verbose) fprintf(stderr, "%s -> %s done\n", v.inpath.c_str(), v.outpath.c_str());

@@ -21,7 +21,7 @@ def bins(tmp_path_factory):
     subprocess.run(["gcc", "-shared", "-fPIC", "-O2", "-o", os.path.join(d, "librealsr_b200.so"), os.path.join(ROOT, "tests", "stub", "stub_realsr.c")], check=True)
     subprocess.run(["g++", "-O2", "-std=c++11", "-Wall", "-Werror", "-o", os.path.join(d, "realsr-b200"), os.path.join(HOST, "realsr_cli.cpp"),
                     "-L" + d, "-lrealsr_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"], check=True)
-    subprocess.run(["g++", "-O2", "-std=c++11", "-Wall", "-Werror", "-o", os.path.join(d, "png_tool"), os.path.join(HOST, "png_tool.cpp"), "-lz"], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++11", "-Wall", "-Werror", "-o", os.path.join(d, "png_tool"), os.path.join(HOST, "png_tool.cpp"), "-lz", "-lpthread"], check=True)
     return d
 
 
@@ -135,7 +135,11 @@ def test_png_encode_roundtrip(bins, tmp_path, c):
         back = np.asarray(Image.open(png))
         assert back.shape == img.shape and np.array_equal(back, img), name
         assert np.array_equal(decode(bins, png, str(tmp_path)), img)
-    assert os.path.getsize(str(tmp_path / "smooth.png")) < smooth.size // 3  # the filter heuristic does compress gradients
+        # parallel row bands (independent raw deflate streams spliced into one zlib stream) and the adaptive-filter mode
+        for lvl, th in (("1", "3"), ("6", "1"), ("6", "4")):
+            subprocess.run([os.path.join(bins, "png_tool"), "encode", raw, "47", "61", str(c), png, lvl, th], check=True)
+            assert np.array_equal(np.asarray(Image.open(png)), img), (name, lvl, th)
+    assert os.path.getsize(str(tmp_path / "smooth.png")) < smooth.size // 3  # filters + deflate do compress gradients
 
 
 def test_jpeg_decode_matches_libjpeg(bins, tmp_path):
