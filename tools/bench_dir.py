@@ -73,10 +73,23 @@ def main():
     rc = cli.main(argv)
     t_e2e = time.time() - t0
     n_out = len(os.listdir(dout))
+    # (iii) the same through the C++ command line (own PNG codec: Paeth + Z_RLE in parallel row bands)
+    cpp = None
+    exe = os.path.join(ROOT, "realsr-ncnn-vulkan_b200", "realsr-b200")
+    if os.path.exists(exe):
+        import subprocess
+        dout2 = os.path.join(work, "out_cpp")
+        os.makedirs(dout2, exist_ok=True)
+        t0 = time.time()
+        r = subprocess.run([exe] + argv[:2] + ["-o", dout2] + argv[4:], capture_output=True, text=True)
+        t_cpp = time.time() - t0
+        cpp = {"seconds": t_cpp, "out_mp_s": out_mp / t_cpp, "rc": r.returncode, "files_written": len(os.listdir(dout2)), "jobs": argv[-1],
+               "codec": "host/png_codec.h"}
     print(json.dumps({"config": "configs[2]: %d x 1920x1080 PNG, models-DF2K, tile %d, %d GPU(s)" % (a.images, a.tile, a.gpus),
                       "proc_only": {"seconds": t_proc, "out_mp_s": out_mp / t_proc, "proc_threads_per_gpu": a.proc_threads},
                       "end_to_end": {"seconds": t_e2e, "out_mp_s": out_mp / t_e2e, "rc": rc, "files_written": n_out, "jobs": argv[-1],
-                                     "codec": "Pillow PNG"}}))
+                                     "codec": "Pillow PNG"},
+                      "end_to_end_cpp": cpp}))
     if not a.keep:
         shutil.rmtree(work, ignore_errors=True)
 
