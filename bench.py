@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="for runs under ncu: warm-up + the device-resident timed steps only "
+                    "(no e2e leg, no per-conv event pass, no CPU baseline), prints no bench line")
     ap.add_argument("--opts", default="", help="engine options for A/B runs, e.g. epilogue_split=1,merge_shapes=1 (default: none; "
                                                "recorded under config.engine_options)")
     args = ap.parse_args()
@@ -234,6 +236,12 @@ def main():
     dev_ms, wall_ms = timed(run_dev, args.steps)
     launches = eng.kernel_launches() - l0
     padded = eng.last_padded_pixels()
+    if args.profile:
+        sampler.stop_flag = True
+        sampler.join()
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "calls": W + args.steps, "launches_per_call": launches // max(1, args.steps), "ms_per_step": dev_ms / args.steps}))
+        return
     for _ in range(2):
         run_e2e()
     e2e_dev_ms, e2e_wall_ms = timed(run_e2e, args.steps)

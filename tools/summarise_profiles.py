@@ -17,8 +17,8 @@ for row in csv.DictReader(lines):
     tot[k] += v / 1e6 if u.startswith("n") else (v / 1e3 if u.startswith("u") else v)
     cnt[k] += 1
 T = sum(tot.values())
-summ = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -s 4236 -c 1412 --csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline",
-        "note": "the 4th process() call of the bench; ncu times are cold-cache and serialised (programmatic-dependent-launch overlap is lost "
+summ = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -s <3rd call> -c <one call> --csv python bench.py ... (tools/final_run.sh)",
+        "note": "one process() call of the bench after warm-up calls; ncu times are cold-cache and serialised (programmatic-dependent-launch overlap is lost "
                 "under the profiler, and the GPU is not power-capped between replays): compare SHARES with the live CUDA-event numbers, not absolutes",
         "total_ms": T, "launches": sum(cnt.values()),
         "kernels": [{"kernel": k, "launches": cnt[k], "total_ms": v, "share": v / T, "avg_us": v / cnt[k] * 1e3}
