@@ -1,4 +1,4 @@
-// png_tool.cpp -- exercises host/png_codec.h and host/jpeg_codec.h (by file extension) from the command line (used by tests/test_cpp_cli.py):
+// png_tool.cpp -- exercises host/png_codec.h, host/jpeg_codec.h and host/webp_codec.h (by file extension) from the command line (used by tests/test_cpp_cli.py):
 //   png_tool decode in.png out.raw     -> prints "w h c", writes w*h*c bytes
 //   png_tool encode in.raw w h c out.png [zlib-level [threads]]
 #include <stdio.h>
@@ -6,6 +6,7 @@
 
 #include "jpeg_codec.h"
 #include "png_codec.h"
+#include "webp_codec.h"
 
 int main(int argc, char** argv)
 {
@@ -15,7 +16,9 @@ int main(int argc, char** argv)
         std::string why;
         const std::string in = argv[2];
         const bool jpg = in.size() > 4 && (in.substr(in.size() - 4) == ".jpg" || in.substr(in.size() - 5) == ".jpeg");
-        if (!(jpg ? rsrhost::jpeg_decode_file(in, w, h, c, px, &why) : rsrhost::png_decode_file(in, w, h, c, px, &why))) {
+        const bool webp = in.size() > 5 && in.substr(in.size() - 5) == ".webp";
+        if (!(webp ? rsrhost::webp_decode_file(in, w, h, c, px, &why)
+                   : jpg ? rsrhost::jpeg_decode_file(in, w, h, c, px, &why) : rsrhost::png_decode_file(in, w, h, c, px, &why))) {
             fprintf(stderr, "decode failed: %s\n", why.c_str());
             return 1;
         }
@@ -32,6 +35,7 @@ int main(int argc, char** argv)
         if (!fp || fread(px.data(), 1, px.size(), fp) != px.size()) return 2;
         fclose(fp);
         const std::string outp = argv[6];
+        if (outp.size() > 5 && outp.substr(outp.size() - 5) == ".webp") return rsrhost::webp_encode_file(outp, px.data(), w, h, c) ? 0 : 1;
         if (outp.size() > 4 && outp.substr(outp.size() - 4) == ".jpg") return rsrhost::jpeg_encode_file(outp, px.data(), w, h, c, argc >= 8 ? atoi(argv[7]) : 100) ? 0 : 1;
         return rsrhost::png_encode_file(outp, px.data(), w, h, c, argc >= 8 ? atoi(argv[7]) : 1, argc >= 9 ? atoi(argv[8]) : 1) ? 0 : 1;
     }

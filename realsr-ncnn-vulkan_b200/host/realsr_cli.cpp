@@ -7,9 +7,9 @@
 // threads, jobs_proc[i] per GPU sharing that GPU's RealSR object -> queue of 8 -> save threads; sentinel shutdown).
 // Differences: `-g` takes CUDA ordinals and `-g -1` (ncnn CPU mode) is refused; one proc count is broadcast to all
 // GPUs (BASELINE configs[2] uses `-j 4:8:4` with 8 GPUs, which the reference itself rejects, main.cpp:560-564); auto
-// tile size is 400; codecs: PNG (host/png_codec.h on zlib) and JPEG (host/jpeg_codec.h: sequential + progressive reader,
-// baseline writer), both written for this repo -- the reference's stb / libwebp files are not copied; WebP goes through
-// the Python CLI (`python -m realsr_ncnn_vulkan_b200.cli`, Pillow).  Host plumbing only: every pixel goes through RealSR::process.
+// tile size is 400; codecs: PNG (host/png_codec.h on zlib), JPEG (host/jpeg_codec.h: sequential + progressive reader,
+// baseline writer) and lossless WebP (host/webp_codec.h), all written for this repo -- the reference's stb / libwebp files
+// are not copied; lossy (VP8) WebP inputs go through the Python CLI (`python -m realsr_ncnn_vulkan_b200.cli`, Pillow).  Host plumbing only: every pixel goes through RealSR::process.
 #include <dirent.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -29,21 +29,22 @@
 #include "jpeg_codec.h"
 #include "png_codec.h"
 #include "realsr.h"
+#include "webp_codec.h"
 
 static void print_usage()
 {
     fprintf(stderr, "Usage: realsr-b200 -i infile -o outfile [options]...\n\n");
     fprintf(stderr, "  -h                   show this help\n");
     fprintf(stderr, "  -v                   verbose output\n");
-    fprintf(stderr, "  -i input-path        input image path (jpg/png) or directory\n");
-    fprintf(stderr, "  -o output-path       output image path (jpg/png) or directory\n");
+    fprintf(stderr, "  -i input-path        input image path (jpg/png/webp) or directory\n");
+    fprintf(stderr, "  -o output-path       output image path (jpg/png/webp) or directory\n");
     fprintf(stderr, "  -s scale             upscale ratio (4, default=4)\n");
     fprintf(stderr, "  -t tile-size         tile size (>=32/0=auto, default=0) can be 0,0,0 for multi-gpu\n");
     fprintf(stderr, "  -m model-path        realsr model path (default=models-DF2K_JPEG)\n");
     fprintf(stderr, "  -g gpu-id            gpu device to use (default=0) can be 0,1,2 for multi-gpu\n");
     fprintf(stderr, "  -j load:proc:save    thread count for load/proc/save (default=1:2:2) can be 1:2,2,2:2 for multi-gpu\n");
     fprintf(stderr, "  -x                   enable tta mode\n");
-    fprintf(stderr, "  -f format            output image format (jpg/png, default=ext/png)\n");
+    fprintf(stderr, "  -f format            output image format (jpg/png/webp, default=ext/png)\n");
 }
 
 static bool is_dir(const std::string& p)
@@ -192,10 +193,6 @@ int main(int argc, char** argv)
         fprintf(stderr, "invalid format argument\n");
         return -1;
     }
-    if (format == "webp") {
-        fprintf(stderr, "format webp is not built into the C++ command line (jpg/png only); use python -m realsr_ncnn_vulkan_b200.cli\n");
-        return -1;
-    }
     // collect input and output file paths (main.cpp:606-659)
     std::vector<std::string> input_files, output_files;
     if (is_dir(inputpath) && is_dir(outputpath)) {
@@ -269,14 +266,15 @@ int main(int argc, char** argv)
                 v.outpath = output_files[i];
                 // by content, like the reference's decoders: PNG signature, else JPEG
                 std::string why;
-                unsigned char magic[2] = {0, 0};
+                unsigned char magic[4] = {0, 0, 0, 0};
                 if (FILE* fp = fopen(v.inpath.c_str(), "rb")) {
-                    if (fread(magic, 1, 2, fp) != 2) magic[0] = magic[1] = 0;
+                    if (fread(magic, 1, 4, fp) != 4) magic[0] = magic[1] = 0;
                     fclose(fp);
                 }
                 bool ok = false;
                 try {
                     ok = (magic[0] == 0xFF && magic[1] == 0xD8) ? rsrhost::jpeg_decode_file(v.inpath, v.w, v.h, v.c, v.in, &why)
+                         : !memcmp(magic, "RIFF", 4)            ? rsrhost::webp_decode_file(v.inpath, v.w, v.h, v.c, v.in, &why)
                                                                 : rsrhost::png_decode_file(v.inpath, v.w, v.h, v.c, v.in, &why);
                     if (ok) v.out.resize((size_t)v.w * scale * v.h * scale * v.c);
                 } catch (const std::bad_alloc&) {  // a header announcing more pixels than the host can hold
@@ -326,8 +324,9 @@ int main(int argc, char** argv)
                 tosave.get(v);
                 if (v.id == END_ID) break;
                 const std::string ext = file_ext(v.outpath);
-                const bool ok = (ext == "png" || ext == "PNG") ? rsrhost::png_encode_file(v.outpath, v.out.data(), v.w * scale, v.h * scale, v.c, 1, png_threads)
-                                                               : rsrhost::jpeg_encode_file(v.outpath, v.out.data(), v.w * scale, v.h * scale, v.c, 100);
+                const bool ok = (ext == "png" || ext == "PNG")     ? rsrhost::png_encode_file(v.outpath, v.out.data(), v.w * scale, v.h * scale, v.c, 1, png_threads)
+                                : (ext == "webp" || ext == "WEBP") ? rsrhost::webp_encode_file(v.outpath, v.out.data(), v.w * scale, v.h * scale, v.c)
+                                                                   : rsrhost::jpeg_encode_file(v.outpath, v.out.data(), v.w * scale, v.h * scale, v.c, 100);
                 if (ok) {
                     if (verbose) fprintf(stderr, "%s -> %s done\n", v.inpath.c_str(), v.outpath.c_str());
                 } else {

@@ -197,6 +197,38 @@ def test_jpeg_encode_quality_100(bins, tmp_path):
         assert back.shape == img.shape and d.max() <= 4 and d.mean() < 0.8, (name, d.max(), d.mean())
 
 
+def test_webp_lossless_reader_and_writer(bins, tmp_path):
+    """VP8L: files written by libwebp (Pillow) at several effort levels -- palette / pixel packing, colour cache, LZ77,
+    all transforms -- decode bit-exactly; files written here are decoded bit-exactly by libwebp; lossy files are refused"""
+    rng = np.random.default_rng(31)
+    yy, xx = np.mgrid[0:75, 0:101]
+    img = np.stack([np.sin(xx / 9.) * 80 + 128 + yy / 2, np.cos(yy / 7.) * 70 + 120 + xx / 3, ((xx * yy) % 200) + 20.], -1)
+    img = np.clip(img + rng.normal(0, 3, img.shape), 0, 255).astype(np.uint8)
+    big = np.asarray(Image.fromarray(img).resize((517, 389), Image.BICUBIC))
+    flat = np.zeros((60, 80, 3), np.uint8)
+    flat[10:40, 20:60] = (200, 30, 40)
+    cases = {"smooth": img, "big": big, "flat": flat, "pal12": np.asarray(Image.fromarray(big).quantize(12).convert("RGB")),
+             "bilevel": (rng.integers(0, 2, (40, 50, 1)) * 255).astype(np.uint8).repeat(3, 2),
+             "rgba": np.dstack([img, (xx * 2 % 256).astype(np.uint8)]), "noise": rng.integers(0, 256, (64, 64, 3), dtype=np.uint8),
+             "one": img[:1, :1], "row": img[:1], "col": img[:, :1], "const": np.full((33, 17, 3), 77, np.uint8)}
+    for name, arr in cases.items():
+        arr = np.ascontiguousarray(arr)
+        mode = "RGBA" if arr.shape[2] == 4 else "RGB"
+        for method in (0, 3, 6):
+            p = str(tmp_path / ("%s_%d.webp" % (name, method)))
+            Image.fromarray(arr).save(p, lossless=True, method=method)
+            assert np.array_equal(decode(bins, p, str(tmp_path)), np.asarray(Image.open(p).convert(mode))), (name, method)
+        raw, out = str(tmp_path / "e.raw"), str(tmp_path / (name + "_own.webp"))
+        arr.tofile(raw)
+        subprocess.run([os.path.join(bins, "png_tool"), "encode", raw, str(arr.shape[1]), str(arr.shape[0]), str(arr.shape[2]), out], check=True)
+        assert np.array_equal(np.asarray(Image.open(out).convert(mode)), arr), name
+        assert np.array_equal(decode(bins, out, str(tmp_path)), arr), name
+    p = str(tmp_path / "lossy.webp")
+    Image.fromarray(img).save(p, quality=80)
+    r = subprocess.run([os.path.join(bins, "png_tool"), "decode", p, str(tmp_path / "x.raw")], capture_output=True, text=True)
+    assert r.returncode == 1 and "lossy" in r.stderr
+
+
 def cli(bins, *args):
     return subprocess.run([os.path.join(bins, "realsr-b200")] + list(args), capture_output=True, text=True)
 
@@ -218,7 +250,6 @@ def test_cli_argument_validation(bins, tmp_path):
     assert "must be either file or directory at the same time" in cli(bins, "-i", img, "-o", str(tmp_path)).stderr
     assert "unknown model dir type" in cli(bins, "-i", img, "-o", out, "-m", "models-other").stderr
     assert "no CPU mode" in cli(bins, "-i", img, "-o", out, "-g", "-1", "-m", "models-DF2K").stderr
-    assert "jpg/png only" in cli(bins, "-i", img, "-o", str(tmp_path / "o.webp")).stderr
     r = cli(bins, "-i", img, "-o", out, "-m", "missing/models-DF2K")
     assert r.returncode != 0 and "load failed" in r.stderr
 
@@ -257,6 +288,12 @@ def test_cli_pipeline_directory_mode(bins, tmp_path):
     up = np.repeat(np.repeat(np.asarray(Image.open(str(dj / "a.jpg")).convert("RGB")), 4, 0), 4, 1).astype(int)
     assert np.abs(np.asarray(Image.open(str(djo / "a.jpg")).convert("RGB")).astype(int) - up).max() <= 6
     assert np.array_equal(np.asarray(Image.open(str(djo / "b.jpg.png"))), np.repeat(np.repeat(imgs["img03.png"], 4, 0), 4, 1))
+    # webp in (lossless), webp out
+    wj = str(tmp_path / "w.webp")
+    Image.fromarray(imgs["img05.png"]).save(wj, lossless=True)
+    r = cli(bins, "-i", wj, "-o", str(tmp_path / "w4.webp"), "-m", "models-DF2K")
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.asarray(Image.open(str(tmp_path / "w4.webp")).convert("RGB")), np.repeat(np.repeat(imgs["img05.png"], 4, 0), 4, 1))
     # file -> file
     one = str(tmp_path / "one.png")
     r = cli(bins, "-i", str(din / "img05.png"), "-o", one, "-m", "x/models-DF2K_JPEG")
