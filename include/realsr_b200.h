@@ -98,7 +98,10 @@ RSR_API long long rsr_last_padded_pixels(const rsr_handle* h);
  * "residual_fp16" (1 default / 0: fp32 copy of the RDB input for the RDB-level residual), "time_convs" (CUDA events
  * around every conv launch), "debug_mask"
  * (timing experiments only, results become garbage: 1 = skip MMAs, 2 = skip activation loads, 4 = skip weight loads,
- * 8 = skip epilogue loads/stores). */
+ * 8 = skip epilogue loads/stores).
+ * Opt-in kernel / scheduling variants, default 0, bit-identical results by construction but not yet run on hardware (see
+ * DESIGN.md section 6, csrc/conv_tc2x.cu): "epilogue_split", "merge_shapes", "serpentine"; "conv_impl" 3 = 32-channel
+ * K-blocks.  Unknown keys and out-of-range values return RSR_ERR_GENERIC. */
 RSR_API int rsr_set_option(rsr_handle* h, const char* key, long long value);
 
 /* Test hook: runs ONE 3x3 convolution of the loaded model (index in file order, >= 1) on the tensor-core kernel.
