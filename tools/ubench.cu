@@ -410,6 +410,12 @@ int main()
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, 0));
     printf("%s, %d SMs, clock %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
+    // CTA-pair MMA issue rates, incl. the shapes the conv kernel actually uses (N=96) and a candidate (N=192)
+    run_mma2<64>();
+    run_mma2<96>();
+    run_mma2<128>();
+    run_mma2<192>();
+    run_mma2<256>();
     run_box(10, 2);
     run_box(10, 3);
     run_box(10, 4);
