@@ -16,3 +16,4 @@ timeout 120 python tools/ab_option.py merge_shapes 0 1 200 2>&1 | tail -3; mark 
 timeout 120 python tools/ab_option.py conv_impl 2 3 2>&1 | tail -3; mark ab-kblock32
 for i in 2 4 5; do RSR_IMPL=3 RSR_DBG_RDB=1 timeout 60 python tools/ts_probe.py $i > gpurun_out/ts_k32_$i.log 2>&1; tail -3 gpurun_out/ts_k32_$i.log; done; mark ts-k32
 RSR_OPTS=serpentine=1,epilogue_split=1 timeout 200 python tools/batch_sweep.py 2>&1 | tail -20; mark batch-sweep-serpentine
+timeout 120 tools/ubench > gpurun_out/r2_ubench.txt 2>&1; head -8 gpurun_out/r2_ubench.txt; mark ubench
