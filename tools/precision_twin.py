@@ -1,0 +1,88 @@
+#!/usr/bin/env python3
+"""CPU model of the engine's precision choices (torch, no GPU): where do the LSBs against the reference come from, and what
+would each candidate change buy?  The network is evaluated on single-tile goldens with activations rounded to fp16 exactly
+where the engine stores fp16 (fp32 accumulation everywhere), then with one choice changed at a time:
+    engine      : what csrc/ does by default (fp32 Conv_0, fp16 dense planes, fp16 x0 for the dense-block residual, fp32
+                  RRDB skip stream, fp16 tail activations)
+    res32       : residual_fp16 = 0 (dense-block residual from an fp32 copy)
+    tail32      : + the four tail convs (after the trunk) read and write fp32 activations ("exact tail")
+    hr32 / v2hr32 / trunk32 : engine precision, but only the HR conv's output / the last two tail tensors / the trunk output exact
+    body32      : fp16 only in the tail
+    all32       : no rounding at all (the reference itself, up to summation order)
+Prints max |diff|, share of bytes off by one and bytes off by more than one against the reference golden.
+Usage: precision_twin.py [golden names...]   (default: the single-tile goldens)"""
+import os, sys
+import numpy as np
+import torch
+import torch.nn.functional as F
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from common import golden, manifest, read_convs, diff_stats
+
+torch.set_num_threads(8)
+H16 = lambda t: t.half().float()
+ID = lambda t: t
+
+
+def net(x, convs, q_body, q_x0res, q_tail, nb=23, q_tails=None):
+    """x: [1,3,H,W] fp32 in 0..1.  q_*: rounding applied where the engine stores fp16."""
+    def conv(i, t):
+        c = convs[i]
+        y = F.conv2d(t, torch.from_numpy(c["w"].astype(np.float32)), torch.from_numpy(c["b"].copy()), padding=1)
+        return F.leaky_relu(y, 0.2) if c["act"] == 2 else y
+    fea = conv(0, x)                      # fp32 (Conv_0 on CUDA cores)
+    r32 = fea
+    t32 = fea
+    x0 = q_body(fea)
+    idx = 1
+    for rrdb in range(nb):
+        for rdb in range(3):
+            feats = [x0]
+            for k in range(4):
+                feats.append(q_body(conv(idx + k, torch.cat(feats, 1))))
+            x5 = conv(idx + 4, torch.cat(feats, 1))
+            t = 0.2 * x5 + (q_x0res(t32) if q_x0res is not ID else t32)
+            if rdb == 2:
+                t = 0.2 * t + r32
+                r32 = t
+            t32 = t
+            x0 = q_body(t)
+            idx += 5
+    qt = q_tails or (q_tail,) * 4         # per tensor: trunk, v1 (2x), v2 (4x), hr (4x, the last conv's input)
+    trunk = qt[0](conv(idx, x0) + fea)
+    u1 = F.interpolate(trunk, scale_factor=2, mode="nearest")
+    v1 = qt[1](conv(idx + 1, u1))
+    u2 = F.interpolate(v1, scale_factor=2, mode="nearest")
+    v2 = qt[2](conv(idx + 2, u2))
+    hr = qt[3](conv(idx + 3, v2))
+    return conv(idx + 4, hr)
+
+
+def run(name, mode):
+    case = [c for c in manifest()["cases"] if c["name"] == name][0]
+    img, gold = golden(name)
+    img = img[..., :3]
+    h, w, _ = img.shape
+    assert h <= case["tilesize"] and w <= case["tilesize"], "single-tile goldens only"
+    convs = read_convs(case["model"])
+    P = 10
+    x = torch.from_numpy(img.astype(np.float32)).permute(2, 0, 1)[None] * (1 / 255.0)
+    x = F.pad(x, (P, P, P, P), mode="reflect")
+    q = dict(engine=(H16, H16, H16), res32=(H16, ID, H16), tail32=(H16, ID, ID), body32=(ID, ID, H16), all32=(ID, ID, ID),
+             hr32=(H16, H16, H16), v2hr32=(H16, H16, H16), trunk32=(H16, H16, H16))[mode]
+    # single tail tensors kept exact (engine precision elsewhere): which hand-off carries the error?
+    q_tails = dict(hr32=(H16, H16, H16, ID), v2hr32=(H16, H16, ID, ID), trunk32=(ID, H16, H16, H16)).get(mode)
+    with torch.no_grad():
+        y = net(x, convs, *q, q_tails=q_tails)[0, :, 4 * P:4 * P + 4 * h, 4 * P:4 * P + 4 * w]
+    out = torch.clamp((y * 255.0 + 0.5).to(torch.int32), 0, 255).permute(1, 2, 0).numpy().astype(np.uint8)  # (int) truncation like the reference
+    return diff_stats(out, gold[..., :3])
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or ["noise_40x36_jpeg_t200", "readme0_crop64_df2k_t200", "natural_28x20_df2k_tta"]
+    for name in names:
+        if "tta" in name:
+            continue  # TTA goldens average 8 passes: not modelled here
+        for mode in ("engine", "res32", "tail32", "hr32", "v2hr32", "trunk32", "body32", "all32"):
+            s = run(name, mode)
+            print("%-28s %-7s max %d  off-by-one %.3f %%  >1: %d of %d" % (name, mode, s["max"], 100 * s["frac_diff"], s["n_gt1"], s["n"]), flush=True)
