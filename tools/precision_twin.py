@@ -8,6 +8,7 @@ where the engine stores fp16 (fp32 accumulation everywhere), then with one choic
     tail32      : + the four tail convs (after the trunk) read and write fp32 activations ("exact tail")
     subpix      : engine precision, but the two "nearest x2 + conv" pairs collapsed into four 2x2 sub-pixel convs on the low-res
                   grid with pre-summed fp16 weights (2.25x fewer MACs for those two convs, no upsampled tensors)
+    wino        : engine precision, every 3x3 conv as Winograd F(2x2,3x3) with fp16-rounded transformed operands (2.25x fewer MACs)
     hr32 / v2hr32 / trunk32 : engine precision, but only the HR conv's output / the last two tail tensors / the trunk output exact
     body32      : fp16 only in the tail
     all32       : no rounding at all (the reference itself, up to summation order)
@@ -45,10 +46,33 @@ def upconv_collapsed(t, c):
     return F.leaky_relu(out, 0.2) if c["act"] == 2 else out
 
 
-def net(x, convs, q_body, q_x0res, q_tail, nb=23, q_tails=None, collapse=False):
+def conv_winograd(t, c):
+    """Winograd F(2x2, 3x3) with the operand rounding a tensor-core implementation would have: U = G g G^T and V = B^T d B are
+    formed in fp32 from the fp16 weights / activations and rounded to fp16 (the MMA operands), the 16 channel contractions
+    accumulate in fp32, the output transform is fp32."""
+    w = torch.from_numpy(c["w"].astype(np.float32))
+    b = torch.from_numpy(c["b"].copy())
+    G = torch.tensor([[1, 0, 0], [.5, .5, .5], [.5, -.5, .5], [0, 0, 1]], dtype=torch.float32)
+    Bt = torch.tensor([[1, 0, -1, 0], [0, 1, 1, 0], [0, -1, 1, 0], [0, 1, 0, -1]], dtype=torch.float32)
+    At = torch.tensor([[1, 1, 1, 0], [0, 1, -1, -1]], dtype=torch.float32)
+    U = torch.einsum("ij,ocjk,lk->ocil", G, w, G).half().float()           # [O, C, 4, 4]
+    _, C, H, W = t.shape
+    Hp, Wp = (H + 1) // 2 * 2, (W + 1) // 2 * 2
+    tp = F.pad(t, (1, 1 + Wp - W, 1, 1 + Hp - H))
+    tiles = tp.unfold(2, 4, 2).unfold(3, 4, 2)                                # [1, C, Hp/2, Wp/2, 4, 4]
+    V = torch.einsum("ij,nchwjk,lk->nchwil", Bt, tiles, Bt).half().float()
+    M = torch.einsum("ocil,nchwil->nohwil", U, V)
+    Y = torch.einsum("ij,nohwjk,lk->nohwil", At, M, At)                       # [1, O, Hp/2, Wp/2, 2, 2]
+    y = Y.permute(0, 1, 2, 4, 3, 5).reshape(1, w.shape[0], Hp, Wp)[:, :, :H, :W] + b.view(1, -1, 1, 1)
+    return F.leaky_relu(y, 0.2) if c["act"] == 2 else y
+
+
+def net(x, convs, q_body, q_x0res, q_tail, nb=23, q_tails=None, collapse=False, wino=False):
     """x: [1,3,H,W] fp32 in 0..1.  q_*: rounding applied where the engine stores fp16."""
     def conv(i, t):
         c = convs[i]
+        if wino and i > 0:
+            return conv_winograd(t, c)
         y = F.conv2d(t, torch.from_numpy(c["w"].astype(np.float32)), torch.from_numpy(c["b"].copy()), padding=1)
         return F.leaky_relu(y, 0.2) if c["act"] == 2 else y
     fea = conv(0, x)                      # fp32 (Conv_0 on CUDA cores)
@@ -94,11 +118,11 @@ def run(name, mode):
     x = torch.from_numpy(img.astype(np.float32)).permute(2, 0, 1)[None] * (1 / 255.0)
     x = F.pad(x, (P, P, P, P), mode="reflect")
     q = dict(engine=(H16, H16, H16), res32=(H16, ID, H16), tail32=(H16, ID, ID), body32=(ID, ID, H16), all32=(ID, ID, ID),
-             hr32=(H16, H16, H16), v2hr32=(H16, H16, H16), trunk32=(H16, H16, H16), subpix=(H16, H16, H16))[mode]
+             hr32=(H16, H16, H16), v2hr32=(H16, H16, H16), trunk32=(H16, H16, H16), subpix=(H16, H16, H16), wino=(H16, H16, H16))[mode]
     # single tail tensors kept exact (engine precision elsewhere): which hand-off carries the error?
     q_tails = dict(hr32=(H16, H16, H16, ID), v2hr32=(H16, H16, ID, ID), trunk32=(ID, H16, H16, H16)).get(mode)
     with torch.no_grad():
-        y = net(x, convs, *q, q_tails=q_tails, collapse=(mode == "subpix"))[0, :, 4 * P:4 * P + 4 * h, 4 * P:4 * P + 4 * w]
+        y = net(x, convs, *q, q_tails=q_tails, collapse=(mode == "subpix"), wino=(mode == "wino"))[0, :, 4 * P:4 * P + 4 * h, 4 * P:4 * P + 4 * w]
     out = torch.clamp((y * 255.0 + 0.5).to(torch.int32), 0, 255).permute(1, 2, 0).numpy().astype(np.uint8)  # (int) truncation like the reference
     return diff_stats(out, gold[..., :3])
 
@@ -108,6 +132,6 @@ if __name__ == "__main__":
     for name in names:
         if "tta" in name:
             continue  # TTA goldens average 8 passes: not modelled here
-        for mode in ("engine", "res32", "tail32", "hr32", "v2hr32", "trunk32", "subpix", "body32", "all32"):
+        for mode in ("engine", "res32", "tail32", "hr32", "v2hr32", "trunk32", "subpix", "wino", "body32", "all32"):
             s = run(name, mode)
             print("%-28s %-7s max %d  off-by-one %.3f %%  >1: %d of %d" % (name, mode, s["max"], 100 * s["frac_diff"], s["n_gt1"], s["n"]), flush=True)
