@@ -19,8 +19,9 @@ Same flag surface, validation messages and file naming as the reference; same 3-
 queue of 8 -> proc threads, `jobs_proc[i]` per GPU sharing one RealSR object -> bounded queue of 8 -> save threads,
 main.cpp:130-177,:311-416,:802-866).  Differences: `-g` takes CUDA ordinals (`-g -1`, the ncnn CPU mode, is refused);
 a single proc count is broadcast to all GPUs (the reference rejects `-j 4:8:4` with 8 GPUs, main.cpp:560-564; BASELINE
-config 2 uses exactly that); auto tile size is 400 (any B200 has the memory the reference's heuristic maps to its largest
-tile, main.cpp:760-774 -- pass -t 200 to reproduce what the reference picks).  Codecs: Pillow (the reference vendors
+config 2 uses exactly that).  Auto tile size (-t 0) is 200: what the reference's heuristic picks on any GPU with more than
+1.9 GB (main.cpp:753-774) -- tile geometry is part of the numerical contract, so default flags give the reference's image;
+pass -t 400 for the larger tiles BASELINE config 1 names.  Codecs: Pillow (the reference vendors
 stb_image / libwebp, main.cpp:243-288,:383-412); RGB and RGBA, grayscale is expanded to RGB like stbi_load(..., 3).
 This file is host plumbing only: every pixel goes through RealSR.process (the C ABI)."""
 import getopt
@@ -170,7 +171,7 @@ def main(argv=None):
         if e.load(param, binf):
             sys.stderr.write("load failed: %s\n" % e.last_error())
             return -1
-        e.scale, e.tilesize, e.prepadding = scale, (t if t else 400), prepadding
+        e.scale, e.tilesize, e.prepadding = scale, (t if t else 200), prepadding
         engines.append(e)
 
     from PIL import Image
@@ -194,10 +195,10 @@ def main(argv=None):
             if item is END:
                 return
             i, img = item
-            out = np.empty((img.shape[0] * scale, img.shape[1] * scale, img.shape[2]), dtype=np.uint8)
-            try:
+            try:  # any failure marks the image failed and keeps the worker alive (a dead worker would wedge the queues)
+                out = np.empty((img.shape[0] * scale, img.shape[1] * scale, img.shape[2]), dtype=np.uint8)
                 rc = engine.process(img, out)
-            except RealSRError as ex:
+            except Exception as ex:
                 rc = -1
                 sys.stderr.write(str(ex) + "\n")
             if rc:
@@ -248,7 +249,7 @@ def main(argv=None):
         tosave.put(END)
     for t in savers:
         t.join()
-    return 0
+    return 0  # like the reference (main.cpp:866-879): failures are reported per image on stderr, the exit status stays 0
 
 
 if __name__ == "__main__":

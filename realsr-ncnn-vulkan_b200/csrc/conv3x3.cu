@@ -1,0 +1,633 @@
+// conv3x3.cu -- the 3x3 stride-1 pad-1 convolution of the RRDB net (reference arithmetic: ncnn layer/convolution.cpp:133-204,
+// activation fused_activation.h:31-36) as an implicit GEMM on B200 CTA PAIRS: tcgen05.mma cta_group::2, TMA-staged
+// NHWC boxes, accumulators in TMEM, everything that follows the conv in the graph (bias, LeakyReLU, Concat slice, Eltwise /
+// BinaryOp residuals, post-processing) fused into the epilogue.  This is the only tensor-core kernel of the engine.
+//
+// GEMM view: M = pixels, N = Cout (x taps, see below), K = 9 * Cin; fp16 x fp16 -> fp32.
+//   * Work tile = 16 rows x 30 columns of output pixels, owned by a cluster of 2 CTAs; CTA r computes rows 8r..8r+7 as two
+//     M-tiles of 128 "positions" (4 rows x pitch 32).  One cta_group::2 MMA (M = 256) covers one M-tile in each CTA.
+//   * A operand: per K-block (KB = 64 or 32 input channels) one haloed TMA box {KB ch, 32 px, 10 rows} (out-of-bounds =
+//     zero fill = the conv's padding).  With a fixed pitch of 32 px the A rows of tap (ky,kx) for 128 consecutive positions
+//     are the 128 consecutive smem rows starting at q + 32*ky + kx: row-shifted UMMA descriptors instead of im2col
+//     (SWIZZLE_128B/64B is a function of the absolute smem address, so any 128-B / 64-B aligned start works).
+//   * Horizontal tap grouping keeps the MMAs wide (an MMA re-reads its 4 KB A tile from smem, so narrow N is feed-bound,
+//     tools/ubench.cu): Cout=32 stacks the three kx taps of a kernel row along N (one N=96 MMA instead of three N=32);
+//     Cout=64 stacks kx=0,1 (N=128) and runs kx=2 as N=64 with the A window shifted by 2; Cout=3 (padded 16): N=64.
+//     Column group g of position q then holds tap (ky,g)'s contribution to the output at q-g; the 32 lanes of an epilogue
+//     warp are 32 consecutive positions of one tile row, so the epilogue fetches it with __shfl_down.
+//   * B operand: each CTA keeps ITS half of the conv's weights resident in smem for the whole launch (B is split N/2 + N/2
+//     between the two CTAs of a pair), fetched once by TMA before the grid dependency is resolved.
+//   * Warp roles (12 warps): warp 0 A producer (TMA), warp 1 MMA issuer (leader CTA), warp 2 weight fetch, warps 4..11
+//     epilogue in two groups of four that alternate work tiles (one per accumulator set).  setmaxnreg moves registers
+//     from the control warpgroup to the epilogue warpgroups.
+//   * Early accumulator hand-back (Cout=32 and the Cout=64 bias/activation convs): an epilogue group first pulls BOTH
+//     M-tiles of its set into registers (taps combined), returns the set to the MMA issuer, and only then does
+//     bias / activation / pack / store -- per-tile timestamps showed the chain "MMAs done -> whole epilogue -> hand-back"
+//     bounding the Cout=32 convs at 2.6 k clk per tile where their MMAs need 1.2 k.
+//   * The MMA issuer's loop carries no divisions, no tile geometry and no 64-bit descriptor arithmetic: stage index and
+//     barrier parities are counters, descriptors are {lo32 = base + immediate, hi32 = constant}.
+//   * Merged multi-shape launches: one launch per layer covers up to four same-shape tile groups (ConvArgs::grp), so a frame
+//     pays the per-launch fill/drain once per layer instead of once per layer and shape.
+// Synchronisation: "full" barriers live in the leader CTA and collect the TMA bytes of both CTAs (cp.async.bulk.tensor
+// .cta_group::2 signalling a shared::cluster mbarrier); "stage free" and "accumulators ready" are signalled in both CTAs at
+// once by tcgen05.commit ... multicast::cluster; the peer's epilogue warps hand an accumulator set back with a remote
+// (CTA-scope release) mbarrier.arrive.  Programmatic dependent launch overlaps the prologue with the previous conv's tail.
+#include <stdlib.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace rsr {
+
+namespace {
+
+constexpr int P = CONV_P;
+constexpr int BW = P - 2;
+constexpr int BH = 8;                         // output rows per CTA
+constexpr int BAND = 2 * BH;                  // output rows per CTA pair
+constexpr int MT = BH * P / 128;              // 2 M-tiles per CTA
+constexpr int NA_MAX = 8;                     // A stages (run-time count: as many as fit next to the resident weights)
+__host__ __device__ constexpr int na_max(int kb) { return kb == 64 ? 4 : 8; }
+__host__ __device__ constexpr int a_bytes(int kb) { return (BH + 2) * P * kb * 2; }   // 40 KB / 20 KB
+__host__ __device__ constexpr int a_slack(int kb) { return kb == 64 ? 1024 : 512; }    // zeroed rows behind the box (kx taps of the last positions)
+__host__ __device__ constexpr int a_stage(int kb) { return a_bytes(kb) + a_slack(kb); }
+constexpr int NEPI = 8;                       // epilogue warps
+constexpr int EPI_WARP0 = 4;                  // first epilogue warp: warps 0..3 are the control warpgroup
+constexpr int NTHREADS = (EPI_WARP0 + NEPI) * 32;
+constexpr int STAGE_BYTES = 32 * 20 * 4;
+constexpr int DCOLS = 128;                    // TMEM columns per M-tile
+constexpr int ACC_COLS = MT * DCOLS;          // 256 per accumulator set
+constexpr int TMEM_COLS = 2 * ACC_COLS;
+constexpr int SMEM_MAX = 227 * 1024 - 1024;   // dynamic part; the kernel also has ~300 B of static shared memory
+constexpr int SMEM_FIXED = 1024 /*align*/ + NEPI * STAGE_BYTES + 256 /*barriers*/;
+constexpr int REGS_CTRL = 64, REGS_EPI = 216; // setmaxnreg: 128 x 64 + 256 x 216 <= 64 K registers
+
+// this CTA's half of the weights of one (64-channel plane, ky): Cout=64 -> pair half (64 rows) + single half (32 rows);
+// Cout<=32 -> triple half (48 rows, padded to 64); Cout<=16 -> 32 rows.  A 32-channel K-block holds half of each row.
+__host__ __device__ constexpr int w_bytes_per_ky(int nreal, int kb) { return (nreal == 64 ? 12288 : (nreal == 32 ? 6144 : 4096)) * kb / 64; }
+
+struct Bars {
+    uint64_t a_full[NA_MAX], a_empty[NA_MAX];
+    uint64_t w_full;
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_ptr;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b)
+{
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// tcgen05.mma cta_group::2 with the descriptors given as {lo32, hi32} halves and an issue predicate inside the asm block: the
+// surrounding loop has no lane-dependent control flow at all, only the instruction itself is predicated on the elected lane
+__device__ __forceinline__ void umma2_issue(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t issue)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_if(uint64_t* bar, uint16_t mask, uint32_t issue)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "h"(mask), "r"(issue)
+        : "memory");
+}
+
+// Where work tile `tt` lives: image b of its group, band by, column tile tx, the group's image size, pixel offset and maps.
+struct TileGeo {
+    int b, by, tx, H, W, desc0, g;
+    size_t pxoff, aux;
+};
+__device__ __forceinline__ TileGeo decode_tile(const ConvArgs& a, const int tt, const int tiles_per_img, const int tiles_x)
+{
+    TileGeo r;
+    if (a.ngroups > 0) {
+        int g = 0;
+#pragma unroll
+        for (int k = 1; k < 4; k++)
+            if (k < a.ngroups && tt >= a.grp[k].tile_start) g = k;
+        // explicit selects: a dynamically indexed kernel parameter would be copied to local memory
+        const int H = g == 0 ? a.grp[0].H : g == 1 ? a.grp[1].H : g == 2 ? a.grp[2].H : a.grp[3].H;
+        const int W = g == 0 ? a.grp[0].W : g == 1 ? a.grp[1].W : g == 2 ? a.grp[2].W : a.grp[3].W;
+        const int tx_n = g == 0 ? a.grp[0].tiles_x : g == 1 ? a.grp[1].tiles_x : g == 2 ? a.grp[2].tiles_x : a.grp[3].tiles_x;
+        const int tpi = g == 0 ? a.grp[0].tiles_per_img : g == 1 ? a.grp[1].tiles_per_img : g == 2 ? a.grp[2].tiles_per_img : a.grp[3].tiles_per_img;
+        const int t0 = g == 0 ? a.grp[0].tile_start : g == 1 ? a.grp[1].tile_start : g == 2 ? a.grp[2].tile_start : a.grp[3].tile_start;
+        r.desc0 = g == 0 ? a.grp[0].desc0 : g == 1 ? a.grp[1].desc0 : g == 2 ? a.grp[2].desc0 : a.grp[3].desc0;
+        r.pxoff = (size_t)(g == 0 ? a.grp[0].px_off : g == 1 ? a.grp[1].px_off : g == 2 ? a.grp[2].px_off : a.grp[3].px_off);
+        r.aux = (size_t)(g == 0 ? a.grp[0].aux_off : g == 1 ? a.grp[1].aux_off : g == 2 ? a.grp[2].aux_off : a.grp[3].aux_off);
+        const int lt = tt - t0;
+        r.b = lt / tpi;
+        const int rem = lt - r.b * tpi;
+        r.by = rem / tx_n;
+        r.tx = rem - r.by * tx_n;
+        r.H = H; r.W = W; r.g = g;
+    } else {
+        r.b = tt / tiles_per_img;
+        const int rem = tt - r.b * tiles_per_img;
+        r.by = rem / tiles_x;
+        r.tx = rem - r.by * tiles_x;
+        r.H = a.H; r.W = a.W; r.desc0 = 0; r.g = 0; r.pxoff = 0; r.aux = 0;
+    }
+    return r;
+}
+
+template <int NREAL, int MODE, int KB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const int NA)
+{
+    constexpr int A_BYTES = a_bytes(KB), A_STAGE = a_stage(KB);
+    constexpr int ROWB = KB * 2;                     // bytes per smem row of an operand tile (one pixel / one weight row)
+    constexpr int GOFF = 64 * ROWB;                  // Cout=64: offset of the single-tap group behind the 64 pair rows
+    constexpr int NGROUPS = NREAL == 64 ? 2 : 1;     // MMA groups per kernel row (pair + single, or one triple)
+    constexpr int ROWS_PER_KY = NREAL == 64 ? 192 : (NREAL == 32 ? 96 : 64);  // weight rows per (plane, ky), see model.cpp
+    constexpr int KSTEPS = KB / 16;
+    // early accumulator hand-back (see header): the modes whose epilogue needs nothing but the accumulators
+    constexpr bool EARLY = MODE == CONV_STORE16;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int nchunk = (a.cin + KB - 1) / KB;        // K-blocks
+    constexpr int W_KY = w_bytes_per_ky(NREAL, KB);
+    uint8_t* smA = smem;
+    uint8_t* smW = smem + NA * A_STAGE;              // resident weights: [K-block][ky] x W_KY bytes
+    uint8_t* smStage = smW + nchunk * 3 * W_KY;
+    Bars* bars = reinterpret_cast<Bars*>(smStage + NEPI * STAGE_BYTES);
+    __shared__ __align__(16) float s_bias[64];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool is_leader = rank == 0;
+    const int tiles_x = (a.W + BW - 1) / BW, bands_y = (a.H + BAND - 1) / BAND;
+    const int tiles_per_img = tiles_x * bands_y;
+    const int ntiles = a.ngroups > 0 ? a.ntiles_multi : tiles_per_img * a.B;  // pair tiles (merged launch: per-group grids)
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NA_MAX; i++) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
+        mbar_init(&bars->w_full, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], NEPI); }  // 4 warps per group x 2 CTAs
+        mbar_fence_init();
+        for (int i = 0; i < 3; i++) tma_prefetch_desc(&maps.m[i]);
+        for (int g = 1; g < a.ngroups; g++)
+            for (int i = 0; i < 3; i++) tma_prefetch_desc(&maps.mg[g - 1][i]);
+        tma_prefetch_desc(&maps.w);
+        tma_prefetch_desc(&maps.w32);
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + NREAL) s_bias[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
+    // rows behind each A box: read by the kx=2 taps of the last two (never stored) positions; keep them finite
+    {
+        constexpr int SL16 = a_slack(KB) / 16;  // uint4 per stage: 64 (KB=64, NA <= 4) or 32 (KB=32, NA <= 8): <= 256 threads
+        if (threadIdx.x >= 128 && threadIdx.x < 128 + NA * SL16) {
+            const int i = threadIdx.x - 128;
+            reinterpret_cast<uint4*>(smA + (i / SL16) * A_STAGE + A_BYTES)[i % SL16] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    cluster_sync();  // barriers of both CTAs are initialised before anybody signals across
+    if (warp == 1) tmem_alloc2(&bars->tmem_ptr, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_ptr;
+
+    if (warp < EPI_WARP0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+        // Resident weights: every CTA fetches ITS half of all weight blocks once (before the grid dependency is resolved --
+        // weights are constants, so this overlaps the previous conv's tail).  All bytes are counted on the leader's w_full.
+        if (warp == 2) {
+            if (elect_one() && !(a.debug_mask & 4)) {
+                const uint32_t wbar = mapa_u32(smem_u32(&bars->w_full), 0);
+                if (is_leader) mbar_expect_tx(&bars->w_full, 2u * (uint32_t)(nchunk * 3 * W_KY));
+                for (int c = 0; c < nchunk; c++)
+                    for (int ky = 0; ky < 3; ky++) {
+                        uint8_t* dst = smW + (c * 3 + ky) * W_KY;
+                        // weight rows are stored per (64-channel plane, ky); a 32-channel K-block is the left or right half of a row
+                        const int plane = KB == 64 ? c : (c >> 1), col = KB == 64 ? 0 : (c & 1) * 32;
+                        const int row0 = (plane * 3 + ky) * ROWS_PER_KY;
+                        if (NREAL == 16) tma2_load_2d(dst, &maps.w32, wbar, col, row0 + (int)rank * 32);
+                        else tma2_load_2d(dst, &maps.w, wbar, col, row0 + (int)rank * (NREAL == 32 ? 48 : 64));  // maps.w box: 48 rows for Cout<=32
+                        if (NREAL == 64) tma2_load_2d(dst + GOFF, &maps.w32, wbar, col, row0 + 128 + (int)rank * 32);
+                    }
+            } else if (is_leader && (a.debug_mask & 4) && lane == 0) {
+                mbar_arrive(&bars->w_full);
+            }
+        }
+        // Programmatic dependent launch: let the next conv's CTAs be scheduled onto SMs as soon as this grid's CTAs retire
+        // (they run their prologue and then block here), and wait until the previous grid has completed and flushed its
+        // outputs before touching any activation.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+
+        if (warp == 0) {
+            // ---------------- A producer (both CTAs; bytes are counted on the leader's barrier) ----------------
+            const bool leader = elect_one();
+            uint32_t s = 0, ph = 1;  // stage counter and the parity to wait for on its "empty" barrier (first pass: free)
+            for (int t = cluster_id; t < ntiles; t += nclusters) {
+                const TileGeo geo = decode_tile(a, t, tiles_per_img, tiles_x);
+                const CUtensorMap* gmaps = geo.g > 0 ? maps.mg[geo.g - 1] : maps.m;
+                const int cx = geo.tx * BW - 1, cy = geo.by * BAND + (int)rank * BH - 1;
+                for (int c = 0; c < nchunk; c++) {
+                    mbar_wait(&bars->a_empty[s], ph);
+                    if (leader) {
+                        if (a.debug_mask & 2) {
+                            if (is_leader) mbar_arrive(&bars->a_full[s]);
+                        } else {
+                            if (is_leader) mbar_expect_tx(&bars->a_full[s], 2 * A_BYTES);
+                            tma2_load_4d(smA + s * A_STAGE, &gmaps[KB == 64 ? c : (c >> 1)], mapa_u32(smem_u32(&bars->a_full[s]), 0),
+                                         KB == 64 ? 0 : (c & 1) * 32, cx, cy, geo.b);
+                        }
+                    }
+                    if (++s == (uint32_t)NA) { s = 0; ph ^= 1; }
+                }
+            }
+        } else if (warp == 1 && is_leader) {
+            // ---------------- MMA issuer (leader CTA only): counters and immediates only ----------------
+            const uint32_t issue = (elect_one() && !(a.debug_mask & 1)) ? 1u : 0u;
+            const uint32_t commit = elect_one() ? 1u : 0u;
+            constexpr uint32_t idesc_wide = umma_idesc_f16(256, NREAL == 32 ? 96 : (NREAL == 16 ? 64 : 128));
+            constexpr uint32_t idesc64 = umma_idesc_f16(256, 64);
+            const uint32_t desc_hi = (uint32_t)((KB == 64 ? umma_desc_sw128(0, 1024, 0) : umma_desc_sw64(0, 512, 0)) >> 32);
+            const uint32_t a_lo0 = (smem_u32(smA) & 0x3FFFFu) >> 4, w_lo0 = (smem_u32(smW) & 0x3FFFFu) >> 4;
+            const int last_ksteps = (a.cin - (nchunk - 1) * KB) >> 4;  // k-steps of the last K-block (Cin = 96 / 160 with KB = 64: 2)
+            uint32_t s = 0, ph = 0;       // A stage counter, parity of its "full" barrier
+            uint32_t buf = 0, phe = 3;    // accumulator set, per-set parity bits to wait for on acc_empty (first use: free)
+            int ti = 0;
+            mbar_wait(&bars->w_full, 0);
+            tc_fence_after();
+            for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
+                const bool ts_on = a.dbg_ts != nullptr && cluster_id == 0 && ti < 64 && commit;
+                if (ts_on) a.dbg_ts[ti * 8 + 0] = clock64();
+                mbar_wait(&bars->acc_empty[buf], (phe >> buf) & 1);
+                phe ^= 1u << buf;
+                tc_fence_after();
+                if (ts_on) a.dbg_ts[ti * 8 + 1] = clock64();
+                const uint32_t acc = tmem_base + buf * ACC_COLS;
+                uint32_t w_lo = w_lo0;
+                for (int c = 0; c < nchunk; c++) {
+                    mbar_wait(&bars->a_full[s], ph);
+                    tc_fence_after();
+                    if (ts_on && c == 0) a.dbg_ts[ti * 8 + 2] = clock64();
+                    const int ksteps = c == nchunk - 1 ? last_ksteps : KSTEPS;
+                    const uint32_t a_lo = a_lo0 + s * (uint32_t)(A_STAGE >> 4);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+                        for (int g = 0; g < NGROUPS; g++) {
+                            const uint32_t idesc = (g == 1) ? idesc64 : idesc_wide;
+#pragma unroll
+                            for (int ks = 0; ks < KSTEPS; ks++) {
+                                const uint32_t on = (KB == 64 && ks >= ksteps) ? 0u : issue;  // KB = 32: Cin % 32 == 0, every K-block is full
+                                const uint32_t accum = (c | ky | g | ks) ? 1u : 0u;
+                                const uint32_t ao = (uint32_t)(((ky * P + g * 2) * ROWB) >> 4) + ks * 2;
+                                const uint32_t bo = (uint32_t)((ky * W_KY + g * GOFF) >> 4) + ks * 2;
+                                umma2_issue(acc + 0 * DCOLS, a_lo + ao, w_lo + bo, desc_hi, idesc, accum, on);
+                                umma2_issue(acc + 1 * DCOLS, a_lo + ao + (128 * ROWB) / 16, w_lo + bo, desc_hi, idesc, accum, on);  // second M-tile: 128 rows further
+                            }
+                        }
+                    umma2_commit_if(&bars->a_empty[s], 3, commit);
+                    w_lo += (uint32_t)((3 * W_KY) >> 4);
+                    if (++s == (uint32_t)NA) { s = 0; ph ^= 1; }
+                }
+                umma2_commit_if(&bars->acc_full[buf], 3, commit);
+                if (ts_on) a.dbg_ts[ti * 8 + 3] = clock64();
+                buf ^= 1;
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        // ---------------- epilogue: warps 4..11 in two groups of four ----------------
+        // Group g = (warp-4)/4 owns accumulator set g, i.e. every second work tile; inside a group warp q4 = warp % 4
+        // (its TMEM lane quarter) handles row q4 of both M-tiles.
+        const int q4 = warp & 3;
+        const int ew = warp - EPI_WARP0;
+        const int group = ew >> 2;
+        uint32_t* stg = reinterpret_cast<uint32_t*>(smStage + ew * STAGE_BYTES);  // [32 rows][20 words]
+        const int tr = lane >> 2, tc = lane & 3;
+        const bool dbg_noepi = (a.debug_mask & 8) != 0;
+        const uint32_t acc_empty_leader = mapa_u32(smem_u32(&bars->acc_empty[group]), 0);
+        const int buf = group;
+        uint32_t phf = 0;  // parity to wait for on this group's acc_full
+        int ti = group;
+        for (int t = cluster_id + group * nclusters; t < ntiles; t += 2 * nclusters, ti += 2) {
+            const TileGeo geo = decode_tile(a, t, tiles_per_img, tiles_x);
+            const int b = geo.b, by = geo.by, tx = geo.tx;
+            const int x0 = tx * BW;
+            int yy[2];
+            size_t rowpix[2];
+            bool vrow[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                yy[i] = by * BAND + (int)rank * BH + i * 4 + q4;
+                vrow[i] = yy[i] < geo.H && !dbg_noepi;
+                rowpix[i] = geo.pxoff + ((size_t)b * geo.H + yy[i]) * geo.W + x0;
+            }
+            bool vcol[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < geo.W);
+            // residual operands.  fp32 modes (CONV_RDB_OUT with T32, CONV_TRUNK with F32): one (M-tile, 32-channel block) is
+            // fetched one block ahead of use.  CONV_RDB_OUT16: ALL fp16 x0 values this thread needs for the tile (4 blocks x
+            // 8 x 8 B = 64 registers) are requested here, before waiting for the MMAs -- per-tile timestamps showed the
+            // one-block-ahead scheme paying one memory latency (~3.7 k clk) per block, 15 k clk per tile against 7.5 k clk of
+            // MMAs.
+            constexpr bool RDB16 = MODE == CONV_RDB_OUT16;
+            constexpr bool RDB = MODE == CONV_RDB_OUT || RDB16;
+            float4 res[2][4];
+            uint2 x0raw[RDB16 ? 2 : 1][2][2][4];  // [i][nb][hf][r], RDB16 only
+            auto load_res = [&](int i, int nb, float4 (&dst)[2][4]) {
+                if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
+                    const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + nb * 32 + tc * 4;
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                        for (int r = 0; r < 4; r++)
+                            if (vcol[r] && vrow[i]) dst[hf][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
+                }
+            };
+            if constexpr (RDB16) {
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int nb = 0; nb < 2; nb++)
+#pragma unroll
+                        for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                            for (int r = 0; r < 4; r++)
+                                if (vcol[r] && vrow[i])
+                                    x0raw[i][nb][hf][r] = *reinterpret_cast<const uint2*>(a.res16 + (rowpix[i] + tr + 8 * r) * 64 + nb * 32 + hf * 16 + tc * 4);
+            } else {
+                load_res(0, 0, res);
+            }
+            if constexpr (RDB) {
+                if (a.rrdb_end) {  // the RRDB-level skip operands of THIS tile: pull the rows into L2 while the MMAs run
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+                        if (vrow[i]) {
+                            const int npx = min(BW, geo.W - x0);
+                            const char* p1 = reinterpret_cast<const char*>(a.r32 + rowpix[i] * 64);
+                            for (int l = lane; l < npx * 2; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + (size_t)l * 128));
+                        }
+                }
+            }
+            const bool ts_on = a.dbg_ts != nullptr && cluster_id == 0 && ti < 64 && is_leader && (ew & 3) == 0 && lane == 0;
+            if (ts_on) a.dbg_ts[ti * 8 + 4] = clock64();
+            mbar_wait(&bars->acc_full[buf], phf);
+            phf ^= 1;
+            tc_fence_after();
+            if (ts_on) a.dbg_ts[ti * 8 + 5] = clock64();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS;
+
+            if constexpr (EARLY) {
+                // ---- both M-tiles -> registers (taps combined, + bias), hand the set back, then activation / pack / store ----
+                float f[2][NREAL];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const uint32_t taddr = taddr0 + i * DCOLS;
+                    if constexpr (NREAL == 32) {  // D[0:32] + right neighbour's D[32:64] + second right neighbour's D[64:96]
+                        uint32_t v[32], u[32], w[32];
+                        tmem_ld32(taddr, v);
+                        tmem_ld32(taddr + 32, u);
+                        tmem_ld32(taddr + 64, w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            f[i][j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
+                                      __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2) + s_bias[j];
+                    } else {  // D[nb*32..] + right neighbour's D[64 + nb*32..]
+#pragma unroll
+                        for (int nb = 0; nb < 2; nb++) {
+                            uint32_t v[32], u[32];
+                            tmem_ld32(taddr + nb * 32, v);
+                            tmem_ld32(taddr + 64 + nb * 32, u);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                f[i][nb * 32 + j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) + s_bias[nb * 32 + j];
+                        }
+                    }
+                }
+                // Plain (CTA-scope release) remote arrive: only the TMEM reads have to be ordered (tcgen05 fence); a cluster-scope
+                // release would also wait for this thread's global stores to drain.
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(acc_empty_leader);
+                if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int nb = 0; nb < NREAL / 32; nb++) {
+                        float* fb = &f[i][nb * 32];
+                        if (a.act == 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) fb[j] = fb[j] > 0.f ? fb[j] : fb[j] * a.slope;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) =
+                                make_uint4(pack_h2(fb[8 * k + 0], fb[8 * k + 1]), pack_h2(fb[8 * k + 2], fb[8 * k + 3]),
+                                           pack_h2(fb[8 * k + 4], fb[8 * k + 5]), pack_h2(fb[8 * k + 6], fb[8 * k + 7]));
+                        __syncwarp();
+                        __half* orow = a.out16 + rowpix[i] * a.out_cs + a.out_co + nb * 32 + tc * 8;
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const uint4 o = *reinterpret_cast<const uint4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
+                            if (vcol[r] && vrow[i]) *reinterpret_cast<uint4*>(orow + (size_t)(tr + 8 * r) * a.out_cs) = o;
+                        }
+                        __syncwarp();
+                    }
+                if (ts_on) a.dbg_ts[ti * 8 + 7] = clock64();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const uint32_t taddr = taddr0 + i * DCOLS;
+                    if constexpr (NREAL == 16) {
+                        uint32_t v[32], u[16];
+                        tmem_ld32(taddr, v);
+                        tmem_ld16(taddr + 32, u);
+                        tmem_ld_wait();
+                        float o[3];
+#pragma unroll
+                        for (int j = 0; j < 3; j++)
+                            o[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[16 + j]), 1) +
+                                   __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 2) + s_bias[j];
+                        const int x = x0 + lane;
+                        if (lane < BW && x < geo.W && vrow[i]) {
+                            const TileDesc td = a.tiles[geo.desc0 + b];
+                            if constexpr (MODE == CONV_LAST_U8) {
+                                const int ii = yy[i] - a.prepad_s, jx = x - a.prepad_s;
+                                if (ii >= 0 && ii < td.crop_h && jx >= 0 && jx < td.crop_w) {
+                                    uint8_t* dst = a.img_out + ((size_t)(td.out_y0 + ii) * a.img_w + td.out_x0 + jx) * a.img_c;
+#pragma unroll
+                                    for (int j = 0; j < 3; j++) {
+                                        int iv = (int)(o[j] * 255.f + 0.5f);
+                                        dst[j] = (uint8_t)min(max(iv, 0), 255);
+                                    }
+                                }
+                            } else {
+                                float4* dst = reinterpret_cast<float4*>(a.tta_out) + geo.aux + (size_t)td.tta_slot * ((size_t)geo.H * geo.W) + (size_t)yy[i] * geo.W + x;
+                                *dst = make_float4(o[0], o[1], o[2], 0.f);
+                            }
+                        }
+                    } else {
+                        // CONV_RDB_OUT / CONV_RDB_OUT16 / CONV_TRUNK (Cout = 64): fp32 math against the residual stream in the transposed domain
+#pragma unroll
+                        for (int nb = 0; nb < 2; nb++) {
+                            uint32_t v[32], u[32];
+                            tmem_ld32(taddr + nb * 32, v);
+                            tmem_ld32(taddr + 64 + nb * 32, u);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1));
+                            float4 nxt[2][4];
+                            if constexpr (!RDB16) {  // prefetch the residual operands of the next (M-tile, 32-channel block)
+                                const int ni = nb == 1 ? i + 1 : i, nnb = nb ^ 1;
+                                if (ni < 2) load_res(ni, nnb, nxt);
+                            }
+#pragma unroll
+                            for (int hf = 0; hf < 2; hf++) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++)
+                                    *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) = make_uint4(v[16 * hf + 4 * k], v[16 * hf + 4 * k + 1], v[16 * hf + 4 * k + 2], v[16 * hf + 4 * k + 3]);
+                                __syncwarp();
+                                const int ch0 = nb * 32 + hf * 16 + tc * 4;
+                                const float4 bb = *reinterpret_cast<const float4*>(&s_bias[ch0]);
+                                float4 acc4[4];
+#pragma unroll
+                                for (int r = 0; r < 4; r++) acc4[r] = *reinterpret_cast<const float4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
+                                __syncwarp();
+                                if constexpr (RDB16) {
+#pragma unroll
+                                    for (int r = 0; r < 4; r++) {
+                                        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&x0raw[i][nb][hf][r].x));
+                                        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&x0raw[i][nb][hf][r].y));
+                                        res[hf][r] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                                    }
+                                }
+                                float4 rr[4];
+                                if (RDB && a.rrdb_end) {
+#pragma unroll
+                                    for (int r = 0; r < 4; r++)
+                                        if (vcol[r] && vrow[i]) rr[r] = *reinterpret_cast<const float4*>(a.r32 + (rowpix[i] + tr + 8 * r) * 64 + ch0);
+                                }
+#pragma unroll
+                                for (int r = 0; r < 4; r++) {
+                                    float4 o;
+                                    if constexpr (RDB) {
+                                        o.x = (acc4[r].x + bb.x) * 0.2f + res[hf][r].x;
+                                        o.y = (acc4[r].y + bb.y) * 0.2f + res[hf][r].y;
+                                        o.z = (acc4[r].z + bb.z) * 0.2f + res[hf][r].z;
+                                        o.w = (acc4[r].w + bb.w) * 0.2f + res[hf][r].w;
+                                        if (a.rrdb_end) {
+                                            o.x = o.x * 0.2f + rr[r].x; o.y = o.y * 0.2f + rr[r].y;
+                                            o.z = o.z * 0.2f + rr[r].z; o.w = o.w * 0.2f + rr[r].w;
+                                        }
+                                    } else {
+                                        o.x = acc4[r].x + bb.x + res[hf][r].x; o.y = acc4[r].y + bb.y + res[hf][r].y;
+                                        o.z = acc4[r].z + bb.z + res[hf][r].z; o.w = acc4[r].w + bb.w + res[hf][r].w;
+                                    }
+                                    if (vcol[r] && vrow[i]) {
+                                        const size_t px = rowpix[i] + tr + 8 * r;
+                                        if constexpr (RDB) {
+                                            if (a.rrdb_end) *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0) = o;
+                                            if constexpr (!RDB16) *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o;
+                                        }
+                                        *reinterpret_cast<uint2*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                                    }
+                                }
+                            }
+                            if constexpr (!RDB16) {
+#pragma unroll
+                                for (int h2 = 0; h2 < 2; h2++)
+#pragma unroll
+                                    for (int r = 0; r < 4; r++) res[h2][r] = nxt[h2][r];
+                            }
+                        }
+                    }
+                }
+                // accumulator set drained by this warp: tell the leader's MMA issuer (CTA-scope release, see above)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(acc_empty_leader);
+                if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync();  // nobody frees TMEM / exits while the peer may still signal or be read
+    if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
+template <int NREAL, int MODE, int KB>
+cudaError_t launch_nmk(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
+{
+    static bool attr_done[64] = {};
+    static int num_sms[64] = {};
+    cudaError_t e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    dev &= 63;
+    if (!attr_done[dev]) {
+        e = cudaFuncSetAttribute(conv3x3_kernel<NREAL, MODE, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        attr_done[dev] = true;
+    }
+    if (a.ngroups < 0 || a.ngroups > 4) return cudaErrorInvalidValue;
+    const long long ntiles = a.ngroups > 0 ? (long long)a.ntiles_multi : (long long)((a.W + BW - 1) / BW) * ((a.H + BAND - 1) / BAND) * a.B;
+    if (ntiles <= 0) return cudaErrorInvalidValue;
+    long long nclusters = num_sms[dev] / 2;
+    if (ntiles < nclusters) nclusters = ntiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * nclusters));
+    cfg.blockDim = dim3(NTHREADS);
+    // resident weights first, then as many A stages as fit (KB = 64: 2..4 of 41 KB; KB = 32: 4..8 of 20.5 KB)
+    const int nchunk = (a.cin + KB - 1) / KB;
+    const int wbytes = nchunk * 3 * w_bytes_per_ky(NREAL, KB);
+    int na = (SMEM_MAX - SMEM_FIXED - wbytes) / a_stage(KB);
+    if (na > na_max(KB)) na = na_max(KB);
+    if (na < 2) return cudaErrorInvalidValue;
+    cfg.dynamicSmemBytes = SMEM_FIXED + wbytes + na * a_stage(KB);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const int use_pdl = getenv("RSR_NOPDL") ? 0 : 1;  // bring-up switch
+    cfg.numAttrs = use_pdl;
+    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_kernel<NREAL, MODE, KB>, *in_map, a, na)) != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+template <int NREAL, int MODE>
+cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
+{
+    return a.kblock == 32 ? launch_nmk<NREAL, MODE, 32>(in_map, a, stream) : launch_nmk<NREAL, MODE, 64>(in_map, a, stream);
+}
+
+}  // namespace
+
+cudaError_t launch_conv3x3(const ConvMaps* in_map, const ConvArgs& a, int cout_pad, cudaStream_t stream)
+{
+    if (cout_pad == 32 && a.mode == CONV_STORE16) return launch_nm<32, CONV_STORE16>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_STORE16) return launch_nm<64, CONV_STORE16>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_RDB_OUT) return launch_nm<64, CONV_RDB_OUT>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_RDB_OUT16) return launch_nm<64, CONV_RDB_OUT16>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_TRUNK) return launch_nm<64, CONV_TRUNK>(in_map, a, stream);
+    if (cout_pad == 16 && a.mode == CONV_LAST_U8) return launch_nm<16, CONV_LAST_U8>(in_map, a, stream);
+    if (cout_pad == 16 && a.mode == CONV_LAST_F32) return launch_nm<16, CONV_LAST_F32>(in_map, a, stream);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace rsr

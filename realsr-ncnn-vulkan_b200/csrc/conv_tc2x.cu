@@ -625,6 +625,55 @@ conv3x3_tc2x_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, con
             mbar_wait(&bars->acc_full[buf], (ti >> 1) & 1);
             tc_fence_after();
             if (ts_on) a.dbg_ts[ti * 8 + 5] = clock64();
+            if constexpr (MODE == CONV_STORE16 && NREAL == 32) {
+                if (a.epi_split == 2) {
+                    // Early hand-back (option epilogue_split=2): both M-tiles' accumulators go to registers (taps combined, same
+                    // operation order as below), the set returns to the MMA issuer, and only then bias/activation/pack/store
+                    // run -- the chain "MMA done -> epilogue of that set -> arrive" (profiles/r1_ts_1.txt: ~3.0 k clk per
+                    // tile) shrinks to the TMEM read.  The two 4-warp groups still alternate tiles, so one group's stores
+                    // overlap the other group's TMEM reads.
+                    float f[2][32];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS + i * DCOLS;
+                        uint32_t v[32], u[32], w[32];
+                        tmem_ld32(taddr, v);
+                        tmem_ld32(taddr + 32, u);
+                        tmem_ld32(taddr + 64, w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            f[i][j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
+                                      __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2) + s_bias[j];
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(acc_empty_leader);
+                    if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        if (a.act == 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) f[i][j] = f[i][j] > 0.f ? f[i][j] : f[i][j] * a.slope;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) =
+                                make_uint4(pack_h2(f[i][8 * k + 0], f[i][8 * k + 1]), pack_h2(f[i][8 * k + 2], f[i][8 * k + 3]),
+                                           pack_h2(f[i][8 * k + 4], f[i][8 * k + 5]), pack_h2(f[i][8 * k + 6], f[i][8 * k + 7]));
+                        __syncwarp();
+                        __half* orow = a.out16 + rowpix[i] * a.out_cs + a.out_co + tc * 8;
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const uint4 o = *reinterpret_cast<const uint4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
+                            if (vcol[r] && vrow[i]) *reinterpret_cast<uint4*>(orow + (size_t)(tr + 8 * r) * a.out_cs) = o;
+                        }
+                        __syncwarp();
+                    }
+                    if (ts_on) a.dbg_ts[ti * 8 + 7] = clock64();
+                    continue;
+                }
+            }
 #pragma unroll
             for (int i = 0; i < 2; i++) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS + i * DCOLS;
@@ -835,12 +884,12 @@ cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t st
     if (a.ngroups > 0) {  // merged multi-shape launch
         if (a.ngroups > 4) return cudaErrorInvalidValue;
         if (a.kblock == 32)
-            return a.epi_split ? launch_nmskm<NREAL, MODE, true, 32, true>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 32, true>(in_map, a, stream);
-        return a.epi_split ? launch_nmskm<NREAL, MODE, true, 64, true>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 64, true>(in_map, a, stream);
+            return a.epi_split == 1 ? launch_nmskm<NREAL, MODE, true, 32, true>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 32, true>(in_map, a, stream);
+        return a.epi_split == 1 ? launch_nmskm<NREAL, MODE, true, 64, true>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 64, true>(in_map, a, stream);
     }
     if (a.kblock == 32)
-        return a.epi_split ? launch_nmskm<NREAL, MODE, true, 32, false>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 32, false>(in_map, a, stream);
-    return a.epi_split ? launch_nmskm<NREAL, MODE, true, 64, false>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 64, false>(in_map, a, stream);
+        return a.epi_split == 1 ? launch_nmskm<NREAL, MODE, true, 32, false>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 32, false>(in_map, a, stream);
+    return a.epi_split == 1 ? launch_nmskm<NREAL, MODE, true, 64, false>(in_map, a, stream) : launch_nmskm<NREAL, MODE, false, 64, false>(in_map, a, stream);
 }
 
 }  // namespace

@@ -204,9 +204,14 @@ void free_ws(Workspace* w)
     delete w;
 }
 
+// conv_impl: 1 single-CTA .ws kernel (conv_tc.cu), 2 CTA-pair kernel of round 1 (conv_tc2.cu), 3 its 32-channel K-block variant
+// (conv_tc2x.cu), 4 / 5 the unified kernel (conv3x3.cu) with 64- / 32-channel K-blocks
+inline int kblock_of(const rsr_handle* h) { return (h->conv_impl == 3 || h->conv_impl == 5) ? 32 : 64; }
+
 struct BatchCtx {
     rsr_handle* h;
     Workspace* ws;
+    int tilesize, prepadding;  // snapshot of the handle's parameters taken (under its mutex) when the call started
     long long launches = 0;
     size_t nconv_ev = 0;
 };
@@ -234,15 +239,20 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
         c.nconv_ev++;
         CK(cudaEventRecord(e0, c.ws->stream));
     }
-    if (h->conv_impl == 3 && !dm.k32_ok) return set_err(h, RSR_ERR_CUDA, "conv_impl 3: SWIZZLE_64B tensor maps are not available");
+    const int kb = kblock_of(h);
+    if (kb == 32 && !dm.k32_ok) return set_err(h, RSR_ERR_CUDA, "32-channel K-blocks: SWIZZLE_64B tensor maps are not available");
     if (h->conv_impl >= 2) {
         ConvMaps mm = *map;
-        mm.w = h->conv_impl == 3 ? dm.wmap_k32[conv_idx] : dm.wmap[conv_idx];
-        mm.w32 = h->conv_impl == 3 ? dm.wmap32_k32[conv_idx] : dm.wmap32[conv_idx];
-        a.kblock = h->conv_impl == 3 ? 32 : 64;
-        // the validated round-1 kernel unless one of the opt-in variants is requested (conv_tc2x.cu)
-        const bool variant = a.epi_split || a.reverse || a.ngroups > 0 || a.kblock == 32;
-        CK((variant ? launch_conv3x3_tc2x : launch_conv3x3_tc2)(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
+        mm.w = kb == 32 ? dm.wmap_k32[conv_idx] : dm.wmap[conv_idx];
+        mm.w32 = kb == 32 ? dm.wmap32_k32[conv_idx] : dm.wmap32[conv_idx];
+        a.kblock = kb;
+        if (h->conv_impl >= 4) {
+            CK(launch_conv3x3(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
+        } else {
+            // the validated round-1 kernel unless one of the opt-in variants is requested (conv_tc2x.cu)
+            const bool variant = a.epi_split || a.reverse || a.ngroups > 0 || a.kblock == 32;
+            CK((variant ? launch_conv3x3_tc2x : launch_conv3x3_tc2)(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
+        }
     } else {
         CK(launch_conv3x3_tc(map, a, dm.cout_pad[conv_idx], c.ws->stream));
     }
@@ -277,7 +287,7 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c
     const size_t plane = npx * 64;
     ConvMaps mapD[2], mapU1, mapV1, mapU2, mapV2;
     const int brows = (h->conv_impl >= 2 ? CONV2_BH : CONV_BH) + 2;
-    const int box_c = h->conv_impl == 3 ? 32 : 64;
+    const int box_c = kblock_of(h);
     for (int i = 0; i < 2; i++)
         for (int pl = 0; pl < 3; pl++)
             if ((r = make_map(h, &mapD[i].m[pl], D[i] + pl * plane, 64, W, H, B, brows, box_c))) return r;
@@ -350,7 +360,7 @@ int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c
         a.H = 4 * H; a.W = 4 * W;
         a.mode = tta_out ? CONV_LAST_F32 : CONV_LAST_U8;
         a.img_out = d_out; a.img_w = img_w * 4; a.img_h = img_h * 4; a.img_c = img_c;
-        a.prepad_s = h->prepadding * 4;
+        a.prepad_s = c.prepadding * 4;
         a.tta_out = (float*)ws->tta.p;
         if ((r = conv(c, &mapU2, a, m.idx_last()))) return r;
     }
@@ -404,7 +414,7 @@ int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_
     __half* D[2] = {(__half*)ws->d16[0].p, (__half*)ws->d16[1].p};
     const size_t plane = npx * 64;
     const int brows = CONV2_BH + 2;
-    const int box_c = h->conv_impl == 3 ? 32 : 64;
+    const int box_c = kblock_of(h);
     ConvMaps mapD[2], mapU1, mapV1, mapU2, mapV2;
     auto slot = [](ConvMaps& cm, int g, int pl) -> CUtensorMap* { return g == 0 ? &cm.m[pl] : &cm.mg[g - 1][pl]; };
     for (int g = 0; g < G; g++) {
@@ -505,7 +515,7 @@ int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_
         fill_groups(a, 4);
         a.mode = tta_out ? CONV_LAST_F32 : CONV_LAST_U8;
         a.img_out = d_out; a.img_w = img_w * 4; a.img_h = img_h * 4; a.img_c = img_c;
-        a.prepad_s = h->prepadding * 4;
+        a.prepad_s = c.prepadding * 4;
         a.tta_out = (float*)ws->tta.p;
         if ((r = conv(c, &mapU2, a, m.idx_last()))) return r;
     }
@@ -514,9 +524,8 @@ int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_
 
 // tiles [tile_first, tile_first + tile_count) of the reference's row-major tile grid; `done` (optional) receives their descriptors
 int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, int hh, int ch, uint8_t* d_out, long long* padded_out,
-                      long long* launches_out, int tile_first, int tile_count, std::vector<TileDesc>* done)
+                      long long* launches_out, int tile_first, int tile_count, std::vector<TileDesc>* done, size_t* nconv_ev_out, int T, int P)
 {
-    const int T = h->tilesize, P = h->prepadding;
     const int xtiles = (w + T - 1) / T, ytiles = (hh + T - 1) / T;
     // tile grid: reference src/realsr.cpp:170-171,:176-187,:235-241 (GPU) == :537-553 (CPU)
     std::map<std::pair<int, int>, std::vector<TileDesc>> groups;
@@ -533,7 +542,7 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
             groups[{t.base_h, t.base_w}].push_back(t);
             if (done) done->push_back(t);
         }
-    BatchCtx c{h, ws};
+    BatchCtx c{h, ws, T, P};
     long long padded = 0;
     int r;
     // Every batch of the call is planned first, so that all tile descriptors go to the device in ONE copy from pinned memory
@@ -700,16 +709,7 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
     }
     *padded_out = padded;
     *launches_out = c.launches;
-    if (h->time_convs) {
-        double ms = 0;
-        for (size_t i = 0; i < c.nconv_ev; i++) {
-            float t = 0;
-            cudaEventElapsedTime(&t, ws->conv_events[i].first, ws->conv_events[i].second);
-            ms += t;
-        }
-        std::lock_guard<std::mutex> g(h->mu);
-        h->last_conv_ms = ms;
-    }
+    *nconv_ev_out = c.nconv_ev;  // the per-conv events are read by the caller AFTER it has synchronised the stream
     return 0;
 }
 
@@ -826,6 +826,9 @@ int rsr_set(rsr_handle* h, int scale, int tilesize, int prepadding)
     if (scale != 4) return set_err(h, RSR_ERR_GENERIC, "invalid scale argument (only 4 is supported, like the reference)");
     if (tilesize < 32) return set_err(h, RSR_ERR_GENERIC, "invalid tilesize argument (must be >= 32)");
     if (prepadding < 0 || prepadding > 64) return set_err(h, RSR_ERR_GENERIC, "invalid prepadding");
+    // RealSR::process() const forwards its public members on every call, possibly from several proc threads at once
+    // (host/realsr.h, reference src/main.cpp:811-828): the write is serialised and every call works on its own snapshot
+    std::lock_guard<std::mutex> g(h->mu);
     h->scale = scale;
     h->tilesize = tilesize;
     h->prepadding = prepadding;
@@ -837,7 +840,13 @@ static int process_impl(rsr_handle* h, const uint8_t* in, int w, int hh, int c, 
 {
     int r = check_args(h, in, w, hh, c, out);
     if (r) return r;
-    const int ntiles_img = ((w + h->tilesize - 1) / h->tilesize) * ((hh + h->tilesize - 1) / h->tilesize);
+    int T, P;
+    {
+        std::lock_guard<std::mutex> g(h->mu);
+        T = h->tilesize;
+        P = h->prepadding;
+    }
+    const int ntiles_img = ((w + T - 1) / T) * ((hh + T - 1) / T);
     const bool whole = tile_count < 0;
     if (whole) { tile_first = 0; tile_count = ntiles_img; }
     if (tile_first < 0 || tile_count < 0 || tile_first + tile_count > ntiles_img)
@@ -861,7 +870,8 @@ static int process_impl(rsr_handle* h, const uint8_t* in, int w, int hh, int c, 
         CK(cudaEventRecord(ws->ev0, ws->stream));
         if (host_buffers) CK(cudaMemcpyAsync(ws->img_in.p, in, in_bytes, cudaMemcpyHostToDevice, ws->stream));
         std::vector<TileDesc> done;
-        if ((rr = process_on_device(h, ws, d_in, w, hh, c, d_out, &padded, &launches, tile_first, tile_count, whole ? nullptr : &done))) return rr;
+        size_t nconv_ev = 0;
+        if ((rr = process_on_device(h, ws, d_in, w, hh, c, d_out, &padded, &launches, tile_first, tile_count, whole ? nullptr : &done, &nconv_ev, T, P))) return rr;
         if (host_buffers) {
             if (whole) {
                 CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ws->stream));
@@ -877,8 +887,15 @@ static int process_impl(rsr_handle* h, const uint8_t* in, int w, int hh, int c, 
         CK(cudaStreamSynchronize(ws->stream));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+        double conv_ms = 0;
+        for (size_t i = 0; i < nconv_ev; i++) {  // time_convs: every pair has completed (stream synchronised above); no silent zeros
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, ws->conv_events[i].first, ws->conv_events[i].second));
+            conv_ms += t;
+        }
         std::lock_guard<std::mutex> g(h->mu);
         h->last_ms = ms;
+        if (h->time_convs) h->last_conv_ms = conv_ms;
         h->last_padded = padded;
         h->launches += launches;
         return 0;
@@ -917,14 +934,14 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
 {
     if (!h || !key) return RSR_ERR_GENERIC;
     if (!strcmp(key, "max_batch")) h->max_batch = value;
-    else if (!strcmp(key, "epilogue_split")) h->epilogue_split = value ? 1 : 0;
+    else if (!strcmp(key, "epilogue_split")) h->epilogue_split = value < 0 || value > 2 ? 0 : (int)value;  // 1 = channel split, 2 = early hand-back (Cout=32 convs)
     else if (!strcmp(key, "serpentine")) h->serpentine = value ? 1 : 0;
     else if (!strcmp(key, "merge_shapes")) h->merge_shapes = value ? 1 : 0;
     else if (!strcmp(key, "debug_mask")) h->debug_mask = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
     else if (!strcmp(key, "conv_impl")) {
-        if (value < 1 || value > 3) return set_err(h, RSR_ERR_GENERIC, "conv_impl must be 1, 2 or 3");
-        if (value == 3 && h->loaded && !h->dm.k32_ok) return set_err(h, RSR_ERR_CUDA, "conv_impl 3: SWIZZLE_64B tensor maps are not available");
+        if (value < 1 || value > 5) return set_err(h, RSR_ERR_GENERIC, "conv_impl must be 1..5");
+        if ((value == 3 || value == 5) && h->loaded && !h->dm.k32_ok) return set_err(h, RSR_ERR_CUDA, "conv_impl 3/5: SWIZZLE_64B tensor maps are not available");
         h->conv_impl = (int)value;
     }
     else if (!strcmp(key, "residual_fp16")) h->residual_fp16 = (int)value;
@@ -1009,10 +1026,10 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     int r = 0;
     for (int pl = 0; pl < 3; pl++)
         if ((r = make_map(h, &map.m[pl], d_in + (size_t)(pl < nplane ? pl : 0) * npx * 64, 64, W, H, 1, (h->conv_impl >= 2 ? CONV2_BH : CONV_BH) + 2,
-                          h->conv_impl == 3 ? 32 : 64)))
+                          kblock_of(h))))
             return r;
-    map.w = h->conv_impl == 3 ? h->dm.wmap_k32[conv_index] : h->dm.wmap[conv_index];
-    map.w32 = h->conv_impl == 3 ? h->dm.wmap32_k32[conv_index] : h->dm.wmap32[conv_index];
+    map.w = kblock_of(h) == 32 ? h->dm.wmap_k32[conv_index] : h->dm.wmap[conv_index];
+    map.w32 = kblock_of(h) == 32 ? h->dm.wmap32_k32[conv_index] : h->dm.wmap32[conv_index];
     ConvArgs a{};
     a.wpk = h->dm.wpk[conv_index]; a.bias = h->dm.bias[conv_index]; a.cin = cl.cin;
     a.H = H; a.W = W; a.B = 1;
@@ -1022,7 +1039,7 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     a.mode = npad == 16 ? CONV_LAST_F32 : CONV_STORE16;
     a.debug_mask = h->debug_mask;
     a.epi_split = h->epilogue_split;
-    a.kblock = h->conv_impl == 3 ? 32 : 64;
+    a.kblock = kblock_of(h);
     long long* d_ts = nullptr;
     float* d_r32 = nullptr;
     if (getenv("RSR_DBG_RDB") && npad == 64) {  // bring-up: time the Cout=64 conv with its real (CONV_RDB_OUT) epilogue
@@ -1040,7 +1057,8 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
         a.dbg_ts = d_ts;
     }
     for (int rep = 0; rep < (d_ts ? 2 : 1); rep++) {
-        if (h->conv_impl >= 2) CK(((a.epi_split || a.kblock == 32) ? launch_conv3x3_tc2x : launch_conv3x3_tc2)(&map, a, npad, 0));
+        if (h->conv_impl >= 4) CK(launch_conv3x3(&map, a, npad, 0));
+        else if (h->conv_impl >= 2) CK(((a.epi_split || a.kblock == 32) ? launch_conv3x3_tc2x : launch_conv3x3_tc2)(&map, a, npad, 0));
         else CK(launch_conv3x3_tc(&map, a, npad, 0));
     }
     CK(cudaDeviceSynchronize());

@@ -99,6 +99,8 @@ cudaError_t launch_conv3x3_tc(const ConvMaps* in_maps, const ConvArgs& a, int co
 cudaError_t launch_conv3x3_tc2(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
 // conv_tc2x.cu: the same kernel with the opt-in variants (ConvArgs::epi_split / kblock / ngroups / reverse); conv_tc2.cu ignores those
 cudaError_t launch_conv3x3_tc2x(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
+// conv3x3.cu: the unified CTA-pair kernel (early accumulator hand-back, lean MMA issuer, merged launches, K-block 64 / 32)
+cudaError_t launch_conv3x3(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
 constexpr int CONV2_BH = 8;
 constexpr int CONV2_BW = 30;    // output columns per work tile of the CTA-pair kernel (CONV_P - 2)
 constexpr int CONV2_BAND = 16;  // output rows per work tile of the CTA-pair kernel (2 x CONV2_BH)

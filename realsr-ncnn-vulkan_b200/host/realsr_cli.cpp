@@ -7,7 +7,8 @@
 // threads, jobs_proc[i] per GPU sharing that GPU's RealSR object -> queue of 8 -> save threads; sentinel shutdown).
 // Differences: `-g` takes CUDA ordinals and `-g -1` (ncnn CPU mode) is refused; one proc count is broadcast to all
 // GPUs (BASELINE configs[2] uses `-j 4:8:4` with 8 GPUs, which the reference itself rejects, main.cpp:560-564); auto
-// tile size is 400; codecs: PNG (host/png_codec.h on zlib), JPEG (host/jpeg_codec.h: sequential + progressive reader,
+// tile size (-t 0) is 200, the reference's pick on any GPU with more than 1.9 GB (main.cpp:753-774: tile geometry is part of the
+// numerical contract); codecs: PNG (host/png_codec.h on zlib), JPEG (host/jpeg_codec.h: sequential + progressive reader,
 // baseline writer) and lossless WebP (host/webp_codec.h), all written for this repo -- the reference's stb / libwebp files
 // are not copied; lossy (VP8) WebP inputs go through the Python CLI (`python -m realsr_ncnn_vulkan_b200.cli`, Pillow).  Host plumbing only: every pixel goes through RealSR::process.
 #include <dirent.h>
@@ -250,7 +251,7 @@ int main(int argc, char** argv)
             return -1;
         }
         realsr[i]->scale = scale;
-        realsr[i]->tilesize = tilesize[i] ? tilesize[i] : 400;
+        realsr[i]->tilesize = tilesize[i] ? tilesize[i] : 200;  // main.cpp:766-767
         realsr[i]->prepadding = prepadding;
     }
 

@@ -54,11 +54,17 @@ def process_sharded(engines, inimage, outimage):
     h, w, _ = inimage.shape
     parts = split_tiles(w, h, e0.tilesize, e0.prepadding, len(engines))
     rcs = [0] * len(engines)
+    errs = [None] * len(engines)
 
     def work(i):
         first, count = parts[i]
-        if count:
+        if not count:
+            return
+        try:
             rcs[i] = engines[i].process_tiles(inimage, outimage, first, count)
+        except BaseException as ex:  # a worker thread must not swallow it: the shard's tiles would stay unwritten
+            errs[i] = ex
+            rcs[i] = -1
 
     threads = [threading.Thread(target=work, args=(i,)) for i in range(1, len(engines))]
     for t in threads:
@@ -66,6 +72,9 @@ def process_sharded(engines, inimage, outimage):
     work(0)
     for t in threads:
         t.join()
+    for ex in errs:
+        if ex is not None:
+            raise ex
     for rc in rcs:
         if rc:
             return rc
