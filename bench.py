@@ -64,8 +64,9 @@ def ref_binary():
     return p, "port"
 
 
-def run_cpu_reference(img, tilesize, threads):
-    """process_cpu wall time (seconds, measured inside the binary around the call, model load excluded)"""
+def run_cpu_reference(img, tilesize, threads, want_output=False):
+    """process_cpu wall time (seconds, measured inside the binary around the call, model load excluded)
+    [+ the reference's output image when want_output]"""
     exe, kind = ref_binary()
     p, b = model_paths()
     h, w, c = img.shape
@@ -75,7 +76,22 @@ def run_cpu_reference(img, tilesize, threads):
         r = subprocess.run([exe, p, b, fi, str(w), str(h), str(c), fo, str(tilesize), "0", str(threads)], capture_output=True, text=True)
         if r.returncode:
             raise RuntimeError("reference CPU run failed: " + r.stderr[-400:])
-        return json.loads(r.stdout.strip().splitlines()[-1])["seconds"], kind, os.path.basename(exe)
+        secs = json.loads(r.stdout.strip().splitlines()[-1])["seconds"]
+        if want_output:
+            return secs, kind, os.path.basename(exe), np.fromfile(fo, dtype=np.uint8).reshape(h * 4, w * 4, c)
+        return secs, kind, os.path.basename(exe)
+
+
+PADDED_PX = 8 * 420 * 420 + 2 * 340 * 420 + 4 * 420 * 300 + 340 * 300  # network-input pixels of the 15 padded tiles
+
+
+def workload_config(world):
+    """the `config` object of the bench line -- identical in both arms (--impl ours / reference)"""
+    return {"workload": "configs[1]: one 1920x1080 RGB image per GPU per step, models-DF2K, scale 4, tile 400 (15 padded tiles, "
+                        "%d network-input px)" % PADDED_PX,
+            "l2": "no flush needed: one step streams ~280 GB of activations through the memory system (~2.3 M px x 351 layers), far above "
+                  "the 126 MB L2",
+            "parallelism": "dp%d (one image per rank, weights broadcast over NCCL at init only)" % world}
 
 
 _BEST_THREADS = None
@@ -130,9 +146,13 @@ def bench_reference(args, rank, world):
         return
     threads = best_cpu_threads()
     img = np.random.default_rng(1000).integers(0, 256, (IMG_H, IMG_W, 3), dtype=np.uint8)
-    S = 96
+    # Bounded sample per step, SAME tile shapes as the workload: a 400x400 crop at tile=400 is one 420x420 padded tile (the
+    # shape of 8 of the workload's 15 tiles, ~20 s of CPU work); when K + W of those would not finish in a few minutes the
+    # step falls back to a 200x200 crop (one 220x220 padded tile, ~5 s).  out-MP/s is per padded pixel the same work.
+    warm = min(args.warmup, 1)
+    S = 400 if (args.steps + warm) * 22.0 <= 240.0 else 200
     sample = np.ascontiguousarray(img[:S, :S])
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(warm):
         run_cpu_reference(sample, TILE, threads)
     secs, kind, exe = [], None, None
     for _ in range(args.steps):
@@ -141,11 +161,12 @@ def bench_reference(args, rank, world):
     mp = S * 4 * S * 4 / 1e6
     ms = 1e3 * sum(secs) / len(secs)
     v = mp / (ms * 1e-3)
-    desc = "%dx%d crop of the workload image, tile=%d (one %dx%d padded tile) per step, %s" % (S, S, TILE, S + 20, S + 20, exe)
+    desc = "%dx%d crop of the workload image at tile=%d (one %dx%d padded tile) per step, %s, %d OpenMP threads (fastest of 4/8/16/32 on this " \
+           "host, %d logical cores)" % (S, S, TILE, S + 20, S + 20, exe, threads, os.cpu_count() or 1)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 1920x1080 RGB, models-DF2K, scale 4, tile 400 -- bounded CPU sample: " + desc},
+        "config": workload_config(max(1, args.gpus)),
         "cpu_baseline": {"value": v, "unit": "MP/s", "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -225,8 +246,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1])
 
+    # what the reference's caller hands over: plain malloc'd pixels (stb decoder, main.cpp:243,:275) and an ncnn::Mat
+    # (posix_memalign, main.cpp:276) -- pageable host memory
+    p_in = img.copy()
+    p_out = np.empty((IMG_H * 4, IMG_W * 4, 3), dtype=np.uint8)
+    p_out[:] = 0  # touch the pages once, like a caller that reuses its buffers
     run_dev = lambda: eng.process_device(d_in.data_ptr(), IMG_W, IMG_H, 3, d_out.data_ptr())
     run_e2e = lambda: eng.process_ptr(h_in.data_ptr(), IMG_W, IMG_H, 3, h_out.data_ptr())
+    run_e2e_pageable = lambda: eng.process(p_in, p_out)
 
     for _ in range(W):
         run_dev()
@@ -245,9 +272,11 @@ def main():
     for _ in range(2):
         run_e2e()
     e2e_dev_ms, e2e_wall_ms = timed(run_e2e, args.steps)
+    run_e2e_pageable()
+    pg_dev_ms, pg_wall_ms = timed(run_e2e_pageable, args.steps)
     sampler.stop_flag = True
     sampler.join()
-    same = bool(torch.equal(h_out.cuda(), d_out))
+    same = bool(torch.equal(h_out.cuda(), d_out)) and bool(np.array_equal(p_out, h_out.numpy()))
 
     # dominant kernel, timed live with CUDA events around every conv launch (separate steps: the extra events serialise
     # launch tails, so they are kept out of the headline region)
@@ -258,6 +287,7 @@ def main():
         conv_ms.append(eng.last_ms(1))
     eng.set_option("time_convs", 0)
     conv_ms = float(np.median(conv_ms))
+    n_conv_launches = eng.last_conv_launches()
     if world > 1:
         t = torch.tensor([conv_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -270,38 +300,51 @@ def main():
         else:
             peak, peak_src = 1400.0, "B200_PROFILING.md fallback, sustained (of fallback)"
         achieved = FLOP_PER_PADDED_PX * padded / (conv_ms * 1e-3) / 1e12
-        n_conv_launches = 350 * 4  # 350 tensor-core convs x 4 shape batches of the 15 tiles
-        traffic = None
-        tf = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
-        if os.path.exists(tf):
-            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+        # DRAM bytes per conv launch cannot be measured by this run (no ncu inside bench.py): the figure is read from the
+        # committed ncu --set full capture of the same build and labelled as such
+        traffic, traffic_src = None, None
+        for tf in ("r2_conv_traffic.json", "r1_conv_traffic.json"):
+            if os.path.exists(os.path.join(ROOT, "profiles", tf)):
+                traffic = json.load(open(os.path.join(ROOT, "profiles", tf))).get("dram_bytes_per_launch")
+                traffic_src = "profiles/%s (ncu --set full capture, step average per conv launch; not measured by this run)" % tf
+                break
         ms_step = dev_ms / args.steps
         line = {
             "metric": METRIC, "value": OUT_MP * world / (ms_step * 1e-3), "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: one 1920x1080 RGB image per GPU per step, models-DF2K, scale 4, tile 400 (15 padded tiles, "
-                                   "%d network-input px)" % padded,
-                       "engine_options": engine_options or "defaults",
-                       "precision": "fp16 operands / fp32 accumulate on tcgen05, fp32 Conv_0 and fp32 residual stream",
-                       "l2": "no flush needed: one step streams ~6 GB of activations through HBM, far above the 126 MB L2",
-                       "timing": "CUDA events on the engine's stream around every call, summed over the K steps, max over ranks; "
-                                 "wall clock of the same region %.2f ms/step" % (wall_ms / args.steps),
-                       "parallelism": "dp%d (one image per rank, weights broadcast over NCCL at init only)" % world},
+            "config": workload_config(world),
+            "engine_options": engine_options or "defaults",
+            "precision": "fp16 operands / fp32 accumulate on tcgen05, fp32 Conv_0, fp32 RRDB skip stream",
+            "timing": "CUDA events on the engine's stream around every call, summed over the K steps, max over ranks; "
+                      "wall clock of the same region %.2f ms/step" % (wall_ms / args.steps),
             "e2e": {"value": OUT_MP * world / (e2e_dev_ms / args.steps * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": IMG_W * IMG_H * 3,
                     "d2h_bytes_per_step": IMG_W * IMG_H * 3 * 16, "ms_per_step": e2e_dev_ms / args.steps,
                     "wall_ms_per_step": e2e_wall_ms / args.steps, "host_buffers": "pinned", "matches_device_path": same},
+            # the same call with PAGEABLE caller buffers (what ncnn::Mat / the decoders give the reference's proc stage): wall clock
+            "e2e_pageable": {"value": OUT_MP * world / (pg_wall_ms / args.steps * 1e-3), "unit": "MP/s", "wall_ms_per_step": pg_wall_ms / args.steps,
+                             "device_ms_per_step": pg_dev_ms / args.steps, "host_buffers": "pageable (numpy malloc)"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "conv3x3_tc2_kernel (tcgen05.mma cta_group::2, M=256 over an SM pair)", "launches_per_step": n_conv_launches,
+                         "traffic_source": traffic_src,
+                         "kernel": "conv3x3_kernel (csrc/conv3x3.cu: tcgen05.mma cta_group::2, M=256 over an SM pair)", "launches_per_step": n_conv_launches,
                          "avg_launch_ms": conv_ms / n_conv_launches, "peak_source": peak_src,
                          "flops_per_step": FLOP_PER_PADDED_PX * padded},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = best_cpu_threads()
             sample = np.ascontiguousarray(img[:400, :400])
-            secs, kind, exe = run_cpu_reference(sample, TILE, threads)
+            secs, kind, exe, ref_out = run_cpu_reference(sample, TILE, threads, want_output=True)
+            # parity at the shape the bench times: the engine on the same 400x400 crop (one 420x420 padded tile) vs the reference
+            # CPU path's output (uniform-noise contract of SURVEY 8c: max <= 2 LSB, >= 99.99 % of bytes within 1 LSB)
+            mine = np.zeros_like(ref_out)
+            if eng.process(sample, mine):
+                raise SystemExit("rsr_process failed: " + eng.last_error())
+            d = np.abs(mine.astype(np.int16) - ref_out.astype(np.int16))
+            line["parity"] = {"vs": exe, "shape": "400x400 crop, tile 400 (420x420 padded tile)", "max_abs_diff": int(d.max()),
+                              "frac_bytes_differ": float((d > 0).mean()), "bytes_gt1": int((d > 1).sum()), "bytes": int(d.size),
+                              "contract_met": bool(d.max() <= 2 and (d > 1).sum() <= max(2, d.size // 10000))}
             line["cpu_baseline"] = {"value": 2.56 / secs, "unit": "MP/s", "cores": threads, "kind": kind, "seconds": secs,
                                     "sample": "one 400x400 crop of the workload image at tile=400 (420x420 padded tile, the shape of 8 of the 15 "
                                               "tiles; 2.56 out-MP), %s, %d OpenMP threads (fastest of 4/8/16/32 on this host, %d logical cores); whole-image figure extrapolates "

@@ -94,6 +94,8 @@ RSR_API long long rsr_kernel_launches(const rsr_handle* h);
 RSR_API double rsr_last_ms(const rsr_handle* h, int what /*0 total, 1 conv kernels*/);
 /* Network-input ("padded LR") pixels processed by the last call, x8 in TTA mode: the roofline work unit. */
 RSR_API long long rsr_last_padded_pixels(const rsr_handle* h);
+/* Tensor-core conv kernel launches of the last rsr_process* call (the launches rsr_last_ms(h, 1) sums over). */
+RSR_API long long rsr_last_conv_launches(const rsr_handle* h);
 /* Engine options: "max_batch" (tiles per launch), "conv_impl" (2 = CTA-pair kernel, default; 1 = single-CTA .ws kernel),
  * "residual_fp16" (1 default / 0: fp32 copy of the RDB input for the RDB-level residual), "time_convs" (CUDA events
  * around every conv launch), "debug_mask"

@@ -11,6 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 REF = os.path.join(ROOT, "oracle", "_ref", "oracle_ref_avx2")
+REF512 = os.path.join(ROOT, "oracle", "_ref", "oracle_ref_avx512")  # what bench.py's CPU arm runs on an AVX-512 host
 
 
 def noise(h, w, seed):
@@ -28,13 +29,14 @@ def natural(h, w, seed):
     return np.clip(np.rint(b), 0, 255).astype(np.uint8)
 
 
-def run_ref(img, model, tilesize, tta, threads=8):
+def run_ref(img, model, tilesize, tta, threads=8, exe=None):
+    exe = exe or REF
     h, w, c = img.shape
     with tempfile.TemporaryDirectory() as td:
         fi, fo = os.path.join(td, "i.raw"), os.path.join(td, "o.raw")
         img.tofile(fi)
         mdir = os.path.join(ROOT, "models", model)
-        r = subprocess.run([REF, os.path.join(mdir, "x4.param"), os.path.join(mdir, "x4.bin"), fi, str(w), str(h),
+        r = subprocess.run([exe, os.path.join(mdir, "x4.param"), os.path.join(mdir, "x4.bin"), fi, str(w), str(h),
                             str(c), fo, str(tilesize), str(int(tta)), str(threads)], capture_output=True, text=True)
         if r.returncode:
             raise SystemExit(r.stderr)
@@ -77,6 +79,10 @@ def main():
     # disagree arbitrarily (probed: 10x10, 1x1), the engine clamps; 11 px is the first well-defined size
     cases.append(("noise_12x11_df2k_tta_t32", noise(11, 12, 1008), "models-DF2K", 32, 1))
     cases.append(("noise_45x11_jpeg_t32", noise(11, 45, 1009), "models-DF2K_JPEG", 32, 0))
+    # shapes the benchmark times: one 420x300 padded tile of BASELINE configs[1] (tile 400), and a TTA
+    # 100x140 edge tile of configs[4] (tile 200; variants 4..7 run it transposed)
+    cases.append(("cfg2_tile_420x300_natural_df2k_t400", natural(280, 400, 1010), "models-DF2K", 400, 0))
+    cases.append(("cfg5_tta_edge_100x140_natural_df2k_t200", natural(120, 80, 1011), "models-DF2K", 200, 1))
     only_new = "--only-new" in sys.argv
     manifest = {"generator": "oracle/gen_golden.py", "reference_binary": "oracle/_ref/oracle_ref_avx2 (ncnn b4ba207, AVX2+FMA, OpenMP)",
                 "prepadding": 10, "cases": []}
@@ -91,10 +97,30 @@ def main():
             continue
         out, info = run_ref(img, model, ts, tta)
         np.save(os.path.join(GOLD, name + ".in.npy"), img)
-        np.save(os.path.join(GOLD, name + ".out.npy"), out)
+        if out.size > (4 << 20):  # large outputs are stored compressed (tests/common.py golden() reads either form)
+            np.savez_compressed(os.path.join(GOLD, name + ".out.npz"), out=out)
+        else:
+            np.save(os.path.join(GOLD, name + ".out.npy"), out)
         manifest["cases"].append({"name": name, "model": model, "tilesize": ts, "tta": tta, "h": img.shape[0],
                                   "w": img.shape[1], "c": int(img.shape[2]), "ref_seconds": info["seconds"]})
         print(name, info["seconds"], "s")
+    # ISA cross-check (ncnn's conv kernels, hence the bit pattern, depend on the ISA): the goldens are the AVX2
+    # build's outputs; the AVX-512 build (pack16 Winograd) is run on every case and its byte differences are recorded, so the
+    # contract "vs the reference CPU path" is pinned for both builds
+    if "--cross-isa" in sys.argv and os.path.exists(REF512) and " avx512f" in open("/proc/cpuinfo").read():
+        byname = {c[0]: c for c in cases}
+        for c in manifest["cases"]:
+            if "avx512_vs_avx2" in c and only_new:
+                continue
+            name, img, model, ts, tta = byname[c["name"]]
+            f = os.path.join(GOLD, name + ".out.npy")
+            gold = np.load(f) if os.path.exists(f) else np.load(os.path.join(GOLD, name + ".out.npz"))["out"]
+            out512, _ = run_ref(img, model, ts, tta, exe=REF512)
+            d = np.abs(out512.astype(np.int16) - gold.astype(np.int16))
+            c["avx512_vs_avx2"] = {"max": int(d.max()), "bytes_differ": int((d > 0).sum()), "bytes": int(d.size)}
+            print(name, "avx512 vs avx2:", c["avx512_vs_avx2"])
+        manifest["isa_note"] = ("goldens = AVX2 build; avx512_vs_avx2 = byte differences of the AVX-512 build (ncnn pack16 Winograd) on the same "
+                                "input, generated on " + manifest["host_cpu"])
     json.dump(manifest, open(os.path.join(GOLD, "manifest.json"), "w"), indent=1)
 
 

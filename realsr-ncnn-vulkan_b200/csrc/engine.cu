@@ -97,6 +97,7 @@ struct rsr_handle {
     // stats
     long long launches = 0;
     double last_ms = 0, last_conv_ms = 0;
+    long long last_conv_launches = 0;  // tensor-core conv launches of the last call
     long long last_padded = 0;
 };
 
@@ -212,7 +213,7 @@ struct BatchCtx {
     rsr_handle* h;
     Workspace* ws;
     int tilesize, prepadding;  // snapshot of the handle's parameters taken (under its mutex) when the call started
-    long long launches = 0;
+    long long launches = 0, conv_launches = 0;
     size_t nconv_ev = 0;
 };
 
@@ -258,6 +259,7 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
     }
     if (e1) CK(cudaEventRecord(e1, c.ws->stream));
     c.launches++;
+    c.conv_launches++;
     return 0;
 }
 
@@ -524,7 +526,7 @@ int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_
 
 // tiles [tile_first, tile_first + tile_count) of the reference's row-major tile grid; `done` (optional) receives their descriptors
 int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, int hh, int ch, uint8_t* d_out, long long* padded_out,
-                      long long* launches_out, int tile_first, int tile_count, std::vector<TileDesc>* done, size_t* nconv_ev_out, int T, int P)
+                      long long* launches_out, int tile_first, int tile_count, std::vector<TileDesc>* done, size_t* nconv_ev_out, long long* conv_launches_out, int T, int P)
 {
     const int xtiles = (w + T - 1) / T, ytiles = (hh + T - 1) / T;
     // tile grid: reference src/realsr.cpp:170-171,:176-187,:235-241 (GPU) == :537-553 (CPU)
@@ -709,6 +711,7 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
     }
     *padded_out = padded;
     *launches_out = c.launches;
+    *conv_launches_out = c.conv_launches;
     *nconv_ev_out = c.nconv_ev;  // the per-conv events are read by the caller AFTER it has synchronised the stream
     return 0;
 }
@@ -871,7 +874,8 @@ static int process_impl(rsr_handle* h, const uint8_t* in, int w, int hh, int c, 
         if (host_buffers) CK(cudaMemcpyAsync(ws->img_in.p, in, in_bytes, cudaMemcpyHostToDevice, ws->stream));
         std::vector<TileDesc> done;
         size_t nconv_ev = 0;
-        if ((rr = process_on_device(h, ws, d_in, w, hh, c, d_out, &padded, &launches, tile_first, tile_count, whole ? nullptr : &done, &nconv_ev, T, P))) return rr;
+        long long conv_launches = 0;
+        if ((rr = process_on_device(h, ws, d_in, w, hh, c, d_out, &padded, &launches, tile_first, tile_count, whole ? nullptr : &done, &nconv_ev, &conv_launches, T, P))) return rr;
         if (host_buffers) {
             if (whole) {
                 CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ws->stream));
@@ -896,6 +900,7 @@ static int process_impl(rsr_handle* h, const uint8_t* in, int w, int hh, int c, 
         std::lock_guard<std::mutex> g(h->mu);
         h->last_ms = ms;
         if (h->time_convs) h->last_conv_ms = conv_ms;
+        h->last_conv_launches = conv_launches;
         h->last_padded = padded;
         h->launches += launches;
         return 0;
@@ -929,6 +934,7 @@ const char* rsr_last_error(const rsr_handle* h) { return h ? h->err.c_str() : "n
 long long rsr_kernel_launches(const rsr_handle* h) { return h ? h->launches : 0; }
 double rsr_last_ms(const rsr_handle* h, int what) { return !h ? 0.0 : (what == 1 ? h->last_conv_ms : h->last_ms); }
 long long rsr_last_padded_pixels(const rsr_handle* h) { return h ? h->last_padded : 0; }
+long long rsr_last_conv_launches(const rsr_handle* h) { return h ? h->last_conv_launches : 0; }
 
 int rsr_set_option(rsr_handle* h, const char* key, long long value)
 {

@@ -57,6 +57,8 @@ def load_library():
     lib.rsr_last_ms.argtypes = [vp, ci]
     lib.rsr_last_padded_pixels.restype = ll
     lib.rsr_last_padded_pixels.argtypes = [vp]
+    lib.rsr_last_conv_launches.restype = ll
+    lib.rsr_last_conv_launches.argtypes = [vp]
     lib.rsr_set_option.restype = ci
     lib.rsr_set_option.argtypes = [vp, cc, ll]
     lib.rsr_debug_conv.restype = ci
@@ -150,6 +152,9 @@ class RealSR:
 
     def last_padded_pixels(self):
         return int(self._lib.rsr_last_padded_pixels(self._h))
+
+    def last_conv_launches(self):
+        return int(self._lib.rsr_last_conv_launches(self._h))
 
     def debug_conv(self, conv_index, x16, cout):
         """runs one conv layer of the loaded model on the tensor-core kernel: x16 (H, W, cin) float16 -> (H, W, cout) float32"""
