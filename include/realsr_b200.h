@@ -96,14 +96,10 @@ RSR_API double rsr_last_ms(const rsr_handle* h, int what /*0 total, 1 conv kerne
 RSR_API long long rsr_last_padded_pixels(const rsr_handle* h);
 /* Tensor-core conv kernel launches of the last rsr_process* call (the launches rsr_last_ms(h, 1) sums over). */
 RSR_API long long rsr_last_conv_launches(const rsr_handle* h);
-/* Engine options: "max_batch" (tiles per launch), "conv_impl" (2 = CTA-pair kernel, default; 1 = single-CTA .ws kernel),
- * "residual_fp16" (1 default / 0: fp32 copy of the RDB input for the RDB-level residual), "time_convs" (CUDA events
- * around every conv launch), "debug_mask"
- * (timing experiments only, results become garbage: 1 = skip MMAs, 2 = skip activation loads, 4 = skip weight loads,
- * 8 = skip epilogue loads/stores).
- * Opt-in kernel / scheduling variants, default 0, bit-identical results by construction but not yet run on hardware (see
- * DESIGN.md section 6, csrc/conv_tc2x.cu): "epilogue_split", "merge_shapes", "serpentine"; "conv_impl" 3 = 32-channel
- * K-blocks.  Unknown keys and out-of-range values return RSR_ERR_GENERIC. */
+/* Engine options: "max_batch" (tiles per job, 0 = auto), "merge_shapes" (1 default: one launch per layer over all shape groups of a
+ * frame; 0: one job per shape group), "residual_fp16" (1 default / 0: fp32 copy of the RDB input for the RDB-level residual),
+ * "time_convs" (CUDA events around every conv launch), "debug_mask" (timing experiments only, results become garbage: 1 = skip
+ * MMAs, 2 = skip activation loads, 4 = skip weight loads, 8 = skip epilogue stores).  Unknown keys return RSR_ERR_GENERIC. */
 RSR_API int rsr_set_option(rsr_handle* h, const char* key, long long value);
 
 /* Test hook: runs ONE 3x3 convolution of the loaded model (index in file order, >= 1) on the tensor-core kernel.
@@ -114,13 +110,7 @@ RSR_API int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, 
 /* Host-only checks (no GPU needed): parse + verify a .param/.bin pair exactly as rsr_load() does.
  * On success returns 0 and fills num_rrdb / num_convs; on failure returns RSR_ERR_MODEL and writes the reason to err. */
 RSR_API int rsr_check_model(const char* parampath, const char* modelpath, int* num_rrdb, int* num_convs, char* err, int errlen);
-/* Host-only: shape of conv #conv_index (file order) and, if `packed` is non-NULL, its weights in the swizzled
- * [chunk][tap][cout_pad][64] fp16 layout the tensor-core kernel streams (capacity in uint16 elements).
- * Returns the number of uint16 elements of the packed image, or a negative code. */
-RSR_API long long rsr_debug_pack(const char* parampath, const char* modelpath, int conv_index, int* cin, int* cout, int* cout_pad,
-                                 uint16_t* packed, long long capacity);
-
-/* Host-only: the same conv's weights as the plain row-major [rows][64] fp16 matrix the CTA-pair kernel fetches by TMA
+/* Host-only: conv #conv_index's weights (file order, >= 1) as the plain row-major [rows][64] fp16 matrix the conv kernel fetches by TMA
  * (rows grouped per (64-channel plane, ky): Cout=64 -> 192 rows, Cout<=32 -> 96, Cout<=16 -> 64; see model.h).
  * Returns the number of rows (packed may be NULL), or a negative code. */
 RSR_API long long rsr_debug_pack_rows(const char* parampath, const char* modelpath, int conv_index, uint16_t* packed, long long capacity);

@@ -7,7 +7,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden,-Wall -ccbin /usr/bin/g++"
 mkdir -p build
 pids=()
-for f in conv_tc.cu conv_tc2.cu conv_tc2x.cu conv3x3.cu misc_kernels.cu engine.cu; do
+for f in conv3x3.cu misc_kernels.cu engine.cu; do
   $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f -o build/${f%.cu}.o &
   pids+=($!)
 done
@@ -15,7 +15,7 @@ done
 pids+=($!)
 for p in "${pids[@]}"; do wait $p; done
 # link to a temporary name and rename: a gpurun snapshot taken during a rebuild never sees a half-written library
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT.tmp build/conv_tc.o build/conv_tc2.o build/conv_tc2x.o build/conv3x3.o build/misc_kernels.o build/engine.o build/model.o -ccbin /usr/bin/g++
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT.tmp build/conv3x3.o build/misc_kernels.o build/engine.o build/model.o -ccbin /usr/bin/g++
 mv -f $OUT.tmp $OUT
 echo "built $(realpath $OUT)"
 # host-side C++ mirror of the reference interface (class RealSR over the C ABI) + a minimal caller written like the

@@ -18,12 +18,16 @@
 //   * B operand: each CTA keeps ITS half of the conv's weights resident in smem for the whole launch (B is split N/2 + N/2
 //     between the two CTAs of a pair), fetched once by TMA before the grid dependency is resolved.
 //   * Warp roles (12 warps): warp 0 A producer (TMA), warp 1 MMA issuer (leader CTA), warp 2 weight fetch, warps 4..11
-//     epilogue in two groups of four that alternate work tiles (one per accumulator set).  setmaxnreg moves registers
-//     from the control warpgroup to the epilogue warpgroups.
-//   * Early accumulator hand-back (Cout=32 and the Cout=64 bias/activation convs): an epilogue group first pulls BOTH
-//     M-tiles of its set into registers (taps combined), returns the set to the MMA issuer, and only then does
-//     bias / activation / pack / store -- per-tile timestamps showed the chain "MMAs done -> whole epilogue -> hand-back"
-//     bounding the Cout=32 convs at 2.6 k clk per tile where their MMAs need 1.2 k.
+//     epilogue.  setmaxnreg moves registers from the control warpgroup to the epilogue warpgroups.
+//   * Epilogue of the bias/activation convs (CONV_STORE16: 4 of the 5 convs of a dense block + the tail): one (M-tile, row)
+//     unit per warp, EARLY accumulator hand-back -- the warp pulls its 32 positions x 96/128 columns into registers (taps
+//     combined), returns the set to the MMA issuer and only then does activation / pack / store -- and the row leaves through
+//     a swizzled staging buffer and one TMA store.  Per-tile timestamps of the round-1 scheme showed the chain "MMAs done ->
+//     whole epilogue -> hand-back" bounding the Cout=32 convs at 2.6 k clk per tile where their MMAs need 1.2 k.
+//     The residual / post-processing modes (conv5, trunk, last conv: bounded by their MMAs or by HBM) keep two 4-warp groups
+//     that alternate work tiles, one per accumulator set.
+//   * Tile geometry is walked incrementally (add-with-carry per tile; integer divisions only when a merged launch enters a
+//     new shape group).
 //   * The MMA issuer's loop carries no divisions, no tile geometry and no 64-bit descriptor arithmetic: stage index and
 //     barrier parities are counters, descriptors are {lo32 = base + immediate, hi32 = constant}.
 //   * Merged multi-shape launches: one launch per layer covers up to four same-shape tile groups (ConvArgs::grp), so a frame
@@ -43,28 +47,30 @@ namespace {
 
 constexpr int P = CONV_P;
 constexpr int BW = P - 2;
-constexpr int BH = 8;                         // output rows per CTA
-constexpr int BAND = 2 * BH;                  // output rows per CTA pair
-constexpr int MT = BH * P / 128;              // 2 M-tiles per CTA
+constexpr int KB = 32;                        // K-block: input channels per A stage / per resident weight block (SWIZZLE_64B boxes)
+// Work-tile height per CTA: 8 rows (two M-tiles) for the N = 96 / 64 convs, 4 rows (one M-tile) for the Cout = 64 convs, whose
+// single N = 192 MMA per k-step needs 192 TMEM columns per M-tile (two accumulator sets = 384 of the 512 columns).
+__host__ __device__ constexpr int bh_of(int nreal) { return conv_bh(nreal); }
+__host__ __device__ constexpr int mma_n(int nreal) { return nreal == 64 ? 192 : (nreal == 32 ? 96 : 64); }   // three stacked kx taps
+__host__ __device__ constexpr int dcols_of(int nreal) { return nreal == 64 ? 192 : 128; }                    // TMEM columns per M-tile
 constexpr int NA_MAX = 8;                     // A stages (run-time count: as many as fit next to the resident weights)
-__host__ __device__ constexpr int na_max(int kb) { return kb == 64 ? 4 : 8; }
-__host__ __device__ constexpr int a_bytes(int kb) { return (BH + 2) * P * kb * 2; }   // 40 KB / 20 KB
-__host__ __device__ constexpr int a_slack(int kb) { return kb == 64 ? 1024 : 512; }    // zeroed rows behind the box (kx taps of the last positions)
-__host__ __device__ constexpr int a_stage(int kb) { return a_bytes(kb) + a_slack(kb); }
+__host__ __device__ constexpr int a_bytes(int bh) { return (bh + 2) * P * KB * 2; }   // 20 KB (8 rows) / 12 KB (4 rows)
+constexpr int A_SLACK = 512;                  // zeroed rows behind the box (kx taps of the last, never stored, positions)
+__host__ __device__ constexpr int a_stage(int bh) { return a_bytes(bh) + A_SLACK; }
 constexpr int NEPI = 8;                       // epilogue warps
 constexpr int EPI_WARP0 = 4;                  // first epilogue warp: warps 0..3 are the control warpgroup
 constexpr int NTHREADS = (EPI_WARP0 + NEPI) * 32;
-constexpr int STAGE_BYTES = 32 * 20 * 4;
-constexpr int DCOLS = 128;                    // TMEM columns per M-tile
-constexpr int ACC_COLS = MT * DCOLS;          // 256 per accumulator set
-constexpr int TMEM_COLS = 2 * ACC_COLS;
+// epilogue staging per warp: CONV_STORE16 stages one 32-pixel row of its output as a dense, swizzled TMA-store source
+// (32 x Cout fp16); the other modes transpose 32 x 16 words through a padded tile
+__host__ __device__ constexpr int stage_bytes(int nreal, int mode) { return mode == CONV_STORE16 ? 32 * nreal * 2 : 32 * 20 * 4; }
+constexpr int TMEM_COLS = 512;
 constexpr int SMEM_MAX = 227 * 1024 - 1024;   // dynamic part; the kernel also has ~300 B of static shared memory
-constexpr int SMEM_FIXED = 1024 /*align*/ + NEPI * STAGE_BYTES + 256 /*barriers*/;
+__host__ __device__ constexpr int smem_fixed(int nreal, int mode) { return 1024 /*align*/ + NEPI * stage_bytes(nreal, mode) + 256 /*barriers*/; }
 constexpr int REGS_CTRL = 64, REGS_EPI = 216; // setmaxnreg: 128 x 64 + 256 x 216 <= 64 K registers
 
-// this CTA's half of the weights of one (64-channel plane, ky): Cout=64 -> pair half (64 rows) + single half (32 rows);
-// Cout<=32 -> triple half (48 rows, padded to 64); Cout<=16 -> 32 rows.  A 32-channel K-block holds half of each row.
-__host__ __device__ constexpr int w_bytes_per_ky(int nreal, int kb) { return (nreal == 64 ? 12288 : (nreal == 32 ? 6144 : 4096)) * kb / 64; }
+// this CTA's half (N/2 rows of 32 channels) of the weights of one (K-block, ky): Cout=64 -> 96 rows, Cout<=32 -> 48 rows (padded
+// to 3072 B so that every block stays 512-B aligned for SWIZZLE_64B), Cout<=16 -> 32 rows
+__host__ __device__ constexpr int w_bytes_per_ky(int nreal) { return nreal == 64 ? 6144 : (nreal == 32 ? 3072 : 2048); }
 
 struct Bars {
     uint64_t a_full[NA_MAX], a_empty[NA_MAX];
@@ -103,64 +109,116 @@ __device__ __forceinline__ void umma2_commit_if(uint64_t* bar, uint16_t mask, ui
         : "memory");
 }
 
-// Where work tile `tt` lives: image b of its group, band by, column tile tx, the group's image size, pixel offset and maps.
-struct TileGeo {
-    int b, by, tx, H, W, desc0, g;
+// Incremental walk over the work tiles of one warp role: logical indices u0, u0 + stride, ... < ntiles, physical tile t = u, or
+// t = ntiles-1-u when the launch walks backwards (ConvArgs::reverse: the engine alternates the direction from one conv to the next,
+// so that a conv starts on the pixels the previous conv touched last -- the part of its inputs that is still in the 126 MB L2; the
+// 32-output-channel convs run at 5.3-6.2 TB/s of DRAM traffic, i.e. they are HBM-bound).  A tile index decodes to (group g, image b
+// of the group, band by, column tile tx); the per-tile path is three add-with-carry steps, the integer divisions run only when the
+// walk enters a new shape group (merged launches: at most four times per launch).
+struct Walk {
+    int u, t, gstart, gend, g;
+    int b, by, tx;
+    int tiles_x, bands_y, H, W, desc0;
+    int sb, sby, stx;  // the stride decomposed in this group's (image, band, column) grid
     size_t pxoff, aux;
 };
-__device__ __forceinline__ TileGeo decode_tile(const ConvArgs& a, const int tt, const int tiles_per_img, const int tiles_x)
+__device__ __forceinline__ void walk_seek(Walk& w, const ConvArgs& a, const int u, const int stride, const int ntiles, const int tiles_x0, const int bands_y0)
 {
-    TileGeo r;
+    int t0 = 0, tpi;
+    const int t = a.reverse ? ntiles - 1 - u : u;
+    w.u = u;
+    w.t = t;
     if (a.ngroups > 0) {
         int g = 0;
 #pragma unroll
         for (int k = 1; k < 4; k++)
-            if (k < a.ngroups && tt >= a.grp[k].tile_start) g = k;
+            if (k < a.ngroups && t >= a.grp[k].tile_start) g = k;
         // explicit selects: a dynamically indexed kernel parameter would be copied to local memory
-        const int H = g == 0 ? a.grp[0].H : g == 1 ? a.grp[1].H : g == 2 ? a.grp[2].H : a.grp[3].H;
-        const int W = g == 0 ? a.grp[0].W : g == 1 ? a.grp[1].W : g == 2 ? a.grp[2].W : a.grp[3].W;
-        const int tx_n = g == 0 ? a.grp[0].tiles_x : g == 1 ? a.grp[1].tiles_x : g == 2 ? a.grp[2].tiles_x : a.grp[3].tiles_x;
-        const int tpi = g == 0 ? a.grp[0].tiles_per_img : g == 1 ? a.grp[1].tiles_per_img : g == 2 ? a.grp[2].tiles_per_img : a.grp[3].tiles_per_img;
-        const int t0 = g == 0 ? a.grp[0].tile_start : g == 1 ? a.grp[1].tile_start : g == 2 ? a.grp[2].tile_start : a.grp[3].tile_start;
-        r.desc0 = g == 0 ? a.grp[0].desc0 : g == 1 ? a.grp[1].desc0 : g == 2 ? a.grp[2].desc0 : a.grp[3].desc0;
-        r.pxoff = (size_t)(g == 0 ? a.grp[0].px_off : g == 1 ? a.grp[1].px_off : g == 2 ? a.grp[2].px_off : a.grp[3].px_off);
-        r.aux = (size_t)(g == 0 ? a.grp[0].aux_off : g == 1 ? a.grp[1].aux_off : g == 2 ? a.grp[2].aux_off : a.grp[3].aux_off);
-        const int lt = tt - t0;
-        r.b = lt / tpi;
-        const int rem = lt - r.b * tpi;
-        r.by = rem / tx_n;
-        r.tx = rem - r.by * tx_n;
-        r.H = H; r.W = W; r.g = g;
+        w.H = g == 0 ? a.grp[0].H : g == 1 ? a.grp[1].H : g == 2 ? a.grp[2].H : a.grp[3].H;
+        w.W = g == 0 ? a.grp[0].W : g == 1 ? a.grp[1].W : g == 2 ? a.grp[2].W : a.grp[3].W;
+        w.tiles_x = g == 0 ? a.grp[0].tiles_x : g == 1 ? a.grp[1].tiles_x : g == 2 ? a.grp[2].tiles_x : a.grp[3].tiles_x;
+        tpi = g == 0 ? a.grp[0].tiles_per_img : g == 1 ? a.grp[1].tiles_per_img : g == 2 ? a.grp[2].tiles_per_img : a.grp[3].tiles_per_img;
+        t0 = g == 0 ? a.grp[0].tile_start : g == 1 ? a.grp[1].tile_start : g == 2 ? a.grp[2].tile_start : a.grp[3].tile_start;
+        w.desc0 = g == 0 ? a.grp[0].desc0 : g == 1 ? a.grp[1].desc0 : g == 2 ? a.grp[2].desc0 : a.grp[3].desc0;
+        w.pxoff = (size_t)(g == 0 ? a.grp[0].px_off : g == 1 ? a.grp[1].px_off : g == 2 ? a.grp[2].px_off : a.grp[3].px_off);
+        w.aux = (size_t)(g == 0 ? a.grp[0].aux_off : g == 1 ? a.grp[1].aux_off : g == 2 ? a.grp[2].aux_off : a.grp[3].aux_off);
+        w.gend = g + 1 >= a.ngroups ? a.ntiles_multi : (g == 0 ? a.grp[1].tile_start : g == 1 ? a.grp[2].tile_start : a.grp[3].tile_start);
+        w.bands_y = tpi / w.tiles_x;
+        w.g = g;
     } else {
-        r.b = tt / tiles_per_img;
-        const int rem = tt - r.b * tiles_per_img;
-        r.by = rem / tiles_x;
-        r.tx = rem - r.by * tiles_x;
-        r.H = a.H; r.W = a.W; r.desc0 = 0; r.g = 0; r.pxoff = 0; r.aux = 0;
+        w.H = a.H; w.W = a.W; w.tiles_x = tiles_x0; w.bands_y = bands_y0; tpi = tiles_x0 * bands_y0;
+        w.desc0 = 0; w.g = 0; w.pxoff = 0; w.aux = 0; w.gend = 0x7fffffff;
     }
-    return r;
+    w.gstart = t0;
+    const int lt = t - t0;
+    w.b = lt / tpi;
+    int rem = lt - w.b * tpi;
+    w.by = rem / w.tiles_x;
+    w.tx = rem - w.by * w.tiles_x;
+    w.sb = stride / tpi;
+    rem = stride - w.sb * tpi;
+    w.sby = rem / w.tiles_x;
+    w.stx = rem - w.sby * w.tiles_x;
+}
+__device__ __forceinline__ void walk_start(Walk& w, const ConvArgs& a, const int u0, const int stride, const int ntiles, const int tiles_x0, const int bands_y0)
+{
+    if (u0 < ntiles) walk_seek(w, a, u0, stride, ntiles, tiles_x0, bands_y0);
+    else w.u = ntiles;
+}
+__device__ __forceinline__ void walk_step(Walk& w, const ConvArgs& a, const int stride, const int ntiles, const int tiles_x0, const int bands_y0)
+{
+    const int u = w.u + stride;
+    w.u = u;
+    if (u >= ntiles) return;
+    if (!a.reverse) {
+        const int t = w.t + stride;
+        if (t >= w.gend) { walk_seek(w, a, u, stride, ntiles, tiles_x0, bands_y0); return; }
+        w.t = t;
+        w.tx += w.stx;
+        int c = w.tx >= w.tiles_x ? 1 : 0;
+        w.tx -= c ? w.tiles_x : 0;
+        w.by += w.sby + c;
+        c = w.by >= w.bands_y ? 1 : 0;
+        w.by -= c ? w.bands_y : 0;
+        w.b += w.sb + c;
+    } else {
+        const int t = w.t - stride;
+        if (t < w.gstart) { walk_seek(w, a, u, stride, ntiles, tiles_x0, bands_y0); return; }
+        w.t = t;
+        w.tx -= w.stx;
+        int c = w.tx < 0 ? 1 : 0;
+        w.tx += c ? w.tiles_x : 0;
+        w.by -= w.sby + c;
+        c = w.by < 0 ? 1 : 0;
+        w.by += c ? w.bands_y : 0;
+        w.b -= w.sb + c;
+    }
 }
 
-template <int NREAL, int MODE, int KB>
+template <int NREAL, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const int NA)
 {
-    constexpr int A_BYTES = a_bytes(KB), A_STAGE = a_stage(KB);
+    constexpr int BH = bh_of(NREAL);                 // output rows per CTA
+    constexpr int BAND = 2 * BH;                     // output rows per CTA pair
+    constexpr int MT = BH / 4;                       // M-tiles (128 positions = 4 rows x pitch 32) per CTA and work tile
+    constexpr int DCOLS = dcols_of(NREAL);           // TMEM columns per M-tile
+    constexpr int ACC_COLS = MT * DCOLS;             // per accumulator set (two sets)
+    constexpr int A_BYTES = a_bytes(BH), A_STAGE = a_stage(BH);
     constexpr int ROWB = KB * 2;                     // bytes per smem row of an operand tile (one pixel / one weight row)
-    constexpr int GOFF = 64 * ROWB;                  // Cout=64: offset of the single-tap group behind the 64 pair rows
-    constexpr int NGROUPS = NREAL == 64 ? 2 : 1;     // MMA groups per kernel row (pair + single, or one triple)
     constexpr int ROWS_PER_KY = NREAL == 64 ? 192 : (NREAL == 32 ? 96 : 64);  // weight rows per (plane, ky), see model.cpp
     constexpr int KSTEPS = KB / 16;
     // early accumulator hand-back (see header): the modes whose epilogue needs nothing but the accumulators
     constexpr bool EARLY = MODE == CONV_STORE16;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int nchunk = (a.cin + KB - 1) / KB;        // K-blocks
-    constexpr int W_KY = w_bytes_per_ky(NREAL, KB);
-    uint8_t* smA = smem;
-    uint8_t* smW = smem + NA * A_STAGE;              // resident weights: [K-block][ky] x W_KY bytes
-    uint8_t* smStage = smW + nchunk * 3 * W_KY;
-    Bars* bars = reinterpret_cast<Bars*>(smStage + NEPI * STAGE_BYTES);
+    const int nchunk = a.cin / KB;                   // K-blocks (Cin % 32 == 0 for every tensor-core conv of the net)
+    constexpr int W_KY = w_bytes_per_ky(NREAL);
+    constexpr int STAGE_BYTES = stage_bytes(NREAL, MODE);
+    uint8_t* smStage = smem;                         // epilogue staging first: 1024-B aligned (SWIZZLE_128B TMA-store source)
+    uint8_t* smA = smem + NEPI * STAGE_BYTES;
+    uint8_t* smW = smA + NA * A_STAGE;               // resident weights: [K-block][ky] x W_KY bytes
+    Bars* bars = reinterpret_cast<Bars*>(smW + nchunk * 3 * W_KY);
     __shared__ __align__(16) float s_bias[64];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,18 +232,21 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
     if (threadIdx.x == 0) {
         for (int i = 0; i < NA_MAX; i++) { mbar_init(&bars->a_full[i], 1); mbar_init(&bars->a_empty[i], 1); }
         mbar_init(&bars->w_full, 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], NEPI); }  // 4 warps per group x 2 CTAs
+        // hand-back arrivals per accumulator set: EARLY with two M-tiles: 8 warps x 2 CTAs per tile; otherwise the 4 warps of
+        // one group x 2 CTAs
+        for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], (EARLY && MT == 2) ? 2 * NEPI : NEPI); }
         mbar_fence_init();
-        for (int i = 0; i < 3; i++) tma_prefetch_desc(&maps.m[i]);
+        for (int i = 0; i < nchunk; i++) tma_prefetch_desc(&maps.m[i]);
         for (int g = 1; g < a.ngroups; g++)
-            for (int i = 0; i < 3; i++) tma_prefetch_desc(&maps.mg[g - 1][i]);
+            for (int i = 0; i < nchunk; i++) tma_prefetch_desc(&maps.mg[g - 1][i]);
         tma_prefetch_desc(&maps.w);
-        tma_prefetch_desc(&maps.w32);
+        if (EARLY)
+            for (int g = 0; g < (a.ngroups > 0 ? a.ngroups : 1); g++) tma_prefetch_desc(&maps.o[g]);
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + NREAL) s_bias[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
     // rows behind each A box: read by the kx=2 taps of the last two (never stored) positions; keep them finite
     {
-        constexpr int SL16 = a_slack(KB) / 16;  // uint4 per stage: 64 (KB=64, NA <= 4) or 32 (KB=32, NA <= 8): <= 256 threads
+        constexpr int SL16 = A_SLACK / 16;  // 32 uint4 per stage, NA <= 8: <= 256 threads
         if (threadIdx.x >= 128 && threadIdx.x < 128 + NA * SL16) {
             const int i = threadIdx.x - 128;
             reinterpret_cast<uint4*>(smA + (i / SL16) * A_STAGE + A_BYTES)[i % SL16] = make_uint4(0, 0, 0, 0);
@@ -209,13 +270,10 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                 if (is_leader) mbar_expect_tx(&bars->w_full, 2u * (uint32_t)(nchunk * 3 * W_KY));
                 for (int c = 0; c < nchunk; c++)
                     for (int ky = 0; ky < 3; ky++) {
-                        uint8_t* dst = smW + (c * 3 + ky) * W_KY;
-                        // weight rows are stored per (64-channel plane, ky); a 32-channel K-block is the left or right half of a row
-                        const int plane = KB == 64 ? c : (c >> 1), col = KB == 64 ? 0 : (c & 1) * 32;
-                        const int row0 = (plane * 3 + ky) * ROWS_PER_KY;
-                        if (NREAL == 16) tma2_load_2d(dst, &maps.w32, wbar, col, row0 + (int)rank * 32);
-                        else tma2_load_2d(dst, &maps.w, wbar, col, row0 + (int)rank * (NREAL == 32 ? 48 : 64));  // maps.w box: 48 rows for Cout<=32
-                        if (NREAL == 64) tma2_load_2d(dst + GOFF, &maps.w32, wbar, col, row0 + 128 + (int)rank * 32);
+                        // weight rows are stored per (64-channel plane, ky) as [W(ky,0) | W(ky,1) | W(ky,2)]; a 32-channel K-block
+                        // is the left or right half of a row; CTA r takes rows r*N/2 .. (r+1)*N/2-1 (maps.w box: N/2 rows)
+                        const int row0 = ((c >> 1) * 3 + ky) * ROWS_PER_KY;
+                        tma2_load_2d(smW + (c * 3 + ky) * W_KY, &maps.w, wbar, (c & 1) * 32, row0 + (int)rank * (mma_n(NREAL) / 2));
                     }
             } else if (is_leader && (a.debug_mask & 4) && lane == 0) {
                 mbar_arrive(&bars->w_full);
@@ -231,8 +289,9 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             // ---------------- A producer (both CTAs; bytes are counted on the leader's barrier) ----------------
             const bool leader = elect_one();
             uint32_t s = 0, ph = 1;  // stage counter and the parity to wait for on its "empty" barrier (first pass: free)
-            for (int t = cluster_id; t < ntiles; t += nclusters) {
-                const TileGeo geo = decode_tile(a, t, tiles_per_img, tiles_x);
+            Walk geo;
+            walk_start(geo, a, cluster_id, nclusters, ntiles, tiles_x, bands_y);
+            for (; geo.u < ntiles; walk_step(geo, a, nclusters, ntiles, tiles_x, bands_y)) {
                 const CUtensorMap* gmaps = geo.g > 0 ? maps.mg[geo.g - 1] : maps.m;
                 const int cx = geo.tx * BW - 1, cy = geo.by * BAND + (int)rank * BH - 1;
                 for (int c = 0; c < nchunk; c++) {
@@ -242,8 +301,7 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                             if (is_leader) mbar_arrive(&bars->a_full[s]);
                         } else {
                             if (is_leader) mbar_expect_tx(&bars->a_full[s], 2 * A_BYTES);
-                            tma2_load_4d(smA + s * A_STAGE, &gmaps[KB == 64 ? c : (c >> 1)], mapa_u32(smem_u32(&bars->a_full[s]), 0),
-                                         KB == 64 ? 0 : (c & 1) * 32, cx, cy, geo.b);
+                            tma2_load_4d(smA + s * A_STAGE, &gmaps[c], mapa_u32(smem_u32(&bars->a_full[s]), 0), c < 2 ? c * 32 : 0, cx, cy, geo.b);
                         }
                     }
                     if (++s == (uint32_t)NA) { s = 0; ph ^= 1; }
@@ -253,11 +311,9 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             // ---------------- MMA issuer (leader CTA only): counters and immediates only ----------------
             const uint32_t issue = (elect_one() && !(a.debug_mask & 1)) ? 1u : 0u;
             const uint32_t commit = elect_one() ? 1u : 0u;
-            constexpr uint32_t idesc_wide = umma_idesc_f16(256, NREAL == 32 ? 96 : (NREAL == 16 ? 64 : 128));
-            constexpr uint32_t idesc64 = umma_idesc_f16(256, 64);
-            const uint32_t desc_hi = (uint32_t)((KB == 64 ? umma_desc_sw128(0, 1024, 0) : umma_desc_sw64(0, 512, 0)) >> 32);
+            constexpr uint32_t idesc = umma_idesc_f16(256, mma_n(NREAL));
+            const uint32_t desc_hi = (uint32_t)(umma_desc_sw64(0, 512, 0) >> 32);
             const uint32_t a_lo0 = (smem_u32(smA) & 0x3FFFFu) >> 4, w_lo0 = (smem_u32(smW) & 0x3FFFFu) >> 4;
-            const int last_ksteps = (a.cin - (nchunk - 1) * KB) >> 4;  // k-steps of the last K-block (Cin = 96 / 160 with KB = 64: 2)
             uint32_t s = 0, ph = 0;       // A stage counter, parity of its "full" barrier
             uint32_t buf = 0, phe = 3;    // accumulator set, per-set parity bits to wait for on acc_empty (first use: free)
             int ti = 0;
@@ -276,22 +332,17 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                     mbar_wait(&bars->a_full[s], ph);
                     tc_fence_after();
                     if (ts_on && c == 0) a.dbg_ts[ti * 8 + 2] = clock64();
-                    const int ksteps = c == nchunk - 1 ? last_ksteps : KSTEPS;
                     const uint32_t a_lo = a_lo0 + s * (uint32_t)(A_STAGE >> 4);
 #pragma unroll
                     for (int ky = 0; ky < 3; ky++)
 #pragma unroll
-                        for (int g = 0; g < NGROUPS; g++) {
-                            const uint32_t idesc = (g == 1) ? idesc64 : idesc_wide;
+                        for (int ks = 0; ks < KSTEPS; ks++) {
+                            const uint32_t accum = (c | ky | ks) ? 1u : 0u;
+                            const uint32_t ao = (uint32_t)((ky * P * ROWB) >> 4) + ks * 2;
+                            const uint32_t bo = (uint32_t)((ky * W_KY) >> 4) + ks * 2;
 #pragma unroll
-                            for (int ks = 0; ks < KSTEPS; ks++) {
-                                const uint32_t on = (KB == 64 && ks >= ksteps) ? 0u : issue;  // KB = 32: Cin % 32 == 0, every K-block is full
-                                const uint32_t accum = (c | ky | g | ks) ? 1u : 0u;
-                                const uint32_t ao = (uint32_t)(((ky * P + g * 2) * ROWB) >> 4) + ks * 2;
-                                const uint32_t bo = (uint32_t)((ky * W_KY + g * GOFF) >> 4) + ks * 2;
-                                umma2_issue(acc + 0 * DCOLS, a_lo + ao, w_lo + bo, desc_hi, idesc, accum, on);
-                                umma2_issue(acc + 1 * DCOLS, a_lo + ao + (128 * ROWB) / 16, w_lo + bo, desc_hi, idesc, accum, on);  // second M-tile: 128 rows further
-                            }
+                            for (int mt = 0; mt < MT; mt++)  // the M-tiles of a work tile share the B operand; M-tile mt starts 128 rows further
+                                umma2_issue(acc + mt * DCOLS, a_lo + ao + mt * ((128 * ROWB) >> 4), w_lo + bo, desc_hi, idesc, accum, issue);
                         }
                     umma2_commit_if(&bars->a_empty[s], 3, commit);
                     w_lo += (uint32_t)((3 * W_KY) >> 4);
@@ -306,28 +357,112 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        // ---------------- epilogue: warps 4..11 in two groups of four ----------------
-        // Group g = (warp-4)/4 owns accumulator set g, i.e. every second work tile; inside a group warp q4 = warp % 4
-        // (its TMEM lane quarter) handles row q4 of both M-tiles.
-        const int q4 = warp & 3;
+        const int q4 = warp & 3;  // TMEM lane quarter of this warp = row q4 of an M-tile
         const int ew = warp - EPI_WARP0;
+        const bool dbg_noepi = (a.debug_mask & 8) != 0;
+      if constexpr (EARLY) {
+        // ---------------- epilogue, CONV_STORE16: one (M-tile, row) unit per warp, early hand-back, TMA store ----------------
+        // All 8 warps work on EVERY tile: warp (mi, q4) pulls row q4 of M-tile mi -- 32 positions x 96 / 128 accumulator columns --
+        // into registers (taps combined, + bias), returns its share of the accumulator set (16 arrivals per tile), and then
+        // applies the activation, packs to fp16 and writes the 32-pixel row into a swizzled staging buffer that leaves through ONE
+        // TMA store (box {Cout, 30 px, 1 row}: the two garbage columns and everything outside the image are clipped by the
+        // hardware).  Per-tile timestamps of the previous scheme (a group of 4 warps per tile: both M-tiles, smem transpose,
+        // predicated 16-B stores) showed 1.4 k clk until hand-back + 1.2 k clk of stores + 1.1 k clk of index arithmetic per tile.
+        // (Cout = 64: a work tile has one M-tile per CTA, i.e. four units; the two 4-warp groups then alternate work tiles.)
+        const int grp = ew >> 2;
+        const int mi = MT == 2 ? grp : 0;
+        constexpr int TSTEP = MT == 2 ? 1 : 2;      // this warp works on every TSTEP-th tile of the cluster
+        uint8_t* stg = smStage + ew * STAGE_BYTES;  // [32 px][NREAL fp16], 16-B chunks swizzled like the store map (64B / 128B)
+        const uint32_t acc_empty0 = mapa_u32(smem_u32(&bars->acc_empty[0]), 0), acc_empty1 = mapa_u32(smem_u32(&bars->acc_empty[1]), 0);
+        constexpr int ROWB_O = NREAL * 2;
+        const int sw = NREAL == 32 ? ((lane >> 1) & 3) : (lane & 7);
+        uint32_t phf = 0;  // parity bits to wait for on acc_full[0], acc_full[1]
+        int ti = MT == 2 ? 0 : grp;
+        Walk geo;
+        walk_start(geo, a, cluster_id + ti * nclusters, TSTEP * nclusters, ntiles, tiles_x, bands_y);
+        for (; geo.u < ntiles; walk_step(geo, a, TSTEP * nclusters, ntiles, tiles_x, bands_y), ti += TSTEP) {
+            const int buf = ti & 1;
+            const int y = geo.by * BAND + (int)rank * BH + mi * 4 + q4;
+            const bool ts_on = a.dbg_ts != nullptr && cluster_id == 0 && ti < 64 && is_leader && ew == 0 && lane == 0;
+            if (ts_on) a.dbg_ts[ti * 8 + 4] = clock64();
+            mbar_wait(&bars->acc_full[buf], (phf >> buf) & 1);
+            phf ^= 1u << buf;
+            tc_fence_after();
+            if (ts_on) a.dbg_ts[ti * 8 + 5] = clock64();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS + mi * DCOLS;
+            float f[NREAL];
+            if constexpr (NREAL == 32) {  // D[0:32] + right neighbour's D[32:64] + second right neighbour's D[64:96]
+                uint32_t v[32], u[32], w[32];
+                tmem_ld32(taddr, v);
+                tmem_ld32(taddr + 32, u);
+                tmem_ld32(taddr + 64, w);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    f[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
+                           __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2) + s_bias[j];
+            } else {  // D[c] + right neighbour's D[64 + c] + second right neighbour's D[128 + c], 32 channels at a time
+#pragma unroll
+                for (int nb = 0; nb < 2; nb++) {
+                    uint32_t v[32], u[32], w[32];
+                    tmem_ld32(taddr + nb * 32, v);
+                    tmem_ld32(taddr + 64 + nb * 32, u);
+                    tmem_ld32(taddr + 128 + nb * 32, w);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        f[nb * 32 + j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
+                                         __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2) + s_bias[nb * 32 + j];
+                }
+            }
+            // Plain (CTA-scope release) remote arrive: only the TMEM reads have to be ordered (tcgen05 fence); a cluster-scope
+            // release would also wait for this thread's global stores to drain.
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(buf ? acc_empty1 : acc_empty0);
+            if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
+            if (a.act == 2) {
+#pragma unroll
+                for (int j = 0; j < NREAL; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
+            }
+            if (lane == 0) bulk_wait_read<0>();  // the previous tile's TMA store has finished reading this staging buffer
+            __syncwarp();
+            uint8_t* row = stg + lane * ROWB_O;
+#pragma unroll
+            for (int j = 0; j < NREAL / 8; j++)
+                *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) =
+                    make_uint4(pack_h2(f[8 * j + 0], f[8 * j + 1]), pack_h2(f[8 * j + 2], f[8 * j + 3]), pack_h2(f[8 * j + 4], f[8 * j + 5]),
+                               pack_h2(f[8 * j + 6], f[8 * j + 7]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !dbg_noepi && y < geo.H) {
+                tma_store_4d(&maps.o[geo.g], stg, 0, geo.tx * BW, y, geo.b);
+                bulk_commit();
+            }
+            if (ts_on) a.dbg_ts[ti * 8 + 7] = clock64();
+        }
+        if (lane == 0) bulk_wait<0>();  // all of this warp's stores have been performed before the CTA retires
+      } else {
+        // ---------------- epilogue, residual / post-processing modes: warps 4..11 in two groups of four ----------------
+        // Group g = (warp-4)/4 owns accumulator set g, i.e. every second work tile; inside a group warp q4 handles row q4 of the
+        // tile's M-tile(s).  (These convs are bounded by their MMAs or by HBM, not by the accumulator hand-over.)
         const int group = ew >> 2;
         uint32_t* stg = reinterpret_cast<uint32_t*>(smStage + ew * STAGE_BYTES);  // [32 rows][20 words]
         const int tr = lane >> 2, tc = lane & 3;
-        const bool dbg_noepi = (a.debug_mask & 8) != 0;
         const uint32_t acc_empty_leader = mapa_u32(smem_u32(&bars->acc_empty[group]), 0);
         const int buf = group;
         uint32_t phf = 0;  // parity to wait for on this group's acc_full
         int ti = group;
-        for (int t = cluster_id + group * nclusters; t < ntiles; t += 2 * nclusters, ti += 2) {
-            const TileGeo geo = decode_tile(a, t, tiles_per_img, tiles_x);
+        Walk geo;
+        walk_start(geo, a, cluster_id + group * nclusters, 2 * nclusters, ntiles, tiles_x, bands_y);
+        for (; geo.u < ntiles; walk_step(geo, a, 2 * nclusters, ntiles, tiles_x, bands_y), ti += 2) {
             const int b = geo.b, by = geo.by, tx = geo.tx;
             const int x0 = tx * BW;
-            int yy[2];
-            size_t rowpix[2];
-            bool vrow[2];
+            int yy[MT];
+            size_t rowpix[MT];
+            bool vrow[MT];
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
+            for (int i = 0; i < MT; i++) {
                 yy[i] = by * BAND + (int)rank * BH + i * 4 + q4;
                 vrow[i] = yy[i] < geo.H && !dbg_noepi;
                 rowpix[i] = geo.pxoff + ((size_t)b * geo.H + yy[i]) * geo.W + x0;
@@ -343,7 +478,7 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             constexpr bool RDB16 = MODE == CONV_RDB_OUT16;
             constexpr bool RDB = MODE == CONV_RDB_OUT || RDB16;
             float4 res[2][4];
-            uint2 x0raw[RDB16 ? 2 : 1][2][2][4];  // [i][nb][hf][r], RDB16 only
+            uint2 x0raw[MT][2][2][4];  // [i][nb][hf][r], RDB16 only
             auto load_res = [&](int i, int nb, float4 (&dst)[2][4]) {
                 if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
                     const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + nb * 32 + tc * 4;
@@ -356,7 +491,7 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             };
             if constexpr (RDB16) {
 #pragma unroll
-                for (int i = 0; i < 2; i++)
+                for (int i = 0; i < MT; i++)
 #pragma unroll
                     for (int nb = 0; nb < 2; nb++)
 #pragma unroll
@@ -371,7 +506,7 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             if constexpr (RDB) {
                 if (a.rrdb_end) {  // the RRDB-level skip operands of THIS tile: pull the rows into L2 while the MMAs run
 #pragma unroll
-                    for (int i = 0; i < 2; i++)
+                    for (int i = 0; i < MT; i++)
                         if (vrow[i]) {
                             const int npx = min(BW, geo.W - x0);
                             const char* p1 = reinterpret_cast<const char*>(a.r32 + rowpix[i] * 64);
@@ -387,68 +522,9 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             if (ts_on) a.dbg_ts[ti * 8 + 5] = clock64();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS;
 
-            if constexpr (EARLY) {
-                // ---- both M-tiles -> registers (taps combined, + bias), hand the set back, then activation / pack / store ----
-                float f[2][NREAL];
+            {
 #pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const uint32_t taddr = taddr0 + i * DCOLS;
-                    if constexpr (NREAL == 32) {  // D[0:32] + right neighbour's D[32:64] + second right neighbour's D[64:96]
-                        uint32_t v[32], u[32], w[32];
-                        tmem_ld32(taddr, v);
-                        tmem_ld32(taddr + 32, u);
-                        tmem_ld32(taddr + 64, w);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            f[i][j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
-                                      __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2) + s_bias[j];
-                    } else {  // D[nb*32..] + right neighbour's D[64 + nb*32..]
-#pragma unroll
-                        for (int nb = 0; nb < 2; nb++) {
-                            uint32_t v[32], u[32];
-                            tmem_ld32(taddr + nb * 32, v);
-                            tmem_ld32(taddr + 64 + nb * 32, u);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 32; j++)
-                                f[i][nb * 32 + j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) + s_bias[nb * 32 + j];
-                        }
-                    }
-                }
-                // Plain (CTA-scope release) remote arrive: only the TMEM reads have to be ordered (tcgen05 fence); a cluster-scope
-                // release would also wait for this thread's global stores to drain.
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(acc_empty_leader);
-                if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
-#pragma unroll
-                for (int i = 0; i < 2; i++)
-#pragma unroll
-                    for (int nb = 0; nb < NREAL / 32; nb++) {
-                        float* fb = &f[i][nb * 32];
-                        if (a.act == 2) {
-#pragma unroll
-                            for (int j = 0; j < 32; j++) fb[j] = fb[j] > 0.f ? fb[j] : fb[j] * a.slope;
-                        }
-#pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) =
-                                make_uint4(pack_h2(fb[8 * k + 0], fb[8 * k + 1]), pack_h2(fb[8 * k + 2], fb[8 * k + 3]),
-                                           pack_h2(fb[8 * k + 4], fb[8 * k + 5]), pack_h2(fb[8 * k + 6], fb[8 * k + 7]));
-                        __syncwarp();
-                        __half* orow = a.out16 + rowpix[i] * a.out_cs + a.out_co + nb * 32 + tc * 8;
-#pragma unroll
-                        for (int r = 0; r < 4; r++) {
-                            const uint4 o = *reinterpret_cast<const uint4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
-                            if (vcol[r] && vrow[i]) *reinterpret_cast<uint4*>(orow + (size_t)(tr + 8 * r) * a.out_cs) = o;
-                        }
-                        __syncwarp();
-                    }
-                if (ts_on) a.dbg_ts[ti * 8 + 7] = clock64();
-            } else {
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
+                for (int i = 0; i < MT; i++) {
                     const uint32_t taddr = taddr0 + i * DCOLS;
                     if constexpr (NREAL == 16) {
                         uint32_t v[32], u[16];
@@ -482,17 +558,19 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                         // CONV_RDB_OUT / CONV_RDB_OUT16 / CONV_TRUNK (Cout = 64): fp32 math against the residual stream in the transposed domain
 #pragma unroll
                         for (int nb = 0; nb < 2; nb++) {
-                            uint32_t v[32], u[32];
+                            uint32_t v[32], u[32], w[32];  // D[c] + right neighbour's D[64 + c] + second right neighbour's D[128 + c]
                             tmem_ld32(taddr + nb * 32, v);
                             tmem_ld32(taddr + 64 + nb * 32, u);
+                            tmem_ld32(taddr + 128 + nb * 32, w);
                             tmem_ld_wait();
 #pragma unroll
                             for (int j = 0; j < 32; j++)
-                                v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1));
+                                v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
+                                                       __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2));
                             float4 nxt[2][4];
                             if constexpr (!RDB16) {  // prefetch the residual operands of the next (M-tile, 32-channel block)
                                 const int ni = nb == 1 ? i + 1 : i, nnb = nb ^ 1;
-                                if (ni < 2) load_res(ni, nnb, nxt);
+                                if (ni < MT) load_res(ni, nnb, nxt);
                             }
 #pragma unroll
                             for (int hf = 0; hf < 2; hf++) {
@@ -562,6 +640,7 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                 if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
             }
         }
+      }
     }
 
     tc_fence_before();
@@ -569,8 +648,8 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
     if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
-template <int NREAL, int MODE, int KB>
-cudaError_t launch_nmk(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
+template <int NREAL, int MODE>
+cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
 {
     static bool attr_done[64] = {};
     static int num_sms[64] = {};
@@ -579,12 +658,13 @@ cudaError_t launch_nmk(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t s
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     dev &= 63;
     if (!attr_done[dev]) {
-        e = cudaFuncSetAttribute(conv3x3_kernel<NREAL, MODE, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+        e = cudaFuncSetAttribute(conv3x3_kernel<NREAL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
         if (e != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         attr_done[dev] = true;
     }
-    if (a.ngroups < 0 || a.ngroups > 4) return cudaErrorInvalidValue;
+    constexpr int BAND = 2 * bh_of(NREAL);
+    if (a.ngroups < 0 || a.ngroups > 4 || (a.cin % KB) != 0) return cudaErrorInvalidValue;
     const long long ntiles = a.ngroups > 0 ? (long long)a.ntiles_multi : (long long)((a.W + BW - 1) / BW) * ((a.H + BAND - 1) / BAND) * a.B;
     if (ntiles <= 0) return cudaErrorInvalidValue;
     long long nclusters = num_sms[dev] / 2;
@@ -592,13 +672,12 @@ cudaError_t launch_nmk(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t s
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * nclusters));
     cfg.blockDim = dim3(NTHREADS);
-    // resident weights first, then as many A stages as fit (KB = 64: 2..4 of 41 KB; KB = 32: 4..8 of 20.5 KB)
-    const int nchunk = (a.cin + KB - 1) / KB;
-    const int wbytes = nchunk * 3 * w_bytes_per_ky(NREAL, KB);
-    int na = (SMEM_MAX - SMEM_FIXED - wbytes) / a_stage(KB);
-    if (na > na_max(KB)) na = na_max(KB);
+    // resident weights first, then as many A stages as fit (20.5 KB each for 8-row tiles, 12.5 KB for 4-row tiles; at most 8)
+    const int wbytes = (a.cin / KB) * 3 * w_bytes_per_ky(NREAL);
+    int na = (SMEM_MAX - smem_fixed(NREAL, MODE) - wbytes) / a_stage(bh_of(NREAL));
+    if (na > NA_MAX) na = NA_MAX;
     if (na < 2) return cudaErrorInvalidValue;
-    cfg.dynamicSmemBytes = SMEM_FIXED + wbytes + na * a_stage(KB);
+    cfg.dynamicSmemBytes = smem_fixed(NREAL, MODE) + wbytes + na * a_stage(bh_of(NREAL));
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -606,14 +685,8 @@ cudaError_t launch_nmk(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t s
     cfg.attrs = attr;
     static const int use_pdl = getenv("RSR_NOPDL") ? 0 : 1;  // bring-up switch
     cfg.numAttrs = use_pdl;
-    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_kernel<NREAL, MODE, KB>, *in_map, a, na)) != cudaSuccess) return e;
+    if ((e = cudaLaunchKernelEx(&cfg, conv3x3_kernel<NREAL, MODE>, *in_map, a, na)) != cudaSuccess) return e;
     return cudaGetLastError();
-}
-
-template <int NREAL, int MODE>
-cudaError_t launch_nm(const ConvMaps* in_map, const ConvArgs& a, cudaStream_t stream)
-{
-    return a.kblock == 32 ? launch_nmk<NREAL, MODE, 32>(in_map, a, stream) : launch_nmk<NREAL, MODE, 64>(in_map, a, stream);
 }
 
 }  // namespace

@@ -49,22 +49,35 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// Tensor maps of the activation buffers of one job (one or several same-shape tile groups), built once per job.
+// Dense-block buffer D16[i] of a job with npx network-input pixels: plane 0 = [npx][64] (the RDB input x0), then x1..x4 as four
+// [npx][32] planes -- one plane per 32-channel K-block of the growth convs, so that a conv reads exactly the channels it needs
+// (ncu, 64-channel pair planes: the 96- and 160-channel convs fetched a whole 128-B line per pixel for 64 useful bytes and ran
+// at 5.5-6.2 TB/s of DRAM traffic, i.e. HBM-bound).  K-block k of a conv's input lives in map m[k]: k = 0, 1 -> the two halves
+// of plane 0 (channel coordinate 32k), k >= 2 -> plane k-1.  The 64-channel tail buffers use k = 0, 1 only.
+struct JobMaps {
+    ConvMaps d8[2], d4[2];          // dense buffers with 10-row boxes (Cout=32 convs) and 6-row boxes (Cout=64 convs: conv5, trunk)
+    ConvMaps u1_4, u2_4, v2_4;      // tail inputs of the Cout=64 convs (up1 reads U1, up2 reads U2, HR conv reads V2): 6-row boxes
+    ConvMaps u2_8;                  // last conv (Cout=3, 8-row tiles) reads U2
+    CUtensorMap oD[2][4][4];        // [buffer][x1..x4][group]: output maps of the growth convs
+    CUtensorMap oV1[4], oV2[4], oU2[4];
+};
+inline CUtensorMap* map_slot(ConvMaps& cm, int g, int k) { return g == 0 ? &cm.m[k] : &cm.mg[g - 1][k]; }
+
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf d16[2], t32, r32, f32, u1, v1, u2, v2, tta, tiles, img_in, img_out;
+    JobMaps maps;                 // tensor maps of the job being enqueued (kernel parameters are copied at launch)
     TileDesc* h_tiles = nullptr;  // pinned staging for the tile descriptors of one process() call
     size_t h_tiles_cap = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
 };
 
 struct DeviceModel {
-    std::vector<__half*> wpk;   // per conv (index 0 unused)
     std::vector<float*> bias;   // per conv, padded to cout_pad
     std::vector<int> cout_pad;
-    std::vector<CUtensorMap> wmap, wmap32;  // per conv: 2-D maps over its weight rows, box 64 / 32 rows (CTA-pair kernel)
-    std::vector<CUtensorMap> wmap_k32, wmap32_k32;  // same with 32-channel SWIZZLE_64B boxes (conv_impl 3)
-    bool k32_ok = true;         // false: the driver refused the SWIZZLE_64B weight maps, conv_impl 3 is unavailable
+    std::vector<CUtensorMap> wmap;  // per conv: 2-D map over its weight rows [rows][64 ch], box {32 ch, N/2 rows}, SWIZZLE_64B
     float* w0 = nullptr;        // Conv_0 fp32 weights [64][27]
     void* blob = nullptr;       // one allocation holding everything
 };
@@ -82,16 +95,13 @@ struct rsr_handle {
     std::string err;
     // options
     long long max_batch = 0;  // 0 = auto
-    int epilogue_split = 0;   // CTA-pair kernel: channel-split epilogue (see conv_tc2.cu)
-    int merge_shapes = 0;     // CTA-pair kernel, no TTA: one launch per layer over all shape groups of a job (see run_merged)
-    int serpentine = 0;       // CTA-pair kernel: alternate the tile walk direction from conv to conv (L2 reuse, see ConvArgs::reverse)
+    int merge_shapes = 1;     // one launch per layer over all shape groups of a job (see run_job); 0 = one job per shape group
     // 1 (default): the RDB-level residual t = 0.2*x5 + x0 takes x0 from the fp16 dense buffer instead of an fp32 copy (the
     // RRDB-level skip stays fp32).  Measured on the goldens: max error unchanged (1 LSB natural / 2 LSB noise), off-by-one
     // bytes 1.8->2.1 %, 2.4->3.2 % (natural), 5.3 % faster: the Cout=64 conv is HBM-bound and this removes 384 of its
-    // 1024 bytes per pixel.  0 restores the fp32 RDB stream.  CTA-pair kernel only.
+    // 1024 bytes per pixel.  0 restores the fp32 RDB stream.
     int residual_fp16 = 1;
-    int conv_impl = 2;  // 2 = CTA-pair kernel (conv_tc2.cu, default), 1 = single-CTA .ws kernel (conv_tc.cu, kept for A/B: tools/ab_impl.py),
-                        // 3 = CTA-pair kernel with 32-channel K-blocks (SWIZZLE_64B boxes; opt-in until validated on a B200)
+    int serpentine = 1;  // every second conv walks its work tiles backwards: it starts on the pixels the previous conv touched last, which are still in L2
     int debug_mask = 0;  // timing experiments only (see include/realsr_b200.h)
     int time_convs = 0;
     // stats
@@ -132,38 +142,55 @@ int ensure(rsr_handle* h, DevBuf& b, size_t bytes)
     return 0;
 }
 
-// box_c = 64: SWIZZLE_128B rows of 128 B; box_c = 32: SWIZZLE_64B half rows (conv_impl 3)
-int make_wmap(rsr_handle* h, CUtensorMap* m, const void* base, int rows, int box_rows, int box_c = 64)
+// weight rows [rows][64 ch] of one conv, box {32 ch, box_rows}: a CTA's half (N/2 rows) of one (32-channel K-block, ky) block
+int make_wmap(rsr_handle* h, CUtensorMap* m, const void* base, int rows, int box_rows)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[2] = {64, (cuuint64_t)rows};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight map");
     return 0;
 }
 
-int make_map(rsr_handle* h, CUtensorMap* m, const void* base, int C, int W, int H, int B, int box_rows = CONV_BH + 2, int box_c = 64)
+// one fp16 activation plane [B][H][W][C] (C = 64 or 32 channels per pixel); box {32 ch, 32 px, box_rows, 1}, SWIZZLE_64B,
+// out-of-bounds = zero fill (the conv's padding)
+int make_map(rsr_handle* h, CUtensorMap* m, const void* base, int C, int W, int H, int B, int box_rows)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)CONV_P, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[4] = {32, (cuuint32_t)CONV_P, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char b[160];
         snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d) for C=%d W=%d H=%d B=%d", (int)r, C, W, H, B);
         return set_err(h, RSR_ERR_CUDA, b);
     }
+    return 0;
+}
+
+// output map of a CONV_STORE16 launch of the unified kernel (conv3x3.cu): a 64-channel fp16 plane [B][H][W][64], box = one 30-pixel
+// row segment of box_c channels (32: SWIZZLE_64B, 64: SWIZZLE_128B) -- the layout the epilogue stages in shared memory
+int make_omap(rsr_handle* h, CUtensorMap* m, const void* base, int W, int H, int B, int box_c, int C = 64)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)CONV_BW, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled failed for an output map");
     return 0;
 }
 
@@ -205,10 +232,6 @@ void free_ws(Workspace* w)
     delete w;
 }
 
-// conv_impl: 1 single-CTA .ws kernel (conv_tc.cu), 2 CTA-pair kernel of round 1 (conv_tc2.cu), 3 its 32-channel K-block variant
-// (conv_tc2x.cu), 4 / 5 the unified kernel (conv3x3.cu) with 64- / 32-channel K-blocks
-inline int kblock_of(const rsr_handle* h) { return (h->conv_impl == 3 || h->conv_impl == 5) ? 32 : 64; }
-
 struct BatchCtx {
     rsr_handle* h;
     Workspace* ws;
@@ -217,16 +240,15 @@ struct BatchCtx {
     size_t nconv_ev = 0;
 };
 
-int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
+// omaps: the launch's output maps (one per shape group; CONV_STORE16 only)
+int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx, const CUtensorMap* omaps = nullptr, int nomaps = 0)
 {
     rsr_handle* h = c.h;
     const DeviceModel& dm = h->dm;
-    a.wpk = dm.wpk[conv_idx];
     a.bias = dm.bias[conv_idx];
     a.cin = h->model.convs[conv_idx].cin;
     a.debug_mask = h->debug_mask;
-    a.epi_split = h->epilogue_split;
-    a.reverse = h->serpentine ? (int)(c.launches & 1) : 0;
+    a.reverse = h->serpentine ? (int)(c.conv_launches & 1) : 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->time_convs) {
         if (c.nconv_ev >= c.ws->conv_events.size()) {
@@ -240,141 +262,22 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx)
         c.nconv_ev++;
         CK(cudaEventRecord(e0, c.ws->stream));
     }
-    const int kb = kblock_of(h);
-    if (kb == 32 && !dm.k32_ok) return set_err(h, RSR_ERR_CUDA, "32-channel K-blocks: SWIZZLE_64B tensor maps are not available");
-    if (h->conv_impl >= 2) {
-        ConvMaps mm = *map;
-        mm.w = kb == 32 ? dm.wmap_k32[conv_idx] : dm.wmap[conv_idx];
-        mm.w32 = kb == 32 ? dm.wmap32_k32[conv_idx] : dm.wmap32[conv_idx];
-        a.kblock = kb;
-        if (h->conv_impl >= 4) {
-            CK(launch_conv3x3(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
-        } else {
-            // the validated round-1 kernel unless one of the opt-in variants is requested (conv_tc2x.cu)
-            const bool variant = a.epi_split || a.reverse || a.ngroups > 0 || a.kblock == 32;
-            CK((variant ? launch_conv3x3_tc2x : launch_conv3x3_tc2)(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
-        }
-    } else {
-        CK(launch_conv3x3_tc(map, a, dm.cout_pad[conv_idx], c.ws->stream));
-    }
+    ConvMaps mm = *map;
+    mm.w = dm.wmap[conv_idx];
+    for (int g = 0; g < nomaps && g < 4; g++) mm.o[g] = omaps[g];
+    if (a.mode == CONV_STORE16 && nomaps < (a.ngroups > 0 ? a.ngroups : 1)) return set_err(h, RSR_ERR_GENERIC, "conv: missing output maps");
+    CK(launch_conv3x3(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
     if (e1) CK(cudaEventRecord(e1, c.ws->stream));
     c.launches++;
     c.conv_launches++;
     return 0;
 }
 
-// Runs the whole network on one batch of same-shape padded tiles (H x W network-input pixels each).
-// `d_tiles`: the batch's B descriptors, already on the device.
-int run_batch(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, uint8_t* d_out, const TileDesc* d_tiles, int B, int H,
-              int W, bool tta_out)
-{
-    rsr_handle* h = c.h;
-    Workspace* ws = c.ws;
-    const Model& m = h->model;
-    const size_t npx = (size_t)B * H * W;
-    int r;
-    if ((r = ensure(h, ws->d16[0], npx * 192 * 2))) return r;
-    if ((r = ensure(h, ws->d16[1], npx * 192 * 2))) return r;
-    if ((r = ensure(h, ws->t32, npx * 64 * 4))) return r;
-    if ((r = ensure(h, ws->r32, npx * 64 * 4))) return r;
-    if ((r = ensure(h, ws->f32, npx * 64 * 4))) return r;
-    if ((r = ensure(h, ws->u1, npx * 4 * 64 * 2))) return r;
-    if ((r = ensure(h, ws->v1, npx * 4 * 64 * 2))) return r;
-    if ((r = ensure(h, ws->u2, npx * 16 * 64 * 2))) return r;
-    if ((r = ensure(h, ws->v2, npx * 16 * 64 * 2))) return r;
-    cudaStream_t st = ws->stream;
-
-    // dense-block buffers: three 64-channel planes each (x0 | x1,x2 | x3,x4)
-    __half* D[2] = {(__half*)ws->d16[0].p, (__half*)ws->d16[1].p};
-    const size_t plane = npx * 64;
-    ConvMaps mapD[2], mapU1, mapV1, mapU2, mapV2;
-    const int brows = (h->conv_impl >= 2 ? CONV2_BH : CONV_BH) + 2;
-    const int box_c = kblock_of(h);
-    for (int i = 0; i < 2; i++)
-        for (int pl = 0; pl < 3; pl++)
-            if ((r = make_map(h, &mapD[i].m[pl], D[i] + pl * plane, 64, W, H, B, brows, box_c))) return r;
-    if ((r = make_map(h, &mapU1.m[0], ws->u1.p, 64, 2 * W, 2 * H, B, brows, box_c))) return r;
-    if ((r = make_map(h, &mapV1.m[0], ws->v1.p, 64, 2 * W, 2 * H, B, brows, box_c))) return r;
-    if ((r = make_map(h, &mapU2.m[0], ws->u2.p, 64, 4 * W, 4 * H, B, brows, box_c))) return r;
-    if ((r = make_map(h, &mapV2.m[0], ws->v2.p, 64, 4 * W, 4 * H, B, brows, box_c))) return r;
-    for (ConvMaps* cm : {&mapU1, &mapV1, &mapU2, &mapV2}) cm->m[1] = cm->m[2] = cm->m[0];
-
-    // Conv_0 + preproc
-    {
-        FirstArgs f{};
-        f.img = d_img; f.img_w = img_w; f.img_h = img_h; f.img_c = img_c; f.tiles = d_tiles;
-        f.w = h->dm.w0; f.bias = h->dm.bias[0];
-        f.H = H; f.W = W; f.B = B;
-        f.d16 = D[0]; f.t32 = (float*)ws->t32.p; f.r32 = (float*)ws->r32.p; f.f32 = (float*)ws->f32.p;
-        CK(launch_conv_first(f, st));
-        c.launches++;
-    }
-    ConvArgs base{};
-    base.H = H; base.W = W; base.B = B;
-    base.t32 = (float*)ws->t32.p; base.r32 = (float*)ws->r32.p; base.f32 = (const float*)ws->f32.p;
-    base.tiles = d_tiles;
-    int cur = 0;
-    for (int rrdb = 0; rrdb < m.num_rrdb; rrdb++)
-        for (int rdb = 0; rdb < 3; rdb++) {
-            for (int k = 0; k < 4; k++) {  // x_{k+1} = lrelu(conv([x0..xk])) -> half of plane 1 + k/2 of the same buffer
-                ConvArgs a = base;
-                a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_rdb(rrdb, rdb, k)].slope;
-                a.out16 = D[cur] + (1 + k / 2) * plane; a.out_cs = 64; a.out_co = 32 * (k & 1);
-                if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, k)))) return r;
-            }
-            ConvArgs a = base;  // x5 -> residual(s) -> x0 of the next RDB in the other buffer
-            a.mode = CONV_RDB_OUT; a.rrdb_end = (rdb == 2);
-            if (h->residual_fp16 && h->conv_impl >= 2) { a.mode = CONV_RDB_OUT16; a.res16 = D[cur]; }
-            a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
-            if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, 4)))) return r;
-            cur ^= 1;
-        }
-    {   // trunk conv + fea (BinaryOp ADD), result in channels 0..63 of the other dense buffer
-        ConvArgs a = base;
-        a.mode = CONV_TRUNK; a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
-        if ((r = conv(c, &mapD[cur], a, m.idx_trunk()))) return r;
-        cur ^= 1;
-    }
-    // nearest x2 -> conv+lrelu, twice (x4.param:996-999); the first source is plane 0 of the dense buffer
-    CK(launch_upsample2x(D[cur], 64, (__half*)ws->u1.p, B, H, W, st));
-    c.launches++;
-    {
-        ConvArgs a = base;
-        a.H = 2 * H; a.W = 2 * W;
-        a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_up1()].slope;
-        a.out16 = (__half*)ws->v1.p; a.out_cs = 64; a.out_co = 0;
-        if ((r = conv(c, &mapU1, a, m.idx_up1()))) return r;
-    }
-    CK(launch_upsample2x((const __half*)ws->v1.p, 64, (__half*)ws->u2.p, B, 2 * H, 2 * W, st));
-    c.launches++;
-    {
-        ConvArgs a = base;
-        a.H = 4 * H; a.W = 4 * W;
-        a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_up2()].slope;
-        a.out16 = (__half*)ws->v2.p; a.out_cs = 64; a.out_co = 0;
-        if ((r = conv(c, &mapU2, a, m.idx_up2()))) return r;
-        a.slope = m.convs[m.idx_hr()].slope;
-        a.out16 = (__half*)ws->u2.p;  // u2 is dead after up2: reuse it for the HR conv output
-        if ((r = conv(c, &mapV2, a, m.idx_hr()))) return r;
-    }
-    {   // last conv (64->3, N padded to 16) + postproc / TTA store
-        ConvArgs a = base;
-        a.H = 4 * H; a.W = 4 * W;
-        a.mode = tta_out ? CONV_LAST_F32 : CONV_LAST_U8;
-        a.img_out = d_out; a.img_w = img_w * 4; a.img_h = img_h * 4; a.img_c = img_c;
-        a.prepad_s = c.prepadding * 4;
-        a.tta_out = (float*)ws->tta.p;
-        if ((r = conv(c, &mapU2, a, m.idx_last()))) return r;
-    }
-    return 0;
-}
-
-
-// ---- merged multi-shape launches ("merge_shapes" option, CTA-pair kernel, no TTA) -------------------------------------------
-// A frame's tiles come in up to four padded shapes (interior, right edge, bottom edge, corner).  run_batch launches every
-// layer once per shape; measured per-launch fill/drain (ncu launch list, profiles/README.md): 7.7 us for the Cout=32 convs and
-// 15 us for the Cout=64 conv, i.e. ~13 % of a 1080p step at 4 x 351 conv launches.  Here the shape groups of a job are
-// concatenated pixel-major in every activation buffer and each layer runs as ONE launch over all of them (ConvArgs::grp).
+// ---- one job = up to four same-shape tile groups run through the whole network, ONE launch per layer --------------------------
+// A frame's tiles come in up to four padded shapes (interior, right edge, bottom edge, corner).  The shape groups of a job are
+// concatenated pixel-major in every activation buffer and each layer runs as one launch over all of them (ConvArgs::grp): the
+// per-launch pipeline fill/drain is paid once per layer, not once per layer and shape (measured: -8 % per 1080p frame).  Option
+// merge_shapes = 0 plans one job per shape group instead (same code path).
 struct Grp {
     size_t off;     // first TileDesc of the group in the call's descriptor array
     int n, H, W;    // tiles, padded tile size
@@ -392,21 +295,21 @@ struct MJob {
     size_t tta_float4 = 0;
 };
 
-int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, uint8_t* d_out, const TileDesc* d_tiles_all,
-               const std::vector<Grp>& gs, bool tta_out)
+int run_job(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, uint8_t* d_out, const TileDesc* d_tiles_all,
+            const std::vector<Grp>& gs, bool tta_out)
 {
     rsr_handle* h = c.h;
     Workspace* ws = c.ws;
     const Model& m = h->model;
     const int G = (int)gs.size();
-    if (G < 1 || G > 4) return set_err(h, RSR_ERR_GENERIC, "run_merged: 1..4 shape groups per job");
+    if (G < 1 || G > 4) return set_err(h, RSR_ERR_GENERIC, "run_job: 1..4 shape groups per job");
     size_t npx = 0;
     for (const Grp& g : gs) npx += (size_t)g.n * g.H * g.W;
     int r;
     if ((r = ensure(h, ws->d16[0], npx * 192 * 2))) return r;
     if ((r = ensure(h, ws->d16[1], npx * 192 * 2))) return r;
     if ((r = ensure(h, ws->r32, npx * 64 * 4))) return r;
-    if ((r = ensure(h, ws->t32, npx * 64 * 4))) return r;
+    if (!h->residual_fp16 && (r = ensure(h, ws->t32, npx * 64 * 4))) return r;
     if ((r = ensure(h, ws->f32, npx * 64 * 4))) return r;
     if ((r = ensure(h, ws->u1, npx * 4 * 64 * 2))) return r;
     if ((r = ensure(h, ws->v1, npx * 4 * 64 * 2))) return r;
@@ -414,23 +317,32 @@ int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_
     if ((r = ensure(h, ws->v2, npx * 16 * 64 * 2))) return r;
     cudaStream_t st = ws->stream;
     __half* D[2] = {(__half*)ws->d16[0].p, (__half*)ws->d16[1].p};
-    const size_t plane = npx * 64;
-    const int brows = CONV2_BH + 2;
-    const int box_c = kblock_of(h);
-    ConvMaps mapD[2], mapU1, mapV1, mapU2, mapV2;
-    auto slot = [](ConvMaps& cm, int g, int pl) -> CUtensorMap* { return g == 0 ? &cm.m[pl] : &cm.mg[g - 1][pl]; };
+    // dense buffer layout: plane 0 = x0 [npx][64], then x1..x4 as four [npx][32] planes (see JobMaps)
+    auto xplane = [&](int i, int k) -> __half* { return D[i] + npx * 64 + (size_t)(k - 1) * npx * 32; };  // k = 1..4
+    const int rows8 = conv_bh(32) + 2, rows4 = conv_bh(64) + 2;
+    JobMaps* jm = &ws->maps;
     for (int g = 0; g < G; g++) {
         const Grp& gr = gs[g];
-        for (int i = 0; i < 2; i++)
-            for (int pl = 0; pl < 3; pl++)
-                if ((r = make_map(h, slot(mapD[i], g, pl), D[i] + pl * plane + gr.px_off * 64, 64, gr.W, gr.H, gr.n, brows, box_c))) return r;
-        struct { ConvMaps* cm; void* base; int s; } tails[4] = {{&mapU1, ws->u1.p, 2}, {&mapV1, ws->v1.p, 2}, {&mapU2, ws->u2.p, 4}, {&mapV2, ws->v2.p, 4}};
-        for (auto& t : tails) {
-            if ((r = make_map(h, slot(*t.cm, g, 0), (__half*)t.base + gr.px_off * (size_t)(t.s * t.s) * 64, 64, t.s * gr.W, t.s * gr.H, gr.n, brows, box_c)))
-                return r;
-            *slot(*t.cm, g, 1) = *slot(*t.cm, g, 0);
-            *slot(*t.cm, g, 2) = *slot(*t.cm, g, 0);
+        for (int i = 0; i < 2; i++) {
+            for (int k = 0; k < CONV_MAX_KBLOCKS; k++) {
+                const __half* base = k < 2 ? D[i] + gr.px_off * 64 : xplane(i, k - 1) + gr.px_off * 32;
+                const int C = k < 2 ? 64 : 32;
+                if ((r = make_map(h, map_slot(jm->d8[i], g, k), base, C, gr.W, gr.H, gr.n, rows8))) return r;
+                if ((r = make_map(h, map_slot(jm->d4[i], g, k), base, C, gr.W, gr.H, gr.n, rows4))) return r;
+            }
+            for (int k = 1; k <= 4; k++)
+                if ((r = make_omap(h, &jm->oD[i][k - 1][g], xplane(i, k) + gr.px_off * 32, gr.W, gr.H, gr.n, 32, 32))) return r;
         }
+        struct { ConvMaps* cm; void* base; int s; int rows; } tails[4] = {{&jm->u1_4, ws->u1.p, 2, rows4}, {&jm->u2_4, ws->u2.p, 4, rows4},
+                                                                          {&jm->v2_4, ws->v2.p, 4, rows4}, {&jm->u2_8, ws->u2.p, 4, rows8}};
+        for (auto& t : tails) {
+            if ((r = make_map(h, map_slot(*t.cm, g, 0), (__half*)t.base + gr.px_off * (size_t)(t.s * t.s) * 64, 64, t.s * gr.W, t.s * gr.H, gr.n, t.rows)))
+                return r;
+            *map_slot(*t.cm, g, 1) = *map_slot(*t.cm, g, 0);
+        }
+        if ((r = make_omap(h, &jm->oV1[g], (__half*)ws->v1.p + gr.px_off * 4 * 64, 2 * gr.W, 2 * gr.H, gr.n, 64))) return r;
+        if ((r = make_omap(h, &jm->oV2[g], (__half*)ws->v2.p + gr.px_off * 16 * 64, 4 * gr.W, 4 * gr.H, gr.n, 64))) return r;
+        if ((r = make_omap(h, &jm->oU2[g], (__half*)ws->u2.p + gr.px_off * 16 * 64, 4 * gr.W, 4 * gr.H, gr.n, 64))) return r;
     }
     // Conv_0 + preproc, one (cheap, bandwidth-bound) launch per group
     for (const Grp& gr : gs) {
@@ -439,20 +351,22 @@ int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_
         f.w = h->dm.w0; f.bias = h->dm.bias[0];
         f.H = gr.H; f.W = gr.W; f.B = gr.n;
         f.d16 = D[0] + gr.px_off * 64;
-        f.t32 = (float*)ws->t32.p + gr.px_off * 64; f.r32 = (float*)ws->r32.p + gr.px_off * 64; f.f32 = (float*)ws->f32.p + gr.px_off * 64;
+        f.t32 = h->residual_fp16 ? nullptr : (float*)ws->t32.p + gr.px_off * 64;  // the fp32 RDB stream only exists with residual_fp16 = 0
+        f.r32 = (float*)ws->r32.p + gr.px_off * 64; f.f32 = (float*)ws->f32.p + gr.px_off * 64;
         CK(launch_conv_first(f, st));
         c.launches++;
     }
-    // group table at scale s (1 for the body, 2 / 4 for the tail)
-    auto fill_groups = [&](ConvArgs& a, int s) {
+    // group table of a launch at scale s (1 for the body, 2 / 4 for the tail) for a conv with cout_pad output channels
+    auto fill_groups = [&](ConvArgs& a, int s, int cout_pad) {
+        const int band = 2 * conv_bh(cout_pad);
         a.H = a.W = a.B = 0;
         a.ngroups = G;
         int t0 = 0;
         for (int g = 0; g < G; g++) {
             ConvGroup& cg = a.grp[g];
             cg.H = gs[g].H * s; cg.W = gs[g].W * s; cg.B = gs[g].n;
-            cg.tiles_x = (cg.W + CONV2_BW - 1) / CONV2_BW;
-            cg.tiles_per_img = cg.tiles_x * ((cg.H + CONV2_BAND - 1) / CONV2_BAND);
+            cg.tiles_x = (cg.W + CONV_BW - 1) / CONV_BW;
+            cg.tiles_per_img = cg.tiles_x * ((cg.H + band - 1) / band);
             cg.tile_start = t0;
             cg.desc0 = (int)gs[g].off;
             cg.px_off = (long long)gs[g].px_off * s * s;
@@ -464,39 +378,40 @@ int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_
     ConvArgs base{};
     base.t32 = (float*)ws->t32.p; base.r32 = (float*)ws->r32.p; base.f32 = (const float*)ws->f32.p;
     base.tiles = d_tiles_all;
-    fill_groups(base, 1);
     int cur = 0;
     for (int rrdb = 0; rrdb < m.num_rrdb; rrdb++)
         for (int rdb = 0; rdb < 3; rdb++) {
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < 4; k++) {  // x_{k+1} = lrelu(conv([x0..xk])) -> its own 32-channel plane of the same buffer
                 ConvArgs a = base;
+                fill_groups(a, 1, 32);
                 a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_rdb(rrdb, rdb, k)].slope;
-                a.out16 = D[cur] + (1 + k / 2) * plane; a.out_cs = 64; a.out_co = 32 * (k & 1);
-                if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, k)))) return r;
+                if ((r = conv(c, &jm->d8[cur], a, m.idx_rdb(rrdb, rdb, k), jm->oD[cur][k], G))) return r;
             }
-            ConvArgs a = base;
+            ConvArgs a = base;  // x5 -> residual(s) -> x0 of the next RDB in the other buffer
+            fill_groups(a, 1, 64);
             a.mode = CONV_RDB_OUT; a.rrdb_end = (rdb == 2);
             if (h->residual_fp16) { a.mode = CONV_RDB_OUT16; a.res16 = D[cur]; }
             a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
-            if ((r = conv(c, &mapD[cur], a, m.idx_rdb(rrdb, rdb, 4)))) return r;
+            if ((r = conv(c, &jm->d4[cur], a, m.idx_rdb(rrdb, rdb, 4)))) return r;
             cur ^= 1;
         }
-    {
+    {   // trunk conv + fea (BinaryOp ADD), result in plane 0 of the other dense buffer
         ConvArgs a = base;
+        fill_groups(a, 1, 64);
         a.mode = CONV_TRUNK; a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
-        if ((r = conv(c, &mapD[cur], a, m.idx_trunk()))) return r;
+        if ((r = conv(c, &jm->d4[cur], a, m.idx_trunk()))) return r;
         cur ^= 1;
     }
+    // nearest x2 -> conv+lrelu, twice (x4.param:996-999); the first source is plane 0 of the dense buffer
     for (const Grp& gr : gs) {
         CK(launch_upsample2x(D[cur] + gr.px_off * 64, 64, (__half*)ws->u1.p + gr.px_off * 4 * 64, gr.n, gr.H, gr.W, st));
         c.launches++;
     }
     {
         ConvArgs a = base;
-        fill_groups(a, 2);
+        fill_groups(a, 2, 64);
         a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_up1()].slope;
-        a.out16 = (__half*)ws->v1.p; a.out_cs = 64; a.out_co = 0;
-        if ((r = conv(c, &mapU1, a, m.idx_up1()))) return r;
+        if ((r = conv(c, &jm->u1_4, a, m.idx_up1(), jm->oV1, G))) return r;
     }
     for (const Grp& gr : gs) {
         CK(launch_upsample2x((const __half*)ws->v1.p + gr.px_off * 4 * 64, 64, (__half*)ws->u2.p + gr.px_off * 16 * 64, gr.n, 2 * gr.H, 2 * gr.W, st));
@@ -504,22 +419,20 @@ int run_merged(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_
     }
     {
         ConvArgs a = base;
-        fill_groups(a, 4);
+        fill_groups(a, 4, 64);
         a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_up2()].slope;
-        a.out16 = (__half*)ws->v2.p; a.out_cs = 64; a.out_co = 0;
-        if ((r = conv(c, &mapU2, a, m.idx_up2()))) return r;
-        a.slope = m.convs[m.idx_hr()].slope;
-        a.out16 = (__half*)ws->u2.p;  // u2 is dead after up2: reuse it for the HR conv output
-        if ((r = conv(c, &mapV2, a, m.idx_hr()))) return r;
+        if ((r = conv(c, &jm->u2_4, a, m.idx_up2(), jm->oV2, G))) return r;
+        a.slope = m.convs[m.idx_hr()].slope;  // u2 is dead after up2: it takes the HR conv's output
+        if ((r = conv(c, &jm->v2_4, a, m.idx_hr(), jm->oU2, G))) return r;
     }
-    {
+    {   // last conv (64->3, N padded to 16) + postproc / TTA store
         ConvArgs a = base;
-        fill_groups(a, 4);
+        fill_groups(a, 4, 16);
         a.mode = tta_out ? CONV_LAST_F32 : CONV_LAST_U8;
         a.img_out = d_out; a.img_w = img_w * 4; a.img_h = img_h * 4; a.img_c = img_c;
         a.prepad_s = c.prepadding * 4;
         a.tta_out = (float*)ws->tta.p;
-        if ((r = conv(c, &mapU2, a, m.idx_last()))) return r;
+        if ((r = conv(c, &jm->u2_8, a, m.idx_last()))) return r;
     }
     return 0;
 }
@@ -550,14 +463,14 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
     // Every batch of the call is planned first, so that all tile descriptors go to the device in ONE copy from pinned memory
     // and the batches then run back to back on the stream with no host synchronisation in between (same-stream order makes
     // the reuse of the activation buffers safe).  Larger shapes first: the workspace is sized once.
-    struct Job { size_t off; int n, H, W; bool tta_out, gather; size_t slot_stride; int mw, mh; };
     std::vector<TileDesc> flat;
-    std::vector<Job> jobs;
-    std::vector<MJob> mjobs;  // merge_shapes: every job = up to 4 shape groups, one launch per layer
-    const bool merged = h->merge_shapes && h->conv_impl >= 2;
+    std::vector<MJob> mjobs;  // every job = up to max_groups shape groups, one launch per layer
     size_t max_tta_bytes = 0;
-    if (merged) {
+    {
         const double budget = 16e9;  // workspace bytes per job
+        const int per_tile = h->tta ? 8 : 1;   // network passes per tile
+        const size_t need = h->tta ? 2 : 1;    // group slots per chunk: TTA runs variants 0..3 as H x W and 4..7 as W x H
+        const size_t max_groups = h->merge_shapes ? 4 : need;
         MJob cur;
         double cur_bytes = 0;
         size_t cur_px = 0;
@@ -569,17 +482,16 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
             cur = MJob();
             cur_bytes = 0; cur_px = 0;
         };
-        const int per_tile = h->tta ? 8 : 1;   // network passes per tile
-        const size_t need = h->tta ? 2 : 1;    // group slots per chunk: TTA runs variants 0..3 as H x W and 4..7 as W x H
-        for (auto g = groups.rbegin(); g != groups.rend(); ++g) {
+        for (auto g = groups.rbegin(); g != groups.rend(); ++g) {  // larger shapes first: the workspace is sized once
             const int H = g->first.first, W = g->first.second;
             const std::vector<TileDesc>& tl = g->second;
+            // workspace per padded pixel: 2x192 fp16 + 3x64 fp32 + (u1,v1) 4x64x2 fp16 + (u2,v2) 16x64x2 fp16 [+ TTA 16 float4 x2]
             const double bpt = (double)per_tile * H * W * (768.0 + 768.0 + 1024.0 + 4096.0 + (h->tta ? 512.0 : 0.0));
             size_t pos = 0;
             while (pos < tl.size()) {
                 long long cap = (long long)((budget - cur_bytes) / bpt);
                 if (h->max_batch > 0) cap = std::min(cap, std::max(1LL, h->max_batch / per_tile));
-                if (cur.gs.size() + need > 4 || cap < 1) {
+                if (cur.gs.size() + need > max_groups || cap < 1) {
                     if (cur.gs.empty()) cap = 1;  // a single tile larger than the budget still has to run
                     else { flush(); continue; }
                 }
@@ -620,54 +532,9 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
                 padded += (long long)take * per_tile * H * W;
                 pos += take;
             }
+            if (!h->merge_shapes) flush();
         }
         flush();
-    }
-    for (auto g = groups.rbegin(); !merged && g != groups.rend(); ++g) {
-        const int H = g->first.first, W = g->first.second;
-        std::vector<TileDesc>& tl = g->second;
-        // workspace per padded pixel: 2x192 fp16 + 3x64 fp32 + (u1,v1) 4x64x2 fp16 + (u2,v2) 16x64x2 fp16 [+ TTA 16 float4 x2]
-        const double bytes_per_tile = (double)H * W * (768.0 + 768.0 + 1024.0 + 4096.0 + (h->tta ? 512.0 : 0.0));
-        long long mb = h->max_batch > 0 ? h->max_batch : (long long)(12e9 / bytes_per_tile);
-        mb = std::max(1LL, std::min(mb, 64LL));
-        if (!h->tta) {
-            for (size_t i = 0; i < tl.size(); i += (size_t)mb) {
-                const size_t n = std::min(tl.size(), i + (size_t)mb) - i;
-                jobs.push_back({flat.size(), (int)n, H, W, false, false, 0, 0, 0});
-                flat.insert(flat.end(), tl.begin() + i, tl.begin() + i + n);
-                padded += (long long)n * H * W;
-            }
-        } else {
-            // 8 dihedral variants per tile (src/realsr.cpp:242-318): 0..3 keep the shape, 4..7 run transposed
-            const long long G = std::max(1LL, mb / 4);
-            for (size_t i = 0; i < tl.size(); i += (size_t)G) {
-                const size_t n = std::min(tl.size(), i + (size_t)G) - i;
-                const size_t slot_stride = (size_t)16 * H * W;  // float4 per slot
-                max_tta_bytes = std::max(max_tta_bytes, n * 8 * slot_stride * sizeof(float4));
-                for (int half = 0; half < 2; half++) {
-                    jobs.push_back({flat.size(), (int)n * 4, half ? W : H, half ? H : W, true, false, 0, 0, 0});
-                    for (size_t gi = 0; gi < n; gi++)
-                        for (int v = half * 4; v < half * 4 + 4; v++) {
-                            TileDesc t = tl[i + gi];
-                            t.variant = v;
-                            t.tta_slot = (int)(gi * 8 + v);
-                            flat.push_back(t);
-                        }
-                }
-                // the gather needs the 8 descriptors of every tile in slot order
-                int mw = 0, mh = 0;
-                for (size_t gi = 0; gi < n; gi++) { mw = std::max(mw, tl[i + gi].crop_w); mh = std::max(mh, tl[i + gi].crop_h); }
-                jobs.push_back({flat.size(), (int)n, H, W, true, true, slot_stride, mw, mh});
-                for (size_t gi = 0; gi < n; gi++)
-                    for (int v = 0; v < 8; v++) {
-                        TileDesc t = tl[i + gi];
-                        t.variant = v;
-                        t.tta_slot = (int)(gi * 8 + v);
-                        flat.push_back(t);
-                    }
-                padded += (long long)n * 8 * H * W;
-            }
-        }
     }
     if (flat.size() > ws->h_tiles_cap) {
         if (ws->h_tiles) cudaFreeHost(ws->h_tiles);
@@ -682,23 +549,12 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
     CK(cudaMemcpyAsync(ws->tiles.p, ws->h_tiles, sizeof(TileDesc) * flat.size(), cudaMemcpyHostToDevice, ws->stream));
     const TileDesc* d_tiles = (const TileDesc*)ws->tiles.p;
     for (const MJob& mj : mjobs) {
-        if ((r = run_merged(c, d_in, w, hh, ch, d_out, d_tiles, mj.gs, h->tta != 0))) return r;
+        if ((r = run_job(c, d_in, w, hh, ch, d_out, d_tiles, mj.gs, h->tta != 0))) return r;
         for (const GatherJob& gj : mj.gathers) {
             TtaGatherArgs ga{};
             ga.tta_out = (const float*)((const float4*)ws->tta.p + gj.tta_off); ga.tiles = d_tiles + gj.off; ga.ngroups = gj.n;
             ga.slot_stride = gj.slot_stride; ga.img_out = d_out; ga.img_w = w * 4; ga.img_h = hh * 4; ga.img_c = ch; ga.prepad_s = P * 4;
             CK(launch_tta_gather(ga, gj.mw, gj.mh, ws->stream));
-            c.launches++;
-        }
-    }
-    for (const Job& j : jobs) {
-        if (!j.gather) {
-            if ((r = run_batch(c, d_in, w, hh, ch, d_out, d_tiles + j.off, j.n, j.H, j.W, j.tta_out))) return r;
-        } else {
-            TtaGatherArgs ga{};
-            ga.tta_out = (const float*)ws->tta.p; ga.tiles = d_tiles + j.off; ga.ngroups = j.n;
-            ga.slot_stride = j.slot_stride; ga.img_out = d_out; ga.img_w = w * 4; ga.img_h = hh * 4; ga.img_c = ch; ga.prepad_s = P * 4;
-            CK(launch_tta_gather(ga, j.mw, j.mh, ws->stream));
             c.launches++;
         }
     }
@@ -765,8 +621,8 @@ int rsr_load(rsr_handle* h, const char* parampath, const char* modelpath)
     if (r) return set_err(h, RSR_ERR_MODEL, m.error);
     // pack + upload: one blob, 1024-B aligned sub-allocations (bulk copies need 16 B; keep slabs nicely aligned)
     const int nconv = (int)m.convs.size();
-    std::vector<std::vector<uint16_t>> packed(nconv), packed_rows(nconv);
-    std::vector<size_t> off_w(nconv, 0), off_b(nconv, 0), off_r(nconv, 0);
+    std::vector<std::vector<uint16_t>> packed_rows(nconv);
+    std::vector<size_t> off_b(nconv, 0), off_r(nconv, 0);
     std::vector<int> nrows(nconv, 0);
     DeviceModel dm;
     dm.cout_pad.assign(nconv, 0);
@@ -777,9 +633,7 @@ int rsr_load(rsr_handle* h, const char* parampath, const char* modelpath)
         const ConvLayer& c = m.convs[i];
         dm.cout_pad[i] = c.cout <= 16 ? 16 : (c.cout <= 32 ? 32 : 64);
         if (i > 0) {
-            if (c.cout > 64 || (c.cin % 16)) return set_err(h, RSR_ERR_MODEL, "unsupported conv shape in " + c.name);
-            pack_conv_weights(c, dm.cout_pad[i], packed[i]);
-            off_w[i] = bump(packed[i].size() * 2);
+            if (c.cout > 64 || (c.cin % 32) || c.cin > 32 * CONV_MAX_KBLOCKS) return set_err(h, RSR_ERR_MODEL, "unsupported conv shape in " + c.name);
             nrows[i] = pack_conv_weight_rows(c, dm.cout_pad[i], packed_rows[i]);
             off_r[i] = bump(packed_rows[i].size() * 2);
         }
@@ -790,33 +644,18 @@ int rsr_load(rsr_handle* h, const char* parampath, const char* modelpath)
     std::vector<uint8_t> host(total, 0);
     memcpy(host.data() + off_w0, m.convs[0].weight.data(), 64 * 27 * 4);
     for (int i = 0; i < nconv; i++) {
-        if (i > 0) memcpy(host.data() + off_w[i], packed[i].data(), packed[i].size() * 2);
         if (i > 0) memcpy(host.data() + off_r[i], packed_rows[i].data(), packed_rows[i].size() * 2);
         memcpy(host.data() + off_b[i], m.convs[i].bias.data(), m.convs[i].cout * 4);
     }
     CK(cudaMemcpy(dm.blob, host.data(), total, cudaMemcpyHostToDevice));
     dm.w0 = (float*)((uint8_t*)dm.blob + off_w0);
-    dm.wpk.assign(nconv, nullptr);
     dm.bias.assign(nconv, nullptr);
     dm.wmap.resize(nconv);
-    dm.wmap32.resize(nconv);
-    dm.wmap_k32.resize(nconv);
-    dm.wmap32_k32.resize(nconv);
-    for (int i = 1; i < nconv; i++) {
-        int rr = make_wmap(h, &dm.wmap[i], (uint8_t*)dm.blob + off_r[i], nrows[i], dm.cout_pad[i] == 32 ? 48 : 64);
-        if (!rr) rr = make_wmap(h, &dm.wmap32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], 32);
+    for (int i = 1; i < nconv; i++) {  // box = a CTA's half of one (K-block, ky) weight block: N/2 rows (N = 192 / 96 / 64)
+        const int rr = make_wmap(h, &dm.wmap[i], (uint8_t*)dm.blob + off_r[i], nrows[i], dm.cout_pad[i] == 64 ? 96 : (dm.cout_pad[i] == 32 ? 48 : 32));
         if (rr) return rr;
-        // maps of the opt-in conv_impl=3: must never be able to fail a load of the default path
-        if (dm.k32_ok && (make_wmap(h, &dm.wmap_k32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], dm.cout_pad[i] == 32 ? 48 : 64, 32) ||
-                          make_wmap(h, &dm.wmap32_k32[i], (uint8_t*)dm.blob + off_r[i], nrows[i], 32, 32))) {
-            dm.k32_ok = false;
-            set_err(h, 0, "");
-        }
     }
-    for (int i = 0; i < nconv; i++) {
-        if (i > 0) dm.wpk[i] = (__half*)((uint8_t*)dm.blob + off_w[i]);
-        dm.bias[i] = (float*)((uint8_t*)dm.blob + off_b[i]);
-    }
+    for (int i = 0; i < nconv; i++) dm.bias[i] = (float*)((uint8_t*)dm.blob + off_b[i]);
     h->model = std::move(m);
     h->dm = dm;
     h->loaded = true;
@@ -940,16 +779,10 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
 {
     if (!h || !key) return RSR_ERR_GENERIC;
     if (!strcmp(key, "max_batch")) h->max_batch = value;
-    else if (!strcmp(key, "epilogue_split")) h->epilogue_split = value < 0 || value > 2 ? 0 : (int)value;  // 1 = channel split, 2 = early hand-back (Cout=32 convs)
     else if (!strcmp(key, "serpentine")) h->serpentine = value ? 1 : 0;
     else if (!strcmp(key, "merge_shapes")) h->merge_shapes = value ? 1 : 0;
     else if (!strcmp(key, "debug_mask")) h->debug_mask = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
-    else if (!strcmp(key, "conv_impl")) {
-        if (value < 1 || value > 5) return set_err(h, RSR_ERR_GENERIC, "conv_impl must be 1..5");
-        if ((value == 3 || value == 5) && h->loaded && !h->dm.k32_ok) return set_err(h, RSR_ERR_CUDA, "conv_impl 3/5: SWIZZLE_64B tensor maps are not available");
-        h->conv_impl = (int)value;
-    }
     else if (!strcmp(key, "residual_fp16")) h->residual_fp16 = (int)value;
     else return set_err(h, RSR_ERR_GENERIC, std::string("unknown option ") + key);
     return 0;
@@ -965,27 +798,6 @@ int rsr_check_model(const char* parampath, const char* modelpath, int* num_rrdb,
     if (num_rrdb) *num_rrdb = m.num_rrdb;
     if (num_convs) *num_convs = (int)m.convs.size();
     return 0;
-}
-
-long long rsr_debug_pack(const char* parampath, const char* modelpath, int conv_index, int* cin, int* cout, int* cout_pad, uint16_t* packed,
-                         long long capacity)
-{
-    if (!parampath || !modelpath) return RSR_ERR_GENERIC;
-    Model m;
-    if (load_model(parampath, modelpath, m)) return RSR_ERR_MODEL;
-    if (conv_index < 0 || conv_index >= (int)m.convs.size()) return RSR_ERR_GENERIC;
-    const ConvLayer& c = m.convs[conv_index];
-    const int npad = c.cout <= 16 ? 16 : (c.cout <= 32 ? 32 : 64);
-    if (cin) *cin = c.cin;
-    if (cout) *cout = c.cout;
-    if (cout_pad) *cout_pad = npad;
-    std::vector<uint16_t> out;
-    pack_conv_weights(c, npad, out);
-    if (packed) {
-        if ((long long)out.size() > capacity) return RSR_ERR_GENERIC;
-        memcpy(packed, out.data(), out.size() * 2);
-    }
-    return (long long)out.size();
 }
 
 long long rsr_debug_pack_rows(const char* parampath, const char* modelpath, int conv_index, uint16_t* packed, long long capacity)
@@ -1015,37 +827,37 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     __half *d_in = nullptr, *d_out = nullptr;
     float* d_f = nullptr;
     TileDesc* d_td = nullptr;
-    const int nplane = (cl.cin + 63) / 64;
-    CK(cudaMalloc(&d_in, npx * nplane * 64 * 2));
+    // the engine's dense-buffer layout: plane 0 = channels 0..63 [px][64], then one [px][32] plane per further 32-channel K-block
+    const int nkb = cl.cin / 32;
+    CK(cudaMalloc(&d_in, npx * (size_t)std::max(cl.cin, 64) * 2));
     CK(cudaMalloc(&d_out, npx * 64 * 2));
     CK(cudaMalloc(&d_f, npx * 16));
     CK(cudaMalloc(&d_td, sizeof(TileDesc)));
-    {   // [H][W][cin] -> planes [plane][H][W][64] (zero padded), the engine's dense-buffer layout
-        std::vector<uint16_t> planes(npx * nplane * 64, 0);
+    {
+        std::vector<uint16_t> planes(npx * (size_t)std::max(cl.cin, 64), 0);
         for (size_t p = 0; p < npx; p++)
-            for (int ci = 0; ci < cl.cin; ci++) planes[((size_t)(ci >> 6) * npx + p) * 64 + (ci & 63)] = in16[p * cl.cin + ci];
+            for (int ci = 0; ci < cl.cin; ci++) {
+                const size_t dst = ci < 64 ? p * 64 + ci : npx * 64 + (size_t)((ci - 64) >> 5) * npx * 32 + p * 32 + (ci & 31);
+                planes[dst] = in16[p * cl.cin + ci];
+            }
         CK(cudaMemcpy(d_in, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice));
     }
     TileDesc td{};
     CK(cudaMemcpy(d_td, &td, sizeof td, cudaMemcpyHostToDevice));
     ConvMaps map;
     int r = 0;
-    for (int pl = 0; pl < 3; pl++)
-        if ((r = make_map(h, &map.m[pl], d_in + (size_t)(pl < nplane ? pl : 0) * npx * 64, 64, W, H, 1, (h->conv_impl >= 2 ? CONV2_BH : CONV_BH) + 2,
-                          kblock_of(h))))
-            return r;
-    map.w = kblock_of(h) == 32 ? h->dm.wmap_k32[conv_index] : h->dm.wmap[conv_index];
-    map.w32 = kblock_of(h) == 32 ? h->dm.wmap32_k32[conv_index] : h->dm.wmap32[conv_index];
+    for (int k = 0; k < nkb && k < CONV_MAX_KBLOCKS; k++)
+        if ((r = make_map(h, &map.m[k], k < 2 ? d_in : d_in + npx * 64 + (size_t)(k - 2) * npx * 32, k < 2 ? 64 : 32, W, H, 1, conv_bh(npad) + 2))) return r;
+    map.w = h->dm.wmap[conv_index];
     ConvArgs a{};
-    a.wpk = h->dm.wpk[conv_index]; a.bias = h->dm.bias[conv_index]; a.cin = cl.cin;
+    a.bias = h->dm.bias[conv_index]; a.cin = cl.cin;
     a.H = H; a.W = W; a.B = 1;
     a.act = cl.act; a.slope = cl.slope;
     a.out16 = d_out; a.out_cs = npad; a.out_co = 0;
     a.tiles = d_td; a.tta_out = d_f;
     a.mode = npad == 16 ? CONV_LAST_F32 : CONV_STORE16;
+    if (npad != 16 && (r = make_omap(h, &map.o[0], d_out, W, H, 1, npad, npad))) return r;
     a.debug_mask = h->debug_mask;
-    a.epi_split = h->epilogue_split;
-    a.kblock = kblock_of(h);
     long long* d_ts = nullptr;
     float* d_r32 = nullptr;
     if (getenv("RSR_DBG_RDB") && npad == 64) {  // bring-up: time the Cout=64 conv with its real (CONV_RDB_OUT) epilogue
@@ -1062,18 +874,13 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
         CK(cudaMemset(d_ts, 0, 64 * 8 * sizeof(long long)));
         a.dbg_ts = d_ts;
     }
-    for (int rep = 0; rep < (d_ts ? 2 : 1); rep++) {
-        if (h->conv_impl >= 4) CK(launch_conv3x3(&map, a, npad, 0));
-        else if (h->conv_impl >= 2) CK(((a.epi_split || a.kblock == 32) ? launch_conv3x3_tc2x : launch_conv3x3_tc2)(&map, a, npad, 0));
-        else CK(launch_conv3x3_tc(&map, a, npad, 0));
-    }
+    for (int rep = 0; rep < (d_ts ? 2 : 1); rep++) CK(launch_conv3x3(&map, a, npad, 0));
     CK(cudaDeviceSynchronize());
     if (d_ts) {  // bring-up: per-tile pipeline timestamps of cluster 0 (clock64 of the leader SM)
         std::vector<long long> ts(64 * 8);
         CK(cudaMemcpy(ts.data(), d_ts, ts.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         const long long t0 = ts[0];
-        fprintf(stderr, "tile: mma_wait_start mma_acc_ready mma_a0_ready mma_issued | epi_wait_start epi_acc_full epi_handback [epi_done]   (clk since first; "
-                        "epilogue_split=0: hand-back == done)\n");
+        fprintf(stderr, "tile: mma_wait_start mma_acc_ready mma_a0_ready mma_issued | epi_wait_start epi_acc_full epi_handback [epi_done]   (clk since first)\n");
         for (int i = 0; i < 64 && ts[i * 8 + 0]; i++)
             fprintf(stderr, "%3d: %8lld %8lld %8lld %8lld | %8lld %8lld %8lld %8lld\n", i, ts[i * 8 + 0] - t0, ts[i * 8 + 1] - t0, ts[i * 8 + 2] - t0,
                     ts[i * 8 + 3] - t0, ts[i * 8 + 4] - t0, ts[i * 8 + 5] - t0, ts[i * 8 + 6] - t0, ts[i * 8 + 7] ? ts[i * 8 + 7] - t0 : 0LL);

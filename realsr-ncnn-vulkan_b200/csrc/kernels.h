@@ -42,7 +42,7 @@ enum ConvMode {
 // are concatenated pixel-major in every buffer, group g starting px_off pixels into it.
 struct ConvGroup {
     int H, W, B;                 // this conv's input == output size of the group, tiles in the group
-    int tiles_x, tiles_per_img;  // work-tile grid of one image of the group (CTA-pair kernel: 30 x 16 px pair tiles)
+    int tiles_x, tiles_per_img;  // work-tile grid of one image of the group (pair tiles of 30 x 2*conv_bh(cout_pad) px)
     int tile_start;              // first work tile of the group in the launch-wide numbering
     int desc0;                   // index of the group's first TileDesc in ConvArgs::tiles
     long long px_off;            // pixel offset of the group inside the activation buffers (already scaled for 2x / 4x layers)
@@ -50,14 +50,13 @@ struct ConvGroup {
 };
 
 struct ConvArgs {
-    const __half* wpk;  // packed weights [chunk][tap][N][64] fp16, pre-swizzled smem image (see model.cpp)
     const float* bias;  // [N]
     int cin;            // real input channels (multiple of 16)
     int H, W, B;        // spatial size of this conv's input == output, batch
     int mode, act;      // ConvMode; act: 0 none, 2 leaky relu
     float slope;
     __half* out16;
-    int out_cs, out_co;  // channels per pixel of the output buffer, channel offset
+    int out_cs, out_co;  // channels per pixel of the output buffer, channel offset (residual modes; CONV_STORE16 goes through ConvMaps::o)
     float* t32;
     float* r32;
     const float* f32;
@@ -71,42 +70,35 @@ struct ConvArgs {
     int img_c;           // bytes per pixel of the output image (3 or 4)
     int prepad_s;        // prepadding*scale
     float* tta_out;
-    long long* dbg_ts;   // optional (bring-up): per-tile clock64 stamps of cluster 0, 8 slots per tile, see conv_tc2.cu
-    // CTA-pair kernel, merged multi-shape launch ("merge_shapes" option): up to 4 same-shape groups in ONE launch per layer, so
-    // that a frame pays the per-launch pipeline fill/drain (7.7 us for the Cout=32 convs, 15 us for the Cout=64 conv, measured)
-    // once per layer instead of once per layer and shape.  ngroups == 0: plain launch described by H, W, B above.
+    long long* dbg_ts;   // optional (bring-up): per-tile clock64 stamps of cluster 0, 8 slots per tile, see conv3x3.cu
+    // Merged multi-shape launch (engine option "merge_shapes", default on): up to 4 same-shape tile groups in ONE launch per layer,
+    // so that a frame pays the per-launch pipeline fill/drain once per layer instead of once per layer and shape.
+    // ngroups == 0: plain launch described by H, W, B above.
     int ngroups;
     int ntiles_multi;     // total work tiles of the merged launch
     ConvGroup grp[4];
-    int reverse;          // CTA-pair kernel: walk the work tiles from last to first.  The engine alternates it from one conv to the next
-                          // ("serpentine" option) so that a conv starts on the pixels the previous conv touched last -- the part of its
-                          // inputs (and of the previous conv's outputs) that is still in the 126 MB L2
-    int kblock;           // CTA-pair kernel: input channels per A stage, 64 (default) or 32 (tensor maps must have 32-channel SWIZZLE_64B boxes)
-    int epi_split;        // CTA-pair kernel: 1 = channel-split epilogue with early accumulator hand-back (conv_tc2.cu: epilogue_split)
+    int reverse;          // walk the work tiles from last to first (the engine alternates it from conv to conv: L2 reuse, see conv3x3.cu Walk)
     int debug_mask;       // debug mask for timing experiments (0 in production): 1 no MMA, 2 no A loads, 4 no B loads, 8 no epilogue I/O
 };
 
-// one tensor map per 64-channel input plane (chunk) of a conv
+// Tensor maps of one conv launch.  Activations: one map per 32-channel K-block of the conv's input, box {32 ch, 32 px,
+// conv_bh(cout_pad) + 2 rows, 1}, SWIZZLE_64B.  K-blocks 0 and 1 are the two halves of a 64-channel plane (the kernel passes channel
+// coordinate 32k), K-blocks >= 2 are 32-channel planes of their own (the dense-block growth channels x1..x4, see engine.cu JobMaps).
+constexpr int CONV_MAX_KBLOCKS = 6;  // Cin <= 192
 struct alignas(64) ConvMaps {
-    CUtensorMap m[3];
-    CUtensorMap w;    // 2-D map over the conv's weight rows [rows][64], box 64 rows (CTA-pair kernel only)
-    CUtensorMap w32;  // same tensor, box 32 rows
-    CUtensorMap mg[3][3];  // merged multi-shape launch: the planes of groups 1..3 (group 0 uses m[])
+    CUtensorMap m[CONV_MAX_KBLOCKS];
+    CUtensorMap w;         // 2-D map over the conv's weight rows [rows][64 ch], box {32 ch, N/2 rows} (N = 192 / 96 / 64), SWIZZLE_64B
+    CUtensorMap mg[3][CONV_MAX_KBLOCKS];  // merged multi-shape launch: the K-block maps of groups 1..3 (group 0 uses m[])
+    CUtensorMap o[4];      // CONV_STORE16: the OUTPUT plane of group g, box {cout_pad ch, 30 px, 1 row}, SWIZZLE_64B (Cout=32: a
+                           // 32-channel plane) / SWIZZLE_128B (Cout=64: a 64-channel plane): the epilogue leaves through TMA stores
 };
-// conv3x3 s1 p1 as implicit GEMM on tcgen05 (conv_tc.cu). cout_pad in {16, 32, 64}.
-cudaError_t launch_conv3x3_tc(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
-// same contract, CTA-pair (cta_group::2) implementation (conv_tc2.cu); needs in_maps->w and 10-row activation boxes
-cudaError_t launch_conv3x3_tc2(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
-// conv_tc2x.cu: the same kernel with the opt-in variants (ConvArgs::epi_split / kblock / ngroups / reverse); conv_tc2.cu ignores those
-cudaError_t launch_conv3x3_tc2x(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
-// conv3x3.cu: the unified CTA-pair kernel (early accumulator hand-back, lean MMA issuer, merged launches, K-block 64 / 32)
+// conv3x3.cu: conv3x3 s1 p1 (+ fused epilogue, see ConvMode) as implicit GEMM on tcgen05 CTA pairs.  cout_pad in {16, 32, 64}.
 cudaError_t launch_conv3x3(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
-constexpr int CONV2_BH = 8;
-constexpr int CONV2_BW = 30;    // output columns per work tile of the CTA-pair kernel (CONV_P - 2)
-constexpr int CONV2_BAND = 16;  // output rows per work tile of the CTA-pair kernel (2 x CONV2_BH)
-// box dims the kernel expects from the tensor map: {64 ch, 32 px, CONV_BH+2 rows, 1}
-constexpr int CONV_BH = 16;
-constexpr int CONV_P = 32;
+constexpr int CONV_P = 32;      // position pitch of a work tile (32 px: 30 output columns + the two halo columns)
+constexpr int CONV_BW = 30;     // output columns per work tile
+// output rows per CTA of a pair and work tile: 4 for the Cout = 64 convs (one N = 192 MMA per k-step: 192 TMEM columns per M-tile),
+// 8 otherwise; a work tile of the pair is 2 x conv_bh rows, the activation boxes have conv_bh + 2 rows
+__host__ __device__ constexpr int conv_bh(int cout_pad) { return cout_pad == 64 ? 4 : 8; }
 
 // Conv_0 (3->64, fp32 CUDA cores) fused with preproc (crop, reflect-101, x 1/255, TTA variant), conv_first.cu
 struct FirstArgs {

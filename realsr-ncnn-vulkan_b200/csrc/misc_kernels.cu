@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(FIRST_THREADS) conv_first_kernel(const FirstAr
 #pragma unroll
     for (int j4 = 0; j4 < 4; j4++) {
         const float4 o = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
-        t[j4] = o; r[j4] = o; f[j4] = o;
+        if (a.t32) t[j4] = o;  // the fp32 copy of the RDB input only exists with residual_fp16 = 0
+        r[j4] = o; f[j4] = o;
     }
     uint4* d = reinterpret_cast<uint4*>(a.d16 + pix * 64 + quarter * 16);
 #pragma unroll

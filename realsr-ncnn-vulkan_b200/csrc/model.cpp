@@ -259,54 +259,6 @@ int load_model(const std::string& parampath, const std::string& binpath, Model& 
     return 0;
 }
 
-// Cout <= 32: two horizontally adjacent taps share one N=64 MMA.  Slab (ky, 0) = rows 0..31 W(ky,kx=0), rows 32..63
-// W(ky,kx=1); slab (ky, 1) = rows 0..31 W(ky,kx=2), rows 32..63 zero.  The kernel runs both with the A window of their
-// first tap; D columns 32..63 then hold the kx=1 contribution of the pixel to the LEFT, which the epilogue fetches with
-// one warp shuffle (see conv_tc.cu).
-static void pack_conv_weights_paired(const ConvLayer& c, std::vector<uint16_t>& out)
-{
-    const int nchunk = (c.cin + 63) / 64;
-    out.assign((size_t)nchunk * 6 * 64 * 64, 0);
-    for (int ch = 0; ch < nchunk; ch++)
-        for (int ky = 0; ky < 3; ky++)
-            for (int half = 0; half < 2; half++) {
-                uint16_t* slab = out.data() + ((size_t)ch * 6 + ky * 2 + half) * 64 * 64;
-                for (int row = 0; row < 64; row++) {
-                    const int n = row & 31, kx = half == 0 ? (row >> 5) : 2;
-                    if (half == 1 && row >= 32) break;
-                    if (n >= c.cout) continue;
-                    for (int k = 0; k < 64; k++) {
-                        const int ci = ch * 64 + k;
-                        if (ci >= c.cin) break;
-                        const int pj = (k >> 3) ^ (row & 7);
-                        slab[row * 64 + pj * 8 + (k & 7)] = c.weight_h[((size_t)n * c.cin + ci) * 9 + ky * 3 + kx];
-                    }
-                }
-            }
-}
-
-// Cout <= 16 (the 64->3 output conv): all three taps of a kernel row share one N=64 MMA.  Slab ky: rows 0..15 W(ky,0),
-// 16..31 W(ky,1), 32..47 W(ky,2), 48..63 zero; the epilogue adds the columns of the positions 1 and 2 to the right.
-static void pack_conv_weights_tripled(const ConvLayer& c, std::vector<uint16_t>& out)
-{
-    const int nchunk = (c.cin + 63) / 64;
-    out.assign((size_t)nchunk * 3 * 64 * 64, 0);
-    for (int ch = 0; ch < nchunk; ch++)
-        for (int ky = 0; ky < 3; ky++) {
-            uint16_t* slab = out.data() + ((size_t)ch * 3 + ky) * 64 * 64;
-            for (int row = 0; row < 48; row++) {
-                const int n = row & 15, kx = row >> 4;
-                if (n >= c.cout) continue;
-                for (int k = 0; k < 64; k++) {
-                    const int ci = ch * 64 + k;
-                    if (ci >= c.cin) break;
-                    const int pj = (k >> 3) ^ (row & 7);
-                    slab[row * 64 + pj * 8 + (k & 7)] = c.weight_h[((size_t)n * c.cin + ci) * 9 + ky * 3 + kx];
-                }
-            }
-        }
-}
-
 int pack_conv_weight_rows(const ConvLayer& c, int cout_pad, std::vector<uint16_t>& out)
 {
     const int nchunk = (c.cin + 63) / 64;
@@ -327,32 +279,6 @@ int pack_conv_weight_rows(const ConvLayer& c, int cout_pad, std::vector<uint16_t
                     }
                 }
     return rows;
-}
-
-void pack_conv_weights(const ConvLayer& c, int cout_pad, std::vector<uint16_t>& out)
-{
-    if (cout_pad == 32) {
-        pack_conv_weights_paired(c, out);
-        return;
-    }
-    if (cout_pad == 16) {
-        pack_conv_weights_tripled(c, out);
-        return;
-    }
-    const int nchunk = (c.cin + 63) / 64;
-    out.assign((size_t)nchunk * 9 * cout_pad * 64, 0);
-    for (int ch = 0; ch < nchunk; ch++)
-        for (int tap = 0; tap < 9; tap++) {
-            uint16_t* slab = out.data() + ((size_t)ch * 9 + tap) * cout_pad * 64;
-            for (int n = 0; n < c.cout; n++)
-                for (int k = 0; k < 64; k++) {
-                    const int ci = ch * 64 + k;
-                    if (ci >= c.cin) break;
-                    const int j = k >> 3;                   // 16-byte chunk within the 128-byte row
-                    const int pj = j ^ (n & 7);             // SWIZZLE_128B
-                    slab[n * 64 + pj * 8 + (k & 7)] = c.weight_h[((size_t)n * c.cin + ci) * 9 + tap];
-                }
-        }
 }
 
 }  // namespace rsr

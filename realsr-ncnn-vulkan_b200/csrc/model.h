@@ -44,13 +44,7 @@ struct Model {
 // returns 0 on success; on failure m.error holds a one-line reason and a negative code is returned
 int load_model(const std::string& parampath, const std::string& binpath, Model& m);
 
-// Packs one conv's fp16 weights into the swizzled shared-memory image the tensor-core kernel streams:
-// [chunk = ceil(cin/64)][tap = 9][n = cout_pad][k = 64] fp16, each [n][64] slab laid out as a K-major SWIZZLE_128B
-// UMMA operand (row n at n*128 B, 16-B chunk j of the row stored at chunk j ^ (n & 7)).  Missing channels / rows = 0.
-// cout_pad == 32 uses the tap-paired layout instead: [chunk][ky = 3][half = 2][64 rows][64] (see model.cpp).
-void pack_conv_weights(const ConvLayer& c, int cout_pad, std::vector<uint16_t>& out);
-
-// Weight rows for the CTA-pair kernel (conv_tc2.cu): plain row-major [rows][64] fp16 (TMA applies the swizzle), rows
+// Weight rows for the conv kernel (conv3x3.cu): plain row-major [rows][64] fp16 (TMA applies the swizzle), rows
 // grouped per (64-channel plane, ky): Cout=64 -> 192 rows [W(ky,0) | W(ky,1) | W(ky,2)]; Cout<=32 -> 96 rows
 // [W(ky,0) | W(ky,1) | W(ky,2)] (32 each); Cout<=16 -> 64 rows [16 | 16 | 16 | 0].  Returns the number of rows.
 int pack_conv_weight_rows(const ConvLayer& c, int cout_pad, std::vector<uint16_t>& out);

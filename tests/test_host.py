@@ -64,51 +64,6 @@ def test_loader_rejects_bad_files(models_dir, tmp_path):
     assert r != 0 and "magic" in err
 
 
-def test_weight_packing_matches_numpy(models_dir):
-    """[chunk][tap][n][64] fp16 with the SWIZZLE_128B chunk permutation, zero padded"""
-    lib = rb.load_library()
-    lib.rsr_debug_pack.restype = ctypes.c_longlong
-    p, b = model_paths("models-DF2K")
-    convs = read_convs("models-DF2K")
-    for idx in (1, 2, 5, 350):
-        c = convs[idx]
-        cin, cout, npad = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
-        n = lib.rsr_debug_pack(p.encode(), b.encode(), idx, ctypes.byref(cin), ctypes.byref(cout), ctypes.byref(npad), None, ctypes.c_longlong(0))
-        assert (cin.value, cout.value) == (c["cin"], c["cout"])
-        nchunk = (c["cin"] + 63) // 64
-        paired = npad.value == 32  # Cout <= 32: [chunk][ky][half][64 rows][64], taps (ky,0)+(ky,1) stacked, (ky,2)+zeros
-        tripled = npad.value == 16  # Cout <= 16: [chunk][ky][64 rows][64], rows 16*kx + n
-        nslab, nrow = (6, 64) if paired else ((3, 64) if tripled else (9, npad.value))
-        assert n == nchunk * nslab * nrow * 64
-        buf = np.zeros(n, dtype=np.uint16)
-        assert lib.rsr_debug_pack(p.encode(), b.encode(), idx, None, None, None, buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(n)) == n
-        ref = np.zeros((nchunk, nslab, nrow, 64), dtype=np.float16)
-        w = c["w"].reshape(c["cout"], c["cin"], 9)
-        for ch in range(nchunk):
-            k = min(64, c["cin"] - ch * 64)
-            blk = np.zeros((nslab, nrow, 64), dtype=np.float16)
-            wt = np.transpose(w[:, ch * 64:ch * 64 + k, :], (2, 0, 1))  # [tap][cout][k]
-            if paired:
-                for ky in range(3):
-                    blk[ky * 2, 0:c["cout"], :k] = wt[ky * 3 + 0]
-                    blk[ky * 2, 32:32 + c["cout"], :k] = wt[ky * 3 + 1]
-                    blk[ky * 2 + 1, 0:c["cout"], :k] = wt[ky * 3 + 2]
-            elif tripled:
-                for ky in range(3):
-                    for kx in range(3):
-                        blk[ky, 16 * kx:16 * kx + c["cout"], :k] = wt[ky * 3 + kx]
-            else:
-                blk[:, :c["cout"], :k] = wt
-            # swizzle: 16-byte chunk j of row n goes to chunk j ^ (n & 7)
-            blk = blk.reshape(nslab, nrow, 8, 8)
-            sw = np.zeros_like(blk)
-            for r in range(nrow):
-                for j in range(8):
-                    sw[:, r, j ^ (r & 7)] = blk[:, r, j]
-            ref[ch] = sw.reshape(nslab, nrow, 64)
-        assert np.array_equal(buf.view(np.float16).reshape(ref.shape).view(np.uint16), ref.view(np.uint16))
-
-
 def test_weight_rows_for_cta_pair_kernel(models_dir):
     """row-major [rows][64] weight matrix of the cta_group::2 kernel: per (plane, ky) the three kx tap groups stacked along N"""
     lib = rb.load_library()
@@ -180,8 +135,7 @@ def test_options_and_tile_api_validate_without_gpu():
     rsr_process_tiles on a handle without a model is an error (no GPU needed for any of it)"""
     e = rb.RealSR(0)
     assert e.set_option("no_such_option", 1) != 0 and "unknown option" in e.last_error()
-    assert e.set_option("conv_impl", 7) != 0 and "conv_impl" in e.last_error()
-    for key in ("epilogue_split", "merge_shapes", "serpentine", "residual_fp16", "max_batch", "conv_impl"):
+    for key in ("merge_shapes", "residual_fp16", "max_batch", "time_convs"):
         assert e.set_option(key, 1) == 0, key
     e.tilesize = 400
     assert e.tile_count(1920, 1080) == 15

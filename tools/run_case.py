@@ -14,10 +14,6 @@ assert e.load(os.path.join(ROOT, "models/models-DF2K/x4.param"), os.path.join(RO
 e.tilesize = tile
 if os.environ.get("RSR_MAX_BATCH"):
     e.set_option("max_batch", int(os.environ["RSR_MAX_BATCH"]))
-if os.environ.get("RSR_EPI_SPLIT"):
-    e.set_option("epilogue_split", int(os.environ["RSR_EPI_SPLIT"]))
-if os.environ.get("RSR_IMPL"):
-    e.set_option("conv_impl", int(os.environ["RSR_IMPL"]))
 if os.environ.get("RSR_DEBUG"):
     e.set_option("debug_mask", int(os.environ["RSR_DEBUG"]))
 if os.environ.get("RSR_TIME_CONVS"):

@@ -1,10 +1,12 @@
 #!/usr/bin/env python3
-"""Turns the raw captures of tools/final_run.sh (gpurun_out/) into the committed summaries under profiles/.
-Needs `ncu` (reads the .ncu-rep); run in the build container after the gpurun call came back."""
-import collections, csv, json, os, re, shutil, subprocess, sys
+"""Turns the raw ncu captures of a gpurun call (gpurun_out/<R>_launches.csv, <R>_conv_full.ncu-rep) into the committed summaries
+under profiles/.  Needs `ncu` (reads the .ncu-rep); run in the build container after the gpurun call came back.
+   summarise_profiles.py <R>        e.g. r2"""
+import collections, csv, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-R = sys.argv[1] if len(sys.argv) > 1 else "r1"
+R = sys.argv[1] if len(sys.argv) > 1 else "r2"
+PX = 2302800  # network-input pixels of the 1080p / tile-400 step: every conv launch (merged shapes) covers all of them
 
 # ---- launch list ----
 lines = [l for l in open(os.path.join(G, R + "_launches.csv")) if not l.startswith("==")]
@@ -12,19 +14,21 @@ tot, cnt = collections.defaultdict(float), collections.Counter()
 for row in csv.DictReader(lines):
     if row.get("Metric Name") != "gpu__time_duration.sum":
         continue
-    k = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void unnamed>::", "").replace("unnamed>::", "").strip()
+    k = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void unnamed>::", "").replace("unnamed>::", "").replace("rsr::<", "").strip()
     v, u = float(row["Metric Value"].replace(",", "")), row["Metric Unit"]
     tot[k] += v / 1e6 if u.startswith("n") else (v / 1e3 if u.startswith("u") else v)
     cnt[k] += 1
 T = sum(tot.values())
-summ = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -s <3rd call> -c <one call> --csv python bench.py ... (tools/final_run.sh)",
-        "note": "one process() call of the bench after warm-up calls; ncu times are cold-cache and serialised (programmatic-dependent-launch overlap is lost "
-                "under the profiler, and the GPU is not power-capped between replays): compare SHARES with the live CUDA-event numbers, not absolutes",
+summ = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -s <3rd call> -c <one call> --csv python bench.py --profile --steps 1 --warmup 2",
+        "note": "one process() call of the bench (BASELINE configs[1]) after two warm-up calls; ncu times are cold-cache and serialised (programmatic-"
+                "dependent-launch overlap is lost under the profiler, and the GPU is not power-capped between replays): compare SHARES with the live "
+                "CUDA-event numbers, not absolutes.  Template arguments: conv3x3_kernel<Cout_pad, ConvMode>",
         "total_ms": T, "launches": sum(cnt.values()),
         "kernels": [{"kernel": k, "launches": cnt[k], "total_ms": v, "share": v / T, "avg_us": v / cnt[k] * 1e3}
                     for k, v in sorted(tot.items(), key=lambda x: -x[1])]}
 json.dump(summ, open(os.path.join(P, R + "_launches_summary.json"), "w"), indent=1)
-shutil.copy(os.path.join(G, R + "_launches.csv"), os.path.join(P, R + "_launches.csv"))
+with open(os.path.join(P, R + "_launches.csv"), "w") as f:
+    f.writelines(lines)
 
 # ---- full capture ----
 rep = os.path.join(G, R + "_conv_full.ncu-rep")
@@ -33,68 +37,47 @@ rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 ix = {h: i for i, h in enumerate(hdr)}
 KEEP = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max", "gpc__cycles_elapsed.avg.per_second",
-        "launch__grid_size", "launch__block_size", "launch__cluster_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_barrier"]
-NAMES = {64: "conv1 64->32", 96: "conv2 96->32", 128: "conv3 128->32", 160: "conv4 160->32", 192: "conv5 192->64 + residual"}
-PX = 8 * 420 * 420
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "gpc__cycles_elapsed.avg.per_second", "launch__grid_size", "launch__block_size", "launch__cluster_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active"]
+FLOP = {64: 2 * 9 * 64 * 32, 96: 2 * 9 * 96 * 32, 128: 2 * 9 * 128 * 32, 160: 2 * 9 * 160 * 32, 192: 2 * 9 * 192 * 64}
+def num(s):
+    return float(s.replace(",", ""))
+def to_bytes(v, u):
+    return num(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+def to_us(v, u):
+    return num(v) * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(u, 1)
 kernels = []
-for d in data:
-    rec = {}
+seq = ["conv1 64->32", "conv2 96->32", "conv3 128->32", "conv4 160->32", "conv5 192->64 (+0.2x, +x0)"] * 2
+cin = [64, 96, 128, 160, 192] * 2
+for n, d in enumerate(data):
+    rec = {"layer": seq[n] if n < len(seq) else "?"}
     for k in KEEP:
         if k in ix:
             rec[k] = (d[ix[k]] + " " + units[ix[k]]).strip()
-    t_us = float(d[ix["gpu__time_duration.sum"]].replace(",", ""))
-    rd, wr = float(d[ix["dram__bytes_read.sum"]].replace(",", "")), float(d[ix["dram__bytes_write.sum"]].replace(",", ""))
-    rec["derived_dram_TBps"] = (rd + wr) / t_us  # Mbyte / us
-    rec["derived_dram_bytes_per_px"] = (rd + wr) * 1e6 / PX
+    t_us = to_us(d[ix["gpu__time_duration.sum"]], units[ix["gpu__time_duration.sum"]])
+    rd = to_bytes(d[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]])
+    wr = to_bytes(d[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
+    rec["derived_dram_TBps"] = (rd + wr) / t_us / 1e6
+    rec["derived_dram_bytes_per_px"] = (rd + wr) / PX
+    rec["derived_dram_bytes"] = rd + wr
+    if n < len(cin):
+        rec["derived_useful_TFLOPs"] = FLOP[cin[n]] * PX / t_us / 1e6
     kernels.append(rec)
-# identify the conv by its DRAM read volume (planes read) and kernel template
-order = []
-for r in kernels:
-    rd = float(r["dram__bytes_read.sum"].split()[0])
-    planes = round(rd / 180.7)
-    r["planes_read"] = planes
-json.dump({"command": "ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc2_kernel -s 4247 -c 10 python bench.py --steps 1 --warmup 1 --no-cpu-baseline",
-           "note": "10 consecutive tensor-core conv launches of the 8 x 420x420 batch (3024 pair tiles on 74 persistent CTA pairs): "
-                   "conv3, conv4, conv5, conv1, conv2, conv3, conv4, conv5, conv1, conv2 of consecutive dense blocks; "
-                   "derived_* = (dram read + write) / duration and / 1 411 200 px",
+json.dump({"command": "ncu --set full --clock-control none --import-source on -k regex:conv3x3_kernel -s <2 calls + 35> -c 10 python bench.py --profile --steps 1 --warmup 2",
+           "note": "10 consecutive conv launches of the third process() call: dense blocks 7 and 8 (block 8 closes an RRDB: its conv5 also reads and "
+                   "writes the fp32 RRDB skip stream); every launch covers all 15 padded tiles of the frame (2 302 800 px, merged shape groups)",
            "kernels": kernels}, open(os.path.join(P, R + "_conv_full_summary.json"), "w"), indent=1)
-shutil.copy(rep, os.path.join(P, R + "_conv_full.ncu-rep"))
-
-# ---- roofline.traffic for bench.py: DRAM bytes per launch, averaged over the dense-block convs (1380 of the 1400 conv launches of a step)
-by_planes_mode = {}
-for r in kernels:
-    key = (r["planes_read"], "<64, 5>" in r["Kernel Name"], round(float(r["gpu__time_duration.sum"].split()[0]) / 20))
-    by_planes_mode.setdefault((r["Kernel Name"], r["planes_read"]), []).append(r)
-per_px = {}
-for r in kernels:
-    rd, wr = float(r["dram__bytes_read.sum"].split()[0]), float(r["dram__bytes_write.sum"].split()[0])
-    name = ("conv5" if "<64, 5>" in r["Kernel Name"] else {1: "conv1", 3: "conv4"}.get(r["planes_read"]))
-    if name is None:  # two planes: conv2 (96 ch) is the faster one
-        name = "conv2or3"
-    per_px.setdefault(name, []).append((rd + wr) * 1e6 / PX)
-avg = {k: sum(v) / len(v) for k, v in per_px.items()}
-rdb_bytes_per_px = avg["conv1"] + 2 * avg["conv2or3"] + avg["conv4"] + avg["conv5"]
-padded_px, nrdb = 2302800, 69
-traffic = {"source": "profiles/%s_conv_full.ncu-rep (ncu --set full, 10 consecutive conv launches of the 8 x 420x420 batch)" % R,
-           "dram_bytes_per_px": avg, "dram_bytes_per_px_per_dense_block": rdb_bytes_per_px,
-           "dram_bytes_per_launch": rdb_bytes_per_px * padded_px * nrdb / (nrdb * 5 * 4),
-           "note": "dram__bytes_read.sum + dram__bytes_write.sum of the five convs of a dense block, per network-input pixel, scaled to the "
-                   "2 302 800 padded px of the 1080p step and divided by its 69 x 5 x 4 dense-block launches (4 shape groups). The 20 other conv "
-                   "launches of a step (RRDB-closing extras, trunk, 4x tail) are not in the capture. Reads equal the planes a conv must fetch "
-                   "(180.6 MB per 64-channel fp16 plane of this batch): halo rows are re-read from L2, not from DRAM."}
+tb = [k["derived_dram_bytes"] for k in kernels]
+traffic = {"source": "profiles/%s_conv_full_summary.json (ncu --set full capture of 10 consecutive conv launches = two dense blocks)" % R,
+           "dram_bytes_per_launch": sum(tb) / len(tb),
+           "dram_bytes_per_px_per_dense_block": sum(tb) / 2 / PX,
+           "note": "dram__bytes_read.sum + dram__bytes_write.sum, average over the 10 captured launches (a step has 345 dense-block launches of this "
+                   "mix + 5 tail launches)"}
 json.dump(traffic, open(os.path.join(P, R + "_conv_traffic.json"), "w"), indent=1)
-for f in (R + "_configs.json",):
-    if os.path.exists(os.path.join(G, f)):
-        shutil.copy(os.path.join(G, f), os.path.join(P, f))
-shutil.copy(os.path.join(G, "bench_%s_n1.json" % R), os.path.join(P, R + "_bench_n1.json"))
-for f in ("ts_1.log", "ts_4.log", "ts_5.log", "knockout.log"):
-    if os.path.exists(os.path.join(G, f)):
-        shutil.copy(os.path.join(G, f), os.path.join(P, R + "_" + f.replace(".log", ".txt")))
 print(json.dumps(traffic, indent=1))
-print("step total %.2f ms" % T, [(k["kernel"], round(k["share"], 3)) for k in summ["kernels"][:4]])
+print("step total %.2f ms" % T, [(k["kernel"], round(k["share"], 3)) for k in summ["kernels"][:5]])
+for k in kernels:
+    print(k["layer"], k["gpu__time_duration.sum"], "tensor", k.get("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active"),
+          "dram %.2f TB/s" % k["derived_dram_TBps"], "%.0f B/px" % k["derived_dram_bytes_per_px"], "%.0f TF/s" % k.get("derived_useful_TFLOPs", 0))

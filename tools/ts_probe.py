@@ -11,8 +11,4 @@ e = rb.RealSR(0)
 assert e.load(os.path.join(ROOT, "models/models-DF2K/x4.param"), os.path.join(ROOT, "models/models-DF2K/x4.bin")) == 0
 cin = {1: 64, 2: 96, 3: 128, 4: 160, 5: 192}.get(idx, 64); cout = 64 if idx in (5,) or idx > 340 else 32
 x = np.zeros((H, W, cin), dtype=np.float16); x[::7, ::5] = 0.25
-if os.environ.get("RSR_IMPL"):
-    e.set_option("conv_impl", int(os.environ["RSR_IMPL"]))
-if os.environ.get("RSR_EPI_SPLIT"):
-    e.set_option("epilogue_split", int(os.environ["RSR_EPI_SPLIT"]))
 e.debug_conv(idx, x, cout)
