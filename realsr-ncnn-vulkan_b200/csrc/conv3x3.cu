@@ -61,8 +61,9 @@ constexpr int NEPI = 8;                       // epilogue warps
 constexpr int EPI_WARP0 = 4;                  // first epilogue warp: warps 0..3 are the control warpgroup
 constexpr int NTHREADS = (EPI_WARP0 + NEPI) * 32;
 // epilogue staging per warp: CONV_STORE16 stages one 32-pixel row of its output as a dense, swizzled TMA-store source
-// (32 x Cout fp16); the other modes transpose 32 x 16 words through a padded tile
-__host__ __device__ constexpr int stage_bytes(int nreal, int mode) { return mode == CONV_STORE16 ? 32 * nreal * 2 : 32 * 20 * 4; }
+// (32 x Cout fp16); the Cout = 64 residual modes transpose 32 px x 32 ch fp32 through a padded tile (row stride 36 words); the last
+// conv stores straight from registers
+__host__ __device__ constexpr int stage_bytes(int nreal, int mode) { return mode == CONV_STORE16 ? 32 * nreal * 2 : (nreal == 64 ? 32 * 36 * 4 : 1024); }
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_MAX = 227 * 1024 - 1024;   // dynamic part; the kernel also has ~300 B of static shared memory
 __host__ __device__ constexpr int smem_fixed(int nreal, int mode) { return 1024 /*align*/ + NEPI * stage_bytes(nreal, mode) + 256 /*barriers*/; }
@@ -447,7 +448,7 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
         // Group g = (warp-4)/4 owns accumulator set g, i.e. every second work tile; inside a group warp q4 handles row q4 of the
         // tile's M-tile(s).  (These convs are bounded by their MMAs or by HBM, not by the accumulator hand-over.)
         const int group = ew >> 2;
-        uint32_t* stg = reinterpret_cast<uint32_t*>(smStage + ew * STAGE_BYTES);  // [32 rows][20 words]
+        uint32_t* stg = reinterpret_cast<uint32_t*>(smStage + ew * STAGE_BYTES);  // [32 px][36 words]
         const int tr = lane >> 2, tc = lane & 3;
         const uint32_t acc_empty_leader = mapa_u32(smem_u32(&bars->acc_empty[group]), 0);
         const int buf = group;
@@ -470,23 +471,26 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             bool vcol[4];
 #pragma unroll
             for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < geo.W);
-            // residual operands.  fp32 modes (CONV_RDB_OUT with T32, CONV_TRUNK with F32): one (M-tile, 32-channel block) is
-            // fetched one block ahead of use.  CONV_RDB_OUT16: ALL fp16 x0 values this thread needs for the tile (4 blocks x
-            // 8 x 8 B = 64 registers) are requested here, before waiting for the MMAs -- per-tile timestamps showed the
-            // one-block-ahead scheme paying one memory latency (~3.7 k clk) per block, 15 k clk per tile against 7.5 k clk of
-            // MMAs.
+            // Residual operands of the Cout = 64 modes.  The fp32 math runs in a TRANSPOSED domain: a 32-channel block of the tile row
+            // goes through a [32 px][32 ch] smem tile, after which thread (tr, tc) holds 8 consecutive channels (tc*8..) of the four
+            // pixels tr, tr+8, tr+16, tr+24 -- every global access is then 16 B of fp16 / 32 B of fp32 / 8 B of int8 per lane and a
+            // full 64-B / 128-B / 32-B run per pixel.  CONV_RDB_OUT16: ALL fp16 x0 values (and int8 extensions) this thread needs
+            // for the tile are requested here, before waiting for the MMAs; fp32 modes (CONV_RDB_OUT with T32, CONV_TRUNK with
+            // F32) fetch one 32-channel block ahead of use.
             constexpr bool RDB16 = MODE == CONV_RDB_OUT16;
             constexpr bool RDB = MODE == CONV_RDB_OUT || RDB16;
-            float4 res[2][4];
-            uint2 x0raw[MT][2][2][4];  // [i][nb][hf][r], RDB16 only
-            auto load_res = [&](int i, int nb, float4 (&dst)[2][4]) {
+            float4 res[4][2];             // [r][8 channels] fp32 residual operands of the current block
+            uint4 x0raw[MT][2][4];        // [i][nb][r]: 8 fp16, RDB16 only
+            uint2 x0ext[MT][2][4];        // their int8 extensions (ConvArgs::ext_in)
+            auto load_res = [&](int i, int nb, float4 (&dst)[4][2]) {
                 if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
-                    const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + nb * 32 + tc * 4;
+                    const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + nb * 32 + tc * 8;
 #pragma unroll
-                    for (int hf = 0; hf < 2; hf++)
-#pragma unroll
-                        for (int r = 0; r < 4; r++)
-                            if (vcol[r] && vrow[i]) dst[hf][r] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + hf * 16);
+                    for (int r = 0; r < 4; r++)
+                        if (vcol[r] && vrow[i]) {
+                            dst[r][0] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64);
+                            dst[r][1] = *reinterpret_cast<const float4*>(base + (size_t)(tr + 8 * r) * 64 + 4);
+                        }
                 }
             };
             if constexpr (RDB16) {
@@ -495,12 +499,13 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
 #pragma unroll
                     for (int nb = 0; nb < 2; nb++)
 #pragma unroll
-                        for (int hf = 0; hf < 2; hf++)
-#pragma unroll
-                            for (int r = 0; r < 4; r++)
-                                if (vcol[r] && vrow[i])
-                                    x0raw[i][nb][hf][r] = *reinterpret_cast<const uint2*>(a.res16 + (rowpix[i] + tr + 8 * r) * 64 + nb * 32 + hf * 16 + tc * 4);
-            } else {
+                        for (int r = 0; r < 4; r++)
+                            if (vcol[r] && vrow[i]) {
+                                const size_t e = (rowpix[i] + tr + 8 * r) * 64 + nb * 32 + tc * 8;
+                                x0raw[i][nb][r] = *reinterpret_cast<const uint4*>(a.res16 + e);
+                                if (a.ext_in) x0ext[i][nb][r] = *reinterpret_cast<const uint2*>(a.ext_in + e);
+                            }
+            } else if constexpr (NREAL == 64) {
                 load_res(0, 0, res);
             }
             if constexpr (RDB) {
@@ -521,6 +526,30 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             tc_fence_after();
             if (ts_on) a.dbg_ts[ti * 8 + 5] = clock64();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS;
+            // Cout = 64 (conv5 / trunk): the accumulators go to registers first (taps combined) and the set returns to the MMA issuer
+            // before any residual math or store -- with 4-row tiles the whole epilogue (~4 k clk of memory latency per tile) would
+            // otherwise sit on the accumulator hand-over chain next to 3.5 k clk of MMAs.
+            uint32_t accv[NREAL == 64 ? MT : 1][NREAL == 64 ? 64 : 1];
+            if constexpr (NREAL == 64) {
+#pragma unroll
+                for (int i = 0; i < MT; i++)
+#pragma unroll
+                    for (int nb = 0; nb < 2; nb++) {
+                        uint32_t v[32], u[32], w[32];  // D[c] + right neighbour's D[64 + c] + second right neighbour's D[128 + c]
+                        tmem_ld32(taddr0 + i * DCOLS + nb * 32, v);
+                        tmem_ld32(taddr0 + i * DCOLS + 64 + nb * 32, u);
+                        tmem_ld32(taddr0 + i * DCOLS + 128 + nb * 32, w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            accv[i][nb * 32 + j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
+                                                                   __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2));
+                    }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(acc_empty_leader);  // CTA-scope release: only the TMEM reads have to be ordered
+                if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
+            }
 
             {
 #pragma unroll
@@ -558,86 +587,111 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                         // CONV_RDB_OUT / CONV_RDB_OUT16 / CONV_TRUNK (Cout = 64): fp32 math against the residual stream in the transposed domain
 #pragma unroll
                         for (int nb = 0; nb < 2; nb++) {
-                            uint32_t v[32], u[32], w[32];  // D[c] + right neighbour's D[64 + c] + second right neighbour's D[128 + c]
-                            tmem_ld32(taddr + nb * 32, v);
-                            tmem_ld32(taddr + 64 + nb * 32, u);
-                            tmem_ld32(taddr + 128 + nb * 32, w);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 32; j++)
-                                v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
-                                                       __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2));
-                            float4 nxt[2][4];
+                            const uint32_t* v = &accv[i][nb * 32];
+                            float4 nxt[4][2];
                             if constexpr (!RDB16) {  // prefetch the residual operands of the next (M-tile, 32-channel block)
                                 const int ni = nb == 1 ? i + 1 : i, nnb = nb ^ 1;
                                 if (ni < MT) load_res(ni, nnb, nxt);
                             }
 #pragma unroll
-                            for (int hf = 0; hf < 2; hf++) {
+                            for (int k = 0; k < 8; k++)  // this lane's pixel, 32 channels -> row `lane` of the tile (stride 36 words: conflict-free)
+                                *reinterpret_cast<uint4*>(stg + lane * 36 + 4 * k) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                            __syncwarp();
+                            const int ch0 = nb * 32 + tc * 8;
+                            const float4 bb0 = *reinterpret_cast<const float4*>(&s_bias[ch0]), bb1 = *reinterpret_cast<const float4*>(&s_bias[ch0 + 4]);
+                            float4 acc8[4][2];
 #pragma unroll
-                                for (int k = 0; k < 4; k++)
-                                    *reinterpret_cast<uint4*>(stg + lane * 20 + 4 * k) = make_uint4(v[16 * hf + 4 * k], v[16 * hf + 4 * k + 1], v[16 * hf + 4 * k + 2], v[16 * hf + 4 * k + 3]);
-                                __syncwarp();
-                                const int ch0 = nb * 32 + hf * 16 + tc * 4;
-                                const float4 bb = *reinterpret_cast<const float4*>(&s_bias[ch0]);
-                                float4 acc4[4];
-#pragma unroll
-                                for (int r = 0; r < 4; r++) acc4[r] = *reinterpret_cast<const float4*>(stg + (tr + 8 * r) * 20 + 4 * tc);
-                                __syncwarp();
-                                if constexpr (RDB16) {
-#pragma unroll
-                                    for (int r = 0; r < 4; r++) {
-                                        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&x0raw[i][nb][hf][r].x));
-                                        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&x0raw[i][nb][hf][r].y));
-                                        res[hf][r] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                                    }
-                                }
-                                float4 rr[4];
-                                if (RDB && a.rrdb_end) {
-#pragma unroll
-                                    for (int r = 0; r < 4; r++)
-                                        if (vcol[r] && vrow[i]) rr[r] = *reinterpret_cast<const float4*>(a.r32 + (rowpix[i] + tr + 8 * r) * 64 + ch0);
-                                }
+                            for (int r = 0; r < 4; r++) {
+                                acc8[r][0] = *reinterpret_cast<const float4*>(stg + (tr + 8 * r) * 36 + 8 * tc);
+                                acc8[r][1] = *reinterpret_cast<const float4*>(stg + (tr + 8 * r) * 36 + 8 * tc + 4);
+                            }
+                            __syncwarp();
+                            if constexpr (RDB16) {
 #pragma unroll
                                 for (int r = 0; r < 4; r++) {
-                                    float4 o;
+                                    const uint4 w = x0raw[i][nb][r];
+                                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+                                    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
+                                    res[r][0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                                    res[r][1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+                                    if (a.ext_in) {  // t = fp16 part + q / 256 ulp: the RDB input with 8 more mantissa bits
+                                        const uint32_t e0 = x0ext[i][nb][r].x, e1 = x0ext[i][nb][r].y;
+                                        res[r][0].x = res_ext_decode(f0.x, (int)(e0 << 24) >> 24); res[r][0].y = res_ext_decode(f0.y, (int)(e0 << 16) >> 24);
+                                        res[r][0].z = res_ext_decode(f1.x, (int)(e0 << 8) >> 24);  res[r][0].w = res_ext_decode(f1.y, (int)e0 >> 24);
+                                        res[r][1].x = res_ext_decode(f2.x, (int)(e1 << 24) >> 24); res[r][1].y = res_ext_decode(f2.y, (int)(e1 << 16) >> 24);
+                                        res[r][1].z = res_ext_decode(f3.x, (int)(e1 << 8) >> 24);  res[r][1].w = res_ext_decode(f3.y, (int)e1 >> 24);
+                                    }
+                                }
+                            }
+                            float4 rr[4][2];
+                            if (RDB && a.rrdb_end) {
+#pragma unroll
+                                for (int r = 0; r < 4; r++)
+                                    if (vcol[r] && vrow[i]) {
+                                        rr[r][0] = *reinterpret_cast<const float4*>(a.r32 + (rowpix[i] + tr + 8 * r) * 64 + ch0);
+                                        rr[r][1] = *reinterpret_cast<const float4*>(a.r32 + (rowpix[i] + tr + 8 * r) * 64 + ch0 + 4);
+                                    }
+                            }
+#pragma unroll
+                            for (int r = 0; r < 4; r++) {
+                                float4 o[2];
+#pragma unroll
+                                for (int q = 0; q < 2; q++) {
+                                    const float4 ac = acc8[r][q], bb = q ? bb1 : bb0, rs = res[r][q];
                                     if constexpr (RDB) {
-                                        o.x = (acc4[r].x + bb.x) * 0.2f + res[hf][r].x;
-                                        o.y = (acc4[r].y + bb.y) * 0.2f + res[hf][r].y;
-                                        o.z = (acc4[r].z + bb.z) * 0.2f + res[hf][r].z;
-                                        o.w = (acc4[r].w + bb.w) * 0.2f + res[hf][r].w;
+                                        o[q].x = (ac.x + bb.x) * 0.2f + rs.x; o[q].y = (ac.y + bb.y) * 0.2f + rs.y;
+                                        o[q].z = (ac.z + bb.z) * 0.2f + rs.z; o[q].w = (ac.w + bb.w) * 0.2f + rs.w;
                                         if (a.rrdb_end) {
-                                            o.x = o.x * 0.2f + rr[r].x; o.y = o.y * 0.2f + rr[r].y;
-                                            o.z = o.z * 0.2f + rr[r].z; o.w = o.w * 0.2f + rr[r].w;
+                                            o[q].x = o[q].x * 0.2f + rr[r][q].x; o[q].y = o[q].y * 0.2f + rr[r][q].y;
+                                            o[q].z = o[q].z * 0.2f + rr[r][q].z; o[q].w = o[q].w * 0.2f + rr[r][q].w;
                                         }
                                     } else {
-                                        o.x = acc4[r].x + bb.x + res[hf][r].x; o.y = acc4[r].y + bb.y + res[hf][r].y;
-                                        o.z = acc4[r].z + bb.z + res[hf][r].z; o.w = acc4[r].w + bb.w + res[hf][r].w;
+                                        o[q].x = ac.x + bb.x + rs.x; o[q].y = ac.y + bb.y + rs.y;
+                                        o[q].z = ac.z + bb.z + rs.z; o[q].w = ac.w + bb.w + rs.w;
                                     }
-                                    if (vcol[r] && vrow[i]) {
-                                        const size_t px = rowpix[i] + tr + 8 * r;
-                                        if constexpr (RDB) {
-                                            if (a.rrdb_end) *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0) = o;
-                                            if constexpr (!RDB16) *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o;
+                                }
+                                if (vcol[r] && vrow[i]) {
+                                    const size_t px = rowpix[i] + tr + 8 * r;
+                                    if constexpr (RDB) {
+                                        if (a.rrdb_end) {
+                                            *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0) = o[0];
+                                            *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0 + 4) = o[1];
                                         }
-                                        *reinterpret_cast<uint2*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint2(pack_h2(o.x, o.y), pack_h2(o.z, o.w));
+                                        if constexpr (!RDB16) {
+                                            *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o[0];
+                                            *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0 + 4) = o[1];
+                                        }
+                                    }
+                                    const uint32_t p0 = pack_h2(o[0].x, o[0].y), p1 = pack_h2(o[0].z, o[0].w), p2 = pack_h2(o[1].x, o[1].y), p3 = pack_h2(o[1].z, o[1].w);
+                                    *reinterpret_cast<uint4*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint4(p0, p1, p2, p3);
+                                    if constexpr (RDB16) {
+                                        if (a.ext_out) {
+                                            const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&p0)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&p1));
+                                            const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&p2)), g3 = __half22float2(*reinterpret_cast<const __half2*>(&p3));
+                                            const uint32_t q0 = (uint32_t)(res_ext_encode(o[0].x, g0.x) & 255) | ((uint32_t)(res_ext_encode(o[0].y, g0.y) & 255) << 8) |
+                                                                ((uint32_t)(res_ext_encode(o[0].z, g1.x) & 255) << 16) | ((uint32_t)res_ext_encode(o[0].w, g1.y) << 24);
+                                            const uint32_t q1 = (uint32_t)(res_ext_encode(o[1].x, g2.x) & 255) | ((uint32_t)(res_ext_encode(o[1].y, g2.y) & 255) << 8) |
+                                                                ((uint32_t)(res_ext_encode(o[1].z, g3.x) & 255) << 16) | ((uint32_t)res_ext_encode(o[1].w, g3.y) << 24);
+                                            *reinterpret_cast<uint2*>(a.ext_out + px * 64 + ch0) = make_uint2(q0, q1);
+                                        }
                                     }
                                 }
                             }
                             if constexpr (!RDB16) {
 #pragma unroll
-                                for (int h2 = 0; h2 < 2; h2++)
-#pragma unroll
-                                    for (int r = 0; r < 4; r++) res[h2][r] = nxt[h2][r];
+                                for (int r = 0; r < 4; r++) { res[r][0] = nxt[r][0]; res[r][1] = nxt[r][1]; }
                             }
                         }
                     }
                 }
-                // accumulator set drained by this warp: tell the leader's MMA issuer (CTA-scope release, see above)
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(acc_empty_leader);
-                if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
+                if constexpr (NREAL != 64) {  // accumulator set drained by this warp: tell the leader's MMA issuer (CTA-scope release)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(acc_empty_leader);
+                    if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
+                } else if (ts_on) {
+                    a.dbg_ts[ti * 8 + 7] = clock64();
+                }
             }
         }
       }

@@ -60,8 +60,12 @@ struct ConvArgs {
     float* t32;
     float* r32;
     const float* f32;
-    const __half* res16;  // CONV_RDB_OUT, optional: take the RDB input from this fp16 plane (64 ch/px) instead of T32 and do
-                          // not write T32 ("residual_fp16" engine option; the RRDB-level skip R32 stays fp32)
+    const __half* res16;  // CONV_RDB_OUT16: take the RDB input from this fp16 plane (64 ch/px) instead of T32 and do not write T32
+                          // ("residual_fp16" engine option; the RRDB-level skip R32 stays fp32)
+    const uint8_t* ext_in;   // CONV_RDB_OUT16, optional ("residual_ext" engine option): int8 [px][64] extension of res16 -- the RDB
+    uint8_t* ext_out;        // input t is carried as fp16(t) + q / 256 of an fp16 ulp (res_ext_encode below), i.e. with 8 more mantissa
+                             // bits than the fp16 MMA operand (64 B/px instead of the 256 B/px of an fp32 copy); ext_out is the
+                             // extension written next to out16 for the next dense block
     int rrdb_end;
     // CONV_LAST_*
     const TileDesc* tiles;
@@ -94,6 +98,17 @@ struct alignas(64) ConvMaps {
 };
 // conv3x3.cu: conv3x3 s1 p1 (+ fused epilogue, see ConvMode) as implicit GEMM on tcgen05 CTA pairs.  cout_pad in {16, 32, 64}.
 cudaError_t launch_conv3x3(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
+
+// Residual carrier (ConvArgs::ext_in / ext_out): a value v travels as its round-to-nearest fp16 h (the MMA operand) plus an int8 q that
+// counts 1/256 of h's ulp: q = round((bits(v) - bits(float(h))) / 32) on the fp32 bit patterns (13 more mantissa bits in fp32 than in
+// fp16, 8 of them kept; bit-pattern arithmetic is monotonic across binades and sign-symmetric), clamped to int8.  Decoding adds q * 32
+// fp32-ulps back.  Values below the fp16 normal range simply clamp (absolute error < 2^-25 either way).
+__device__ __forceinline__ int res_ext_encode(float v, float hf)
+{
+    const int d = (__float_as_int(v) - __float_as_int(hf) + 16) >> 5;
+    return max(-128, min(127, d));
+}
+__device__ __forceinline__ float res_ext_decode(float hf, int q) { return __int_as_float(__float_as_int(hf) + q * 32); }
 constexpr int CONV_P = 32;      // position pitch of a work tile (32 px: 30 output columns + the two halo columns)
 constexpr int CONV_BW = 30;     // output columns per work tile
 // output rows per CTA of a pair and work tile: 4 for the Cout = 64 convs (one N = 192 MMA per k-step: 192 TMEM columns per M-tile),
@@ -110,9 +125,10 @@ struct FirstArgs {
     const float* bias;
     int H, W, B;
     __half* d16;         // plane 0 of D16[0] (64 ch per pixel)
-    float* t32;
+    float* t32;          // optional (residual_fp16 = 0)
     float* r32;
     float* f32;
+    uint8_t* ext;        // optional: int8 [px][64] extension of d16 (see ConvArgs::ext_in)
 };
 cudaError_t launch_conv_first(const FirstArgs& a, cudaStream_t stream);
 

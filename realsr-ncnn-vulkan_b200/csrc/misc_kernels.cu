@@ -104,19 +104,22 @@ __global__ void __launch_bounds__(FIRST_THREADS) conv_first_kernel(const FirstAr
         r[j4] = o; f[j4] = o;
     }
     uint4* d = reinterpret_cast<uint4*>(a.d16 + pix * 64 + quarter * 16);
+    uint32_t ext[4] = {0, 0, 0, 0};  // int8 extensions of the 16 fp16 values (ConvArgs::ext_in), 4 per word
 #pragma unroll
     for (int j8 = 0; j8 < 2; j8++) {
-        __half2 h0 = __floats2half2_rn(acc[j8 * 8 + 0], acc[j8 * 8 + 1]);
-        __half2 h1 = __floats2half2_rn(acc[j8 * 8 + 2], acc[j8 * 8 + 3]);
-        __half2 h2 = __floats2half2_rn(acc[j8 * 8 + 4], acc[j8 * 8 + 5]);
-        __half2 h3 = __floats2half2_rn(acc[j8 * 8 + 6], acc[j8 * 8 + 7]);
-        uint4 o;
-        o.x = *reinterpret_cast<uint32_t*>(&h0);
-        o.y = *reinterpret_cast<uint32_t*>(&h1);
-        o.z = *reinterpret_cast<uint32_t*>(&h2);
-        o.w = *reinterpret_cast<uint32_t*>(&h3);
-        d[j8] = o;
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float v0 = acc[j8 * 8 + 2 * k], v1 = acc[j8 * 8 + 2 * k + 1];
+            __half2 hh = __floats2half2_rn(v0, v1);
+            pk[k] = *reinterpret_cast<uint32_t*>(&hh);
+            const float2 f = __half22float2(hh);
+            const uint32_t q = (uint32_t)(res_ext_encode(v0, f.x) & 255) | ((uint32_t)(res_ext_encode(v1, f.y) & 255) << 8);
+            ext[j8 * 2 + (k >> 1)] |= q << (16 * (k & 1));
+        }
+        d[j8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
+    if (a.ext) *reinterpret_cast<uint4*>(a.ext + pix * 64 + quarter * 16) = make_uint4(ext[0], ext[1], ext[2], ext[3]);
 }
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, int in_vec_stride, uint4* __restrict__ out, int B, int H, int W)

@@ -2,9 +2,11 @@
 Python mirror of the reference's `class RealSR`.
 
 Tolerance contract (vs the reference's own CPU path at the same tile size; stated here because the path is
-floating point: fp16 tensor-core operands with fp32 accumulation, fp32 Conv_0 and fp32 residual stream):
-  * natural images : every byte within 1 LSB, >= 95 % of bytes exact
+floating point: fp16 tensor-core operands with fp32 accumulation, fp32 Conv_0, fp32 RRDB skip stream, dense-block residual
+carried as fp16 + int8 extension):
+  * natural images : every byte within 1 LSB, >= 97 % of bytes exact
   * uniform noise  : max 2 LSB, at most 1 byte in 10 000 off by more than 1 LSB
+(measured on B200, tools/parity_report.py: natural 0.6 - 2.4 % of bytes off by one; noise 5 - 14 %, 3 - 8 bytes of 3 M at 2 LSB)
 Per-layer: abs-or-relative 2e-3 against an fp32 torch conv on the same fp16 operands (ncnn's own Winograd-eligible
 conv tolerance, ncnn/tests/test_convolution.cpp:42-52), result rounded to fp16 as the engine stores it.
 """
@@ -41,7 +43,7 @@ def run(model, img, tilesize, tta=False):
 
 def check_contract(s, natural):
     if natural:
-        assert s["max"] <= 1 and s["frac_diff"] <= 0.05, s
+        assert s["max"] <= 1 and s["frac_diff"] <= 0.03, s
     else:
         assert s["max"] <= 2 and s["n_gt1"] <= max(2, s["n"] // 10000), s
 

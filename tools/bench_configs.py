@@ -2,7 +2,7 @@
 """Measures every single-GPU BASELINE.json config (not only the headline one bench.py reports):
    cfg1 256x256 (T=200, T=256, DF2K_JPEG), cfg2 1920x1080 T=400, cfg4 3840x2160 T=200, cfg5 1280x720 TTA T=200.
 Device-resident input/output (rsr_process_device), CUDA-event time of the call, median of 5 after 2 warm-ups.
-Writes gpurun_out/r1_configs.json (copy it to profiles/)."""
+Writes gpurun_out/r2_configs.json (copy it to profiles/)."""
 import json, os, sys
 import numpy as np
 import torch
@@ -38,4 +38,4 @@ for name, model, w, h, tile, tta in CFG:
     out.append(rec)
     del e
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "r1_configs.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "r2_configs.json"), "w"), indent=1)

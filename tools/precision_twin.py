@@ -2,8 +2,9 @@
 """CPU model of the engine's precision choices (torch, no GPU): where do the LSBs against the reference come from, and what
 would each candidate change buy?  The network is evaluated on single-tile goldens with activations rounded to fp16 exactly
 where the engine stores fp16 (fp32 accumulation everywhere), then with one choice changed at a time:
-    engine      : what csrc/ does by default (fp32 Conv_0, fp16 dense planes, fp16 x0 for the dense-block residual, fp32
-                  RRDB skip stream, fp16 tail activations)
+    engine      : what csrc/ does by default (fp32 Conv_0, fp16 dense planes, dense-block residual from fp16 x0 + its int8 extension
+                  (kernels.h res_ext_encode: 1/256 of an fp16 ulp), fp32 RRDB skip stream, fp16 tail activations)
+    res16       : residual_ext = 0 (round-1 default: dense-block residual from the fp16 operand plane alone)
     res32       : residual_fp16 = 0 (dense-block residual from an fp32 copy)
     tail32      : + the four tail convs (after the trunk) read and write fp32 activations ("exact tail")
     subpix      : engine precision, but the two "nearest x2 + conv" pairs collapsed into four 2x2 sub-pixel convs on the low-res
@@ -25,6 +26,15 @@ from common import golden, manifest, read_convs, diff_stats
 torch.set_num_threads(8)
 H16 = lambda t: t.half().float()
 ID = lambda t: t
+
+
+def EXT8(t):
+    """fp16 value + int8 extension counting 1/256 of its ulp, computed on the fp32 bit patterns exactly like kernels.h res_ext_encode /
+    res_ext_decode"""
+    hf = t.half().float()
+    bv, bh = t.contiguous().view(torch.int32).to(torch.int64), hf.contiguous().view(torch.int32).to(torch.int64)
+    q = torch.clamp((bv - bh + 16) >> 5, -128, 127)
+    return (bh + q * 32).to(torch.int32).view(torch.float32)
 
 
 def upconv_collapsed(t, c):
@@ -67,7 +77,7 @@ def conv_winograd(t, c):
     return F.leaky_relu(y, 0.2) if c["act"] == 2 else y
 
 
-def net(x, convs, q_body, q_x0res, q_tail, nb=23, q_tails=None, collapse=False, wino=False):
+def net(x, convs, q_body, q_x0res, q_tail, nb=23, q_tails=None, collapse=False, wino=False, q_rrdb=None):
     """x: [1,3,H,W] fp32 in 0..1.  q_*: rounding applied where the engine stores fp16."""
     def conv(i, t):
         c = convs[i]
@@ -88,7 +98,7 @@ def net(x, convs, q_body, q_x0res, q_tail, nb=23, q_tails=None, collapse=False, 
             x5 = conv(idx + 4, torch.cat(feats, 1))
             t = 0.2 * x5 + (q_x0res(t32) if q_x0res is not ID else t32)
             if rdb == 2:
-                t = 0.2 * t + r32
+                t = 0.2 * t + (q_rrdb(r32) if q_rrdb else r32)
                 r32 = t
             t32 = t
             x0 = q_body(t)
@@ -117,12 +127,12 @@ def run(name, mode):
     P = 10
     x = torch.from_numpy(img.astype(np.float32)).permute(2, 0, 1)[None] * (1 / 255.0)
     x = F.pad(x, (P, P, P, P), mode="reflect")
-    q = dict(engine=(H16, H16, H16), res32=(H16, ID, H16), tail32=(H16, ID, ID), body32=(ID, ID, H16), all32=(ID, ID, ID),
+    q = dict(engine=(H16, EXT8, H16), rext=(H16, EXT8, H16), res16=(H16, H16, H16), res32=(H16, ID, H16), tail32=(H16, ID, ID), body32=(ID, ID, H16), all32=(ID, ID, ID),
              hr32=(H16, H16, H16), v2hr32=(H16, H16, H16), trunk32=(H16, H16, H16), subpix=(H16, H16, H16), wino=(H16, H16, H16))[mode]
     # single tail tensors kept exact (engine precision elsewhere): which hand-off carries the error?
     q_tails = dict(hr32=(H16, H16, H16, ID), v2hr32=(H16, H16, ID, ID), trunk32=(ID, H16, H16, H16)).get(mode)
     with torch.no_grad():
-        y = net(x, convs, *q, q_tails=q_tails, collapse=(mode == "subpix"), wino=(mode == "wino"))[0, :, 4 * P:4 * P + 4 * h, 4 * P:4 * P + 4 * w]
+        y = net(x, convs, *q, q_tails=q_tails, collapse=(mode == "subpix"), wino=(mode == "wino"), q_rrdb=(EXT8 if mode == "rext" else None))[0, :, 4 * P:4 * P + 4 * h, 4 * P:4 * P + 4 * w]
     out = torch.clamp((y * 255.0 + 0.5).to(torch.int32), 0, 255).permute(1, 2, 0).numpy().astype(np.uint8)  # (int) truncation like the reference
     return diff_stats(out, gold[..., :3])
 
@@ -132,6 +142,6 @@ if __name__ == "__main__":
     for name in names:
         if "tta" in name:
             continue  # TTA goldens average 8 passes: not modelled here
-        for mode in ("engine", "res32", "tail32", "hr32", "v2hr32", "trunk32", "subpix", "wino", "body32", "all32"):
+        for mode in ("engine", "rext", "res16", "res32", "tail32", "hr32", "v2hr32", "trunk32", "subpix", "wino", "body32", "all32"):
             s = run(name, mode)
             print("%-28s %-7s max %d  off-by-one %.3f %%  >1: %d of %d" % (name, mode, s["max"], 100 * s["frac_diff"], s["n_gt1"], s["n"]), flush=True)
