@@ -474,17 +474,18 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             // Residual operands of the Cout = 64 modes.  The fp32 math runs in a TRANSPOSED domain: a 32-channel block of the tile row
             // goes through a [32 px][32 ch] smem tile, after which thread (tr, tc) holds 8 consecutive channels (tc*8..) of the four
             // pixels tr, tr+8, tr+16, tr+24 -- every global access is then 16 B of fp16 / 32 B of fp32 / 8 B of int8 per lane and a
-            // full 64-B / 128-B / 32-B run per pixel.  CONV_RDB_OUT16: ALL fp16 x0 values (and int8 extensions) this thread needs
-            // for the tile are requested here, before waiting for the MMAs; fp32 modes (CONV_RDB_OUT with T32, CONV_TRUNK with
-            // F32) fetch one 32-channel block ahead of use.
-            constexpr bool RDB16 = MODE == CONV_RDB_OUT16;
-            constexpr bool RDB = MODE == CONV_RDB_OUT || RDB16;
+            // full 64-B / 128-B / 32-B run per pixel.  CONV_RDB: ALL fp16 x0 values and int8 extensions this thread needs for the
+            // tile are requested here, before waiting for the MMAs (a memory latency per block otherwise), the RRDB-level operands of
+            // the first block too; CONV_TRUNK fetches its fp32 operands one 32-channel block ahead of use.
+            constexpr bool RDB = MODE == CONV_RDB;
             float4 res[4][2];             // [r][8 channels] fp32 residual operands of the current block
-            uint4 x0raw[MT][2][4];        // [i][nb][r]: 8 fp16, RDB16 only
-            uint2 x0ext[MT][2][4];        // their int8 extensions (ConvArgs::ext_in)
+            uint4 x0raw[MT][2][4];        // [i][nb][r]: 8 fp16 of the block input x0
+            uint2 x0ext[MT][2][4];        // their int8 extensions
+            uint4 rrraw[2][4];            // [nb][r]: the RRDB input R (rrdb_end only), loaded one block ahead
+            uint2 rrext[2][4];
             auto load_res = [&](int i, int nb, float4 (&dst)[4][2]) {
-                if constexpr (MODE == CONV_RDB_OUT || MODE == CONV_TRUNK) {
-                    const float* base = (MODE == CONV_RDB_OUT ? a.t32 : a.f32) + rowpix[i] * 64 + nb * 32 + tc * 8;
+                if constexpr (MODE == CONV_TRUNK) {
+                    const float* base = a.f32 + rowpix[i] * 64 + nb * 32 + tc * 8;
 #pragma unroll
                     for (int r = 0; r < 4; r++)
                         if (vcol[r] && vrow[i]) {
@@ -493,7 +494,18 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                         }
                 }
             };
-            if constexpr (RDB16) {
+            auto load_rr = [&](int i, int nb) {
+                if constexpr (RDB) {
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (vcol[r] && vrow[i]) {
+                            const size_t e = (rowpix[i] + tr + 8 * r) * 64 + nb * 32 + tc * 8;
+                            rrraw[nb][r] = *reinterpret_cast<const uint4*>(a.rr16 + e);
+                            rrext[nb][r] = *reinterpret_cast<const uint2*>(a.rr_ext + e);
+                        }
+                }
+            };
+            if constexpr (RDB) {
 #pragma unroll
                 for (int i = 0; i < MT; i++)
 #pragma unroll
@@ -503,21 +515,11 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                             if (vcol[r] && vrow[i]) {
                                 const size_t e = (rowpix[i] + tr + 8 * r) * 64 + nb * 32 + tc * 8;
                                 x0raw[i][nb][r] = *reinterpret_cast<const uint4*>(a.res16 + e);
-                                if (a.ext_in) x0ext[i][nb][r] = *reinterpret_cast<const uint2*>(a.ext_in + e);
+                                x0ext[i][nb][r] = *reinterpret_cast<const uint2*>(a.ext_in + e);
                             }
+                if (a.rrdb_end) load_rr(0, 0);
             } else if constexpr (NREAL == 64) {
                 load_res(0, 0, res);
-            }
-            if constexpr (RDB) {
-                if (a.rrdb_end) {  // the RRDB-level skip operands of THIS tile: pull the rows into L2 while the MMAs run
-#pragma unroll
-                    for (int i = 0; i < MT; i++)
-                        if (vrow[i]) {
-                            const int npx = min(BW, geo.W - x0);
-                            const char* p1 = reinterpret_cast<const char*>(a.r32 + rowpix[i] * 64);
-                            for (int l = lane; l < npx * 2; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + (size_t)l * 128));
-                        }
-                }
             }
             const bool ts_on = a.dbg_ts != nullptr && cluster_id == 0 && ti < 64 && is_leader && (ew & 3) == 0 && lane == 0;
             if (ts_on) a.dbg_ts[ti * 8 + 4] = clock64();
@@ -584,14 +586,24 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                             }
                         }
                     } else {
-                        // CONV_RDB_OUT / CONV_RDB_OUT16 / CONV_TRUNK (Cout = 64): fp32 math against the residual stream in the transposed domain
+                        // CONV_RDB / CONV_TRUNK (Cout = 64): fp32 math against the residual stream in the transposed domain
+                        auto dec8 = [&](const uint4 w, const uint2 e, float4 (&dst)[2]) {  // 8 x (fp16 + int8 extension) -> fp32
+                            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+                            const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
+                            dst[0].x = res_ext_decode(f0.x, (int)(e.x << 24) >> 24); dst[0].y = res_ext_decode(f0.y, (int)(e.x << 16) >> 24);
+                            dst[0].z = res_ext_decode(f1.x, (int)(e.x << 8) >> 24);  dst[0].w = res_ext_decode(f1.y, (int)e.x >> 24);
+                            dst[1].x = res_ext_decode(f2.x, (int)(e.y << 24) >> 24); dst[1].y = res_ext_decode(f2.y, (int)(e.y << 16) >> 24);
+                            dst[1].z = res_ext_decode(f3.x, (int)(e.y << 8) >> 24);  dst[1].w = res_ext_decode(f3.y, (int)e.y >> 24);
+                        };
 #pragma unroll
                         for (int nb = 0; nb < 2; nb++) {
                             const uint32_t* v = &accv[i][nb * 32];
                             float4 nxt[4][2];
-                            if constexpr (!RDB16) {  // prefetch the residual operands of the next (M-tile, 32-channel block)
+                            if constexpr (!RDB) {  // prefetch the residual operands of the next (M-tile, 32-channel block)
                                 const int ni = nb == 1 ? i + 1 : i, nnb = nb ^ 1;
                                 if (ni < MT) load_res(ni, nnb, nxt);
+                            } else {
+                                if (a.rrdb_end && nb == 0) load_rr(i, 1);
                             }
 #pragma unroll
                             for (int k = 0; k < 8; k++)  // this lane's pixel, 32 channels -> row `lane` of the tile (stride 36 words: conflict-free)
@@ -606,34 +618,9 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                                 acc8[r][1] = *reinterpret_cast<const float4*>(stg + (tr + 8 * r) * 36 + 8 * tc + 4);
                             }
                             __syncwarp();
-                            if constexpr (RDB16) {
-#pragma unroll
-                                for (int r = 0; r < 4; r++) {
-                                    const uint4 w = x0raw[i][nb][r];
-                                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
-                                    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
-                                    res[r][0] = make_float4(f0.x, f0.y, f1.x, f1.y);
-                                    res[r][1] = make_float4(f2.x, f2.y, f3.x, f3.y);
-                                    if (a.ext_in) {  // t = fp16 part + q / 256 ulp: the RDB input with 8 more mantissa bits
-                                        const uint32_t e0 = x0ext[i][nb][r].x, e1 = x0ext[i][nb][r].y;
-                                        res[r][0].x = res_ext_decode(f0.x, (int)(e0 << 24) >> 24); res[r][0].y = res_ext_decode(f0.y, (int)(e0 << 16) >> 24);
-                                        res[r][0].z = res_ext_decode(f1.x, (int)(e0 << 8) >> 24);  res[r][0].w = res_ext_decode(f1.y, (int)e0 >> 24);
-                                        res[r][1].x = res_ext_decode(f2.x, (int)(e1 << 24) >> 24); res[r][1].y = res_ext_decode(f2.y, (int)(e1 << 16) >> 24);
-                                        res[r][1].z = res_ext_decode(f3.x, (int)(e1 << 8) >> 24);  res[r][1].w = res_ext_decode(f3.y, (int)e1 >> 24);
-                                    }
-                                }
-                            }
-                            float4 rr[4][2];
-                            if (RDB && a.rrdb_end) {
-#pragma unroll
-                                for (int r = 0; r < 4; r++)
-                                    if (vcol[r] && vrow[i]) {
-                                        rr[r][0] = *reinterpret_cast<const float4*>(a.r32 + (rowpix[i] + tr + 8 * r) * 64 + ch0);
-                                        rr[r][1] = *reinterpret_cast<const float4*>(a.r32 + (rowpix[i] + tr + 8 * r) * 64 + ch0 + 4);
-                                    }
-                            }
 #pragma unroll
                             for (int r = 0; r < 4; r++) {
+                                if constexpr (RDB) dec8(x0raw[i][nb][r], x0ext[i][nb][r], res[r]);
                                 float4 o[2];
 #pragma unroll
                                 for (int q = 0; q < 2; q++) {
@@ -641,43 +628,38 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                                     if constexpr (RDB) {
                                         o[q].x = (ac.x + bb.x) * 0.2f + rs.x; o[q].y = (ac.y + bb.y) * 0.2f + rs.y;
                                         o[q].z = (ac.z + bb.z) * 0.2f + rs.z; o[q].w = (ac.w + bb.w) * 0.2f + rs.w;
-                                        if (a.rrdb_end) {
-                                            o[q].x = o[q].x * 0.2f + rr[r][q].x; o[q].y = o[q].y * 0.2f + rr[r][q].y;
-                                            o[q].z = o[q].z * 0.2f + rr[r][q].z; o[q].w = o[q].w * 0.2f + rr[r][q].w;
-                                        }
                                     } else {
                                         o[q].x = ac.x + bb.x + rs.x; o[q].y = ac.y + bb.y + rs.y;
                                         o[q].z = ac.z + bb.z + rs.z; o[q].w = ac.w + bb.w + rs.w;
                                     }
                                 }
-                                if (vcol[r] && vrow[i]) {
-                                    const size_t px = rowpix[i] + tr + 8 * r;
-                                    if constexpr (RDB) {
-                                        if (a.rrdb_end) {
-                                            *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0) = o[0];
-                                            *reinterpret_cast<float4*>(a.r32 + px * 64 + ch0 + 4) = o[1];
-                                        }
-                                        if constexpr (!RDB16) {
-                                            *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0) = o[0];
-                                            *reinterpret_cast<float4*>(a.t32 + px * 64 + ch0 + 4) = o[1];
-                                        }
-                                    }
-                                    const uint32_t p0 = pack_h2(o[0].x, o[0].y), p1 = pack_h2(o[0].z, o[0].w), p2 = pack_h2(o[1].x, o[1].y), p3 = pack_h2(o[1].z, o[1].w);
-                                    *reinterpret_cast<uint4*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint4(p0, p1, p2, p3);
-                                    if constexpr (RDB16) {
-                                        if (a.ext_out) {
-                                            const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&p0)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&p1));
-                                            const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&p2)), g3 = __half22float2(*reinterpret_cast<const __half2*>(&p3));
-                                            const uint32_t q0 = (uint32_t)(res_ext_encode(o[0].x, g0.x) & 255) | ((uint32_t)(res_ext_encode(o[0].y, g0.y) & 255) << 8) |
-                                                                ((uint32_t)(res_ext_encode(o[0].z, g1.x) & 255) << 16) | ((uint32_t)res_ext_encode(o[0].w, g1.y) << 24);
-                                            const uint32_t q1 = (uint32_t)(res_ext_encode(o[1].x, g2.x) & 255) | ((uint32_t)(res_ext_encode(o[1].y, g2.y) & 255) << 8) |
-                                                                ((uint32_t)(res_ext_encode(o[1].z, g3.x) & 255) << 16) | ((uint32_t)res_ext_encode(o[1].w, g3.y) << 24);
-                                            *reinterpret_cast<uint2*>(a.ext_out + px * 64 + ch0) = make_uint2(q0, q1);
+                                if constexpr (RDB) {
+                                    if (a.rrdb_end) {  // t = 0.2*t + R (Eltwise at the end of an RRDB, x4.param:47)
+                                        float4 rr[2];
+                                        dec8(rrraw[nb][r], rrext[nb][r], rr);
+#pragma unroll
+                                        for (int q = 0; q < 2; q++) {
+                                            o[q].x = o[q].x * 0.2f + rr[q].x; o[q].y = o[q].y * 0.2f + rr[q].y;
+                                            o[q].z = o[q].z * 0.2f + rr[q].z; o[q].w = o[q].w * 0.2f + rr[q].w;
                                         }
                                     }
                                 }
+                                if (vcol[r] && vrow[i]) {
+                                    const size_t px = rowpix[i] + tr + 8 * r;
+                                    const uint32_t p0 = pack_h2(o[0].x, o[0].y), p1 = pack_h2(o[0].z, o[0].w), p2 = pack_h2(o[1].x, o[1].y), p3 = pack_h2(o[1].z, o[1].w);
+                                    *reinterpret_cast<uint4*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint4(p0, p1, p2, p3);
+                                    if constexpr (RDB) {
+                                        const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&p0)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&p1));
+                                        const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&p2)), g3 = __half22float2(*reinterpret_cast<const __half2*>(&p3));
+                                        const uint32_t q0 = (uint32_t)(res_ext_encode(o[0].x, g0.x) & 255) | ((uint32_t)(res_ext_encode(o[0].y, g0.y) & 255) << 8) |
+                                                            ((uint32_t)(res_ext_encode(o[0].z, g1.x) & 255) << 16) | ((uint32_t)res_ext_encode(o[0].w, g1.y) << 24);
+                                        const uint32_t q1 = (uint32_t)(res_ext_encode(o[1].x, g2.x) & 255) | ((uint32_t)(res_ext_encode(o[1].y, g2.y) & 255) << 8) |
+                                                            ((uint32_t)(res_ext_encode(o[1].z, g3.x) & 255) << 16) | ((uint32_t)res_ext_encode(o[1].w, g3.y) << 24);
+                                        *reinterpret_cast<uint2*>(a.ext_out + px * 64 + ch0) = make_uint2(q0, q1);
+                                    }
+                                }
                             }
-                            if constexpr (!RDB16) {
+                            if constexpr (!RDB) {
 #pragma unroll
                                 for (int r = 0; r < 4; r++) { res[r][0] = nxt[r][0]; res[r][1] = nxt[r][1]; }
                             }
@@ -749,8 +731,7 @@ cudaError_t launch_conv3x3(const ConvMaps* in_map, const ConvArgs& a, int cout_p
 {
     if (cout_pad == 32 && a.mode == CONV_STORE16) return launch_nm<32, CONV_STORE16>(in_map, a, stream);
     if (cout_pad == 64 && a.mode == CONV_STORE16) return launch_nm<64, CONV_STORE16>(in_map, a, stream);
-    if (cout_pad == 64 && a.mode == CONV_RDB_OUT) return launch_nm<64, CONV_RDB_OUT>(in_map, a, stream);
-    if (cout_pad == 64 && a.mode == CONV_RDB_OUT16) return launch_nm<64, CONV_RDB_OUT16>(in_map, a, stream);
+    if (cout_pad == 64 && a.mode == CONV_RDB) return launch_nm<64, CONV_RDB>(in_map, a, stream);
     if (cout_pad == 64 && a.mode == CONV_TRUNK) return launch_nm<64, CONV_TRUNK>(in_map, a, stream);
     if (cout_pad == 16 && a.mode == CONV_LAST_U8) return launch_nm<16, CONV_LAST_U8>(in_map, a, stream);
     if (cout_pad == 16 && a.mode == CONV_LAST_F32) return launch_nm<16, CONV_LAST_F32>(in_map, a, stream);

@@ -50,16 +50,19 @@ struct DevBuf {
 };
 
 // Tensor maps of the activation buffers of one job (one or several same-shape tile groups), built once per job.
-// Dense-block buffer D16[i] of a job with npx network-input pixels: plane 0 = [npx][64] (the RDB input x0), then x1..x4 as four
-// [npx][32] planes -- one plane per 32-channel K-block of the growth convs, so that a conv reads exactly the channels it needs
-// (ncu, 64-channel pair planes: the 96- and 160-channel convs fetched a whole 128-B line per pixel for 64 useful bytes and ran
-// at 5.5-6.2 TB/s of DRAM traffic, i.e. HBM-bound).  K-block k of a conv's input lives in map m[k]: k = 0, 1 -> the two halves
-// of plane 0 (channel coordinate 32k), k >= 2 -> plane k-1.  The 64-channel tail buffers use k = 0, 1 only.
+// Dense-block activations of a job with npx network-input pixels: the block input x0 lives in one of THREE rotating planes X0[i]
+// [npx][64] fp16 (+ its int8 extension E8[i] [npx][64], see ConvArgs::res16): conv5 writes the next block's x0 into another plane
+// than it reads (neighbouring CTAs still read this one's halo), and the input of the enclosing RRDB survives until that RRDB's last
+// block adds it back -- in the same fp16 + int8 form, so no fp32 copy of the stream exists.  The growth channels x1..x4 live in ONE
+// buffer XG as four [npx][32] planes -- one plane per 32-channel K-block, so that a conv reads exactly the channels it needs (ncu,
+// 64-channel pair planes: the 96- and 160-channel convs fetched a whole 128-B line per pixel for 64 useful bytes and ran at
+// 5.5-6.2 TB/s of DRAM traffic, i.e. HBM-bound).  K-block k of a conv's input lives in map m[k]: k = 0, 1 -> the two halves of
+// X0[i] (channel coordinate 32k), k >= 2 -> plane k-2 of XG.  The 64-channel tail buffers use k = 0, 1 only.
 struct JobMaps {
-    ConvMaps d8[2], d4[2];          // dense buffers with 10-row boxes (Cout=32 convs) and 6-row boxes (Cout=64 convs: conv5, trunk)
+    ConvMaps d8[3], d4[3];          // [X0 plane] with 10-row boxes (Cout=32 convs) and 6-row boxes (Cout=64 convs: conv5, trunk)
     ConvMaps u1_4, u2_4, v2_4;      // tail inputs of the Cout=64 convs (up1 reads U1, up2 reads U2, HR conv reads V2): 6-row boxes
     ConvMaps u2_8;                  // last conv (Cout=3, 8-row tiles) reads U2
-    CUtensorMap oD[2][4][4];        // [buffer][x1..x4][group]: output maps of the growth convs
+    CUtensorMap oD[4][4];           // [x1..x4][group]: output maps of the growth convs
     CUtensorMap oV1[4], oV2[4], oU2[4];
 };
 inline CUtensorMap* map_slot(ConvMaps& cm, int g, int k) { return g == 0 ? &cm.m[k] : &cm.mg[g - 1][k]; }
@@ -67,7 +70,7 @@ inline CUtensorMap* map_slot(ConvMaps& cm, int g, int k) { return g == 0 ? &cm.m
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf d16[2], e8[2], t32, r32, f32, u1, v1, u2, v2, tta, tiles, img_in, img_out;
+    DevBuf x0[3], e8[3], xg, f32, u1, v1, u2, v2, tta, tiles, img_in, img_out;
     JobMaps maps;                 // tensor maps of the job being enqueued (kernel parameters are copied at launch)
     TileDesc* h_tiles = nullptr;  // pinned staging for the tile descriptors of one process() call
     size_t h_tiles_cap = 0;
@@ -96,15 +99,6 @@ struct rsr_handle {
     // options
     long long max_batch = 0;  // 0 = auto
     int merge_shapes = 1;     // one launch per layer over all shape groups of a job (see run_job); 0 = one job per shape group
-    // 1 (default): the RDB-level residual t = 0.2*x5 + x0 takes x0 from the fp16 dense buffer instead of an fp32 copy (the
-    // RRDB-level skip stays fp32).  Measured on the goldens: max error unchanged (1 LSB natural / 2 LSB noise), off-by-one
-    // bytes 1.8->2.1 %, 2.4->3.2 % (natural), 5.3 % faster: the Cout=64 conv is HBM-bound and this removes 384 of its
-    // 1024 bytes per pixel.  0 restores the fp32 RDB stream.
-    int residual_fp16 = 1;
-    // 1 (default, with residual_fp16 = 1): the RDB input travels as fp16 + an int8 extension (8 more mantissa bits, ConvArgs::ext_in):
-    // the dense-block residual t = 0.2*x5 + x0 then sees x0 to 2^-19 instead of 2^-11 relative, at 64 instead of 256 bytes per pixel.
-    // Restores the off-by-one rate of the fp32 stream (README crop golden 3.1 % -> 2.4 % of bytes) for a quarter of its traffic.
-    int residual_ext = 1;
     // > 0: MB of L2 set aside for persisting lines; every dense block then pins that share of its input plane x0 (read by all five
     // convs and by the residual) through the stream's access-policy window.  The 32-output-channel convs are HBM-bound (ncu: 5.3-6.2 TB/s).
     long long l2_persist_mb = 0;
@@ -228,7 +222,7 @@ void release_ws(rsr_handle* h, Workspace* w)
 
 void free_ws(Workspace* w)
 {
-    DevBuf* bufs[] = {&w->d16[0], &w->d16[1], &w->e8[0], &w->e8[1], &w->t32, &w->r32, &w->f32, &w->u1, &w->v1, &w->u2, &w->v2, &w->tta, &w->tiles, &w->img_in, &w->img_out};
+    DevBuf* bufs[] = {&w->x0[0], &w->x0[1], &w->x0[2], &w->e8[0], &w->e8[1], &w->e8[2], &w->xg, &w->f32, &w->u1, &w->v1, &w->u2, &w->v2, &w->tta, &w->tiles, &w->img_in, &w->img_out};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (auto& e : w->conv_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -313,35 +307,33 @@ int run_job(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, 
     size_t npx = 0;
     for (const Grp& g : gs) npx += (size_t)g.n * g.H * g.W;
     int r;
-    if ((r = ensure(h, ws->d16[0], npx * 192 * 2))) return r;
-    if ((r = ensure(h, ws->d16[1], npx * 192 * 2))) return r;
-    if ((r = ensure(h, ws->r32, npx * 64 * 4))) return r;
-    if (!h->residual_fp16 && (r = ensure(h, ws->t32, npx * 64 * 4))) return r;
-    const bool ext = h->residual_fp16 && h->residual_ext;
-    if (ext && ((r = ensure(h, ws->e8[0], npx * 64)) || (r = ensure(h, ws->e8[1], npx * 64)))) return r;
+    for (int i = 0; i < 3; i++) {
+        if ((r = ensure(h, ws->x0[i], npx * 64 * 2))) return r;
+        if ((r = ensure(h, ws->e8[i], npx * 64))) return r;
+    }
+    if ((r = ensure(h, ws->xg, npx * 128 * 2))) return r;
     if ((r = ensure(h, ws->f32, npx * 64 * 4))) return r;
     if ((r = ensure(h, ws->u1, npx * 4 * 64 * 2))) return r;
     if ((r = ensure(h, ws->v1, npx * 4 * 64 * 2))) return r;
     if ((r = ensure(h, ws->u2, npx * 16 * 64 * 2))) return r;
     if ((r = ensure(h, ws->v2, npx * 16 * 64 * 2))) return r;
     cudaStream_t st = ws->stream;
-    __half* D[2] = {(__half*)ws->d16[0].p, (__half*)ws->d16[1].p};
-    // dense buffer layout: plane 0 = x0 [npx][64], then x1..x4 as four [npx][32] planes (see JobMaps)
-    auto xplane = [&](int i, int k) -> __half* { return D[i] + npx * 64 + (size_t)(k - 1) * npx * 32; };  // k = 1..4
+    __half* X0[3] = {(__half*)ws->x0[0].p, (__half*)ws->x0[1].p, (__half*)ws->x0[2].p};
+    uint8_t* E8[3] = {(uint8_t*)ws->e8[0].p, (uint8_t*)ws->e8[1].p, (uint8_t*)ws->e8[2].p};
+    auto xplane = [&](int k) -> __half* { return (__half*)ws->xg.p + (size_t)(k - 1) * npx * 32; };  // x_k, k = 1..4: [npx][32]
     const int rows8 = conv_bh(32) + 2, rows4 = conv_bh(64) + 2;
     JobMaps* jm = &ws->maps;
     for (int g = 0; g < G; g++) {
         const Grp& gr = gs[g];
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 3; i++)
             for (int k = 0; k < CONV_MAX_KBLOCKS; k++) {
-                const __half* base = k < 2 ? D[i] + gr.px_off * 64 : xplane(i, k - 1) + gr.px_off * 32;
+                const __half* base = k < 2 ? X0[i] + gr.px_off * 64 : xplane(k - 1) + gr.px_off * 32;
                 const int C = k < 2 ? 64 : 32;
                 if ((r = make_map(h, map_slot(jm->d8[i], g, k), base, C, gr.W, gr.H, gr.n, rows8))) return r;
                 if ((r = make_map(h, map_slot(jm->d4[i], g, k), base, C, gr.W, gr.H, gr.n, rows4))) return r;
             }
-            for (int k = 1; k <= 4; k++)
-                if ((r = make_omap(h, &jm->oD[i][k - 1][g], xplane(i, k) + gr.px_off * 32, gr.W, gr.H, gr.n, 32, 32))) return r;
-        }
+        for (int k = 1; k <= 4; k++)
+            if ((r = make_omap(h, &jm->oD[k - 1][g], xplane(k) + gr.px_off * 32, gr.W, gr.H, gr.n, 32, 32))) return r;
         struct { ConvMaps* cm; void* base; int s; int rows; } tails[4] = {{&jm->u1_4, ws->u1.p, 2, rows4}, {&jm->u2_4, ws->u2.p, 4, rows4},
                                                                           {&jm->v2_4, ws->v2.p, 4, rows4}, {&jm->u2_8, ws->u2.p, 4, rows8}};
         for (auto& t : tails) {
@@ -359,10 +351,9 @@ int run_job(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, 
         f.img = d_img; f.img_w = img_w; f.img_h = img_h; f.img_c = img_c; f.tiles = d_tiles_all + gr.off;
         f.w = h->dm.w0; f.bias = h->dm.bias[0];
         f.H = gr.H; f.W = gr.W; f.B = gr.n;
-        f.d16 = D[0] + gr.px_off * 64;
-        f.t32 = h->residual_fp16 ? nullptr : (float*)ws->t32.p + gr.px_off * 64;  // the fp32 RDB stream only exists with residual_fp16 = 0
-        f.r32 = (float*)ws->r32.p + gr.px_off * 64; f.f32 = (float*)ws->f32.p + gr.px_off * 64;
-        f.ext = ext ? (uint8_t*)ws->e8[0].p + gr.px_off * 64 : nullptr;
+        f.d16 = X0[0] + gr.px_off * 64;
+        f.ext = E8[0] + gr.px_off * 64;
+        f.f32 = (float*)ws->f32.p + gr.px_off * 64;
         CK(launch_conv_first(f, st));
         c.launches++;
     }
@@ -386,9 +377,8 @@ int run_job(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, 
         a.ntiles_multi = t0;
     };
     ConvArgs base{};
-    base.t32 = (float*)ws->t32.p; base.r32 = (float*)ws->r32.p; base.f32 = (const float*)ws->f32.p;
+    base.f32 = (const float*)ws->f32.p;
     base.tiles = d_tiles_all;
-    int cur = 0;
     size_t persist_bytes = 0;
     if (h->l2_persist_mb > 0) {
         int dev = 0, maxp = 0;
@@ -411,40 +401,47 @@ int run_job(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, 
         CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
         return 0;
     };
-    if ((r = pin_x0(D[cur]))) return r;
-    for (int rrdb = 0; rrdb < m.num_rrdb; rrdb++)
+    // X0 plane rotation: `cur` holds the current block's input, `rin` the input of the enclosing RRDB (kept until its last block)
+    int cur = 0;
+    if ((r = pin_x0(X0[cur]))) return r;
+    for (int rrdb = 0; rrdb < m.num_rrdb; rrdb++) {
+        const int rin = cur;
         for (int rdb = 0; rdb < 3; rdb++) {
-            for (int k = 0; k < 4; k++) {  // x_{k+1} = lrelu(conv([x0..xk])) -> its own 32-channel plane of the same buffer
+            for (int k = 0; k < 4; k++) {  // x_{k+1} = lrelu(conv([x0..xk])) -> its own 32-channel plane
                 ConvArgs a = base;
                 fill_groups(a, 1, 32);
                 a.mode = CONV_STORE16; a.act = 2; a.slope = m.convs[m.idx_rdb(rrdb, rdb, k)].slope;
-                if ((r = conv(c, &jm->d8[cur], a, m.idx_rdb(rrdb, rdb, k), jm->oD[cur][k], G))) return r;
+                if ((r = conv(c, &jm->d8[cur], a, m.idx_rdb(rrdb, rdb, k), jm->oD[k], G))) return r;
             }
-            ConvArgs a = base;  // x5 -> residual(s) -> x0 of the next RDB in the other buffer
+            int nxt = 0;  // the plane that is neither this block's input nor the RRDB's input
+            while (nxt == cur || nxt == rin) nxt++;
+            ConvArgs a = base;  // x5 -> residual(s) -> x0 of the next block
             fill_groups(a, 1, 64);
-            a.mode = CONV_RDB_OUT; a.rrdb_end = (rdb == 2);
-            if (h->residual_fp16) { a.mode = CONV_RDB_OUT16; a.res16 = D[cur]; }
-            if (ext) { a.ext_in = (const uint8_t*)ws->e8[cur].p; a.ext_out = (uint8_t*)ws->e8[cur ^ 1].p; }
-            a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
-            if ((r = pin_x0(D[cur ^ 1]))) return r;  // conv5 writes the next block's x0: those lines are the ones to keep from now on
+            a.mode = CONV_RDB; a.rrdb_end = (rdb == 2);
+            a.res16 = X0[cur]; a.ext_in = E8[cur];
+            a.rr16 = X0[rin]; a.rr_ext = E8[rin];
+            a.out16 = X0[nxt]; a.ext_out = E8[nxt]; a.out_cs = 64; a.out_co = 0;
+            if ((r = pin_x0(X0[nxt]))) return r;  // conv5 writes the next block's x0: those lines are the ones to keep from now on
             if ((r = conv(c, &jm->d4[cur], a, m.idx_rdb(rrdb, rdb, 4)))) return r;
-            cur ^= 1;
+            cur = nxt;
         }
+    }
     if (persist_bytes) {  // back to normal caching for the tail
         cudaStreamAttrValue v{};
         v.accessPolicyWindow.num_bytes = 0;
         CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
     }
-    {   // trunk conv + fea (BinaryOp ADD), result in plane 0 of the other dense buffer
+    const int tr_out = (cur + 1) % 3;
+    {   // trunk conv + fea (BinaryOp ADD), result in another X0 plane
         ConvArgs a = base;
         fill_groups(a, 1, 64);
-        a.mode = CONV_TRUNK; a.out16 = D[cur ^ 1]; a.out_cs = 64; a.out_co = 0;
+        a.mode = CONV_TRUNK; a.out16 = X0[tr_out]; a.out_cs = 64; a.out_co = 0;
         if ((r = conv(c, &jm->d4[cur], a, m.idx_trunk()))) return r;
-        cur ^= 1;
+        cur = tr_out;
     }
     // nearest x2 -> conv+lrelu, twice (x4.param:996-999); the first source is plane 0 of the dense buffer
     for (const Grp& gr : gs) {
-        CK(launch_upsample2x(D[cur] + gr.px_off * 64, 64, (__half*)ws->u1.p + gr.px_off * 4 * 64, gr.n, gr.H, gr.W, st));
+        CK(launch_upsample2x(X0[cur] + gr.px_off * 64, 64, (__half*)ws->u1.p + gr.px_off * 4 * 64, gr.n, gr.H, gr.W, st));
         c.launches++;
     }
     {
@@ -525,8 +522,8 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
         for (auto g = groups.rbegin(); g != groups.rend(); ++g) {  // larger shapes first: the workspace is sized once
             const int H = g->first.first, W = g->first.second;
             const std::vector<TileDesc>& tl = g->second;
-            // workspace per padded pixel: 2x192 fp16 + 3x64 fp32 + (u1,v1) 4x64x2 fp16 + (u2,v2) 16x64x2 fp16 [+ TTA 16 float4 x2]
-            const double bpt = (double)per_tile * H * W * (768.0 + 768.0 + 1024.0 + 4096.0 + (h->tta ? 512.0 : 0.0));
+            // workspace per padded pixel: 3 x (x0 fp16 + ext) + x1..x4 fp16 + fea fp32 + (u1,v1) 4x64x2 fp16 + (u2,v2) 16x64x2 fp16 [+ TTA 16 float4 x2]
+            const double bpt = (double)per_tile * H * W * (576.0 + 256.0 + 256.0 + 1024.0 + 4096.0 + (h->tta ? 512.0 : 0.0));
             size_t pos = 0;
             while (pos < tl.size()) {
                 long long cap = (long long)((budget - cur_bytes) / bpt);
@@ -824,8 +821,6 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
     else if (!strcmp(key, "merge_shapes")) h->merge_shapes = value ? 1 : 0;
     else if (!strcmp(key, "debug_mask")) h->debug_mask = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
-    else if (!strcmp(key, "residual_fp16")) h->residual_fp16 = (int)value;
-    else if (!strcmp(key, "residual_ext")) h->residual_ext = value ? 1 : 0;
     else return set_err(h, RSR_ERR_GENERIC, std::string("unknown option ") + key);
     return 0;
 }
@@ -901,14 +896,14 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
     if (npad != 16 && (r = make_omap(h, &map.o[0], d_out, W, H, 1, npad, npad))) return r;
     a.debug_mask = h->debug_mask;
     long long* d_ts = nullptr;
-    float* d_r32 = nullptr;
-    if (getenv("RSR_DBG_RDB") && npad == 64) {  // bring-up: time the Cout=64 conv with its real (CONV_RDB_OUT) epilogue
-        CK(cudaMalloc(&d_r32, npx * 64 * 4));
-        CK(cudaMemset(d_r32, 0, npx * 64 * 4));
-        a.mode = h->residual_fp16 ? CONV_RDB_OUT16 : CONV_RDB_OUT;
-        a.r32 = d_r32;
-        a.t32 = d_r32;
-        a.res16 = d_in;
+    uint8_t* d_ext = nullptr;
+    if (getenv("RSR_DBG_RDB") && npad == 64) {  // bring-up: time the Cout=64 conv with its real (CONV_RDB) epilogue; value 2 = at an RRDB end
+        CK(cudaMalloc(&d_ext, npx * 64 * 2));
+        CK(cudaMemset(d_ext, 0, npx * 64 * 2));
+        a.mode = CONV_RDB;
+        a.res16 = d_in; a.ext_in = d_ext;
+        a.rr16 = d_in; a.rr_ext = d_ext;
+        a.ext_out = d_ext + npx * 64;
         a.rrdb_end = atoi(getenv("RSR_DBG_RDB")) > 1;
     }
     if (getenv("RSR_DBG_TS")) {
@@ -928,7 +923,7 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
                     ts[i * 8 + 3] - t0, ts[i * 8 + 4] - t0, ts[i * 8 + 5] - t0, ts[i * 8 + 6] - t0, ts[i * 8 + 7] ? ts[i * 8 + 7] - t0 : 0LL);
         cudaFree(d_ts);
     }
-    if (d_r32) cudaFree(d_r32);
+    if (d_ext) cudaFree(d_ext);
     if (npad == 16) {
         std::vector<float> tmp(npx * 4);
         CK(cudaMemcpy(tmp.data(), d_f, npx * 16, cudaMemcpyDeviceToHost));

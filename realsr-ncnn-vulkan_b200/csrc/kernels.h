@@ -30,13 +30,13 @@ struct TileDesc {
 };
 
 enum ConvMode {
-    CONV_STORE16 = 0,   // out16 = fp16(act(acc + b))
-    CONV_RDB_OUT = 1,   // t = 0.2*(acc+b) + T32 ; [rrdb_end: t = 0.2*t + R32 ; R32 = t] ; T32 = t ; out16 = fp16(t)
+    CONV_STORE16 = 0,   // out = fp16(act(acc + b)) through ConvMaps::o (TMA store)
+    CONV_RDB = 1,       // t = 0.2*(acc+b) + x0 ; [rrdb_end: t = 0.2*t + R] ; next x0 = fp16(t) + int8 extension (see res_ext_encode)
     CONV_TRUNK = 2,     // out16 = fp16(acc + b + F32)
     CONV_LAST_U8 = 3,   // v = acc+b -> crop, v*255+0.5, (int) trunc, clamp -> u8 HWC output image
     CONV_LAST_F32 = 4,  // v = acc+b -> fp32 [slot][4H][4W][4] (TTA; averaged by tta_gather)
-    CONV_RDB_OUT16 = 5, // like CONV_RDB_OUT, but the RDB input is read from the fp16 plane `res16` and T32 is not written
 };
+
 
 // One same-shape group of padded tiles inside a merged multi-shape launch (ConvArgs::ngroups > 0): the groups' activations
 // are concatenated pixel-major in every buffer, group g starting px_off pixels into it.
@@ -57,15 +57,17 @@ struct ConvArgs {
     float slope;
     __half* out16;
     int out_cs, out_co;  // channels per pixel of the output buffer, channel offset (residual modes; CONV_STORE16 goes through ConvMaps::o)
-    float* t32;
-    float* r32;
-    const float* f32;
-    const __half* res16;  // CONV_RDB_OUT16: take the RDB input from this fp16 plane (64 ch/px) instead of T32 and do not write T32
-                          // ("residual_fp16" engine option; the RRDB-level skip R32 stays fp32)
-    const uint8_t* ext_in;   // CONV_RDB_OUT16, optional ("residual_ext" engine option): int8 [px][64] extension of res16 -- the RDB
-    uint8_t* ext_out;        // input t is carried as fp16(t) + q / 256 of an fp16 ulp (res_ext_encode below), i.e. with 8 more mantissa
-                             // bits than the fp16 MMA operand (64 B/px instead of the 256 B/px of an fp32 copy); ext_out is the
-                             // extension written next to out16 for the next dense block
+    const float* f32;     // CONV_TRUNK: Conv_0's output `fea` (BinaryOp ADD, x4.param:994-995)
+    // CONV_RDB: the dense-block residual stream.  A residual operand travels as the fp16 plane that is also the next block's MMA
+    // operand plus an int8 extension plane [px][64] that counts 1/256 of the fp16 value's ulp (res_ext_encode below): 8 more
+    // mantissa bits for 64 B/px (an fp32 copy is 256 B/px; without the extension the README-crop golden has 3.2 % of its bytes off
+    // by one, outside the 97 % contract).  res16/ext_in = this block's input x0; rr16/rr_ext = the input of the enclosing RRDB (read
+    // only when rrdb_end: t = 0.2*t + R, Eltwise x4.param:47); out16/ext_out = the next block's x0.
+    const __half* res16;
+    const uint8_t* ext_in;
+    const __half* rr16;
+    const uint8_t* rr_ext;
+    uint8_t* ext_out;
     int rrdb_end;
     // CONV_LAST_*
     const TileDesc* tiles;
@@ -124,11 +126,9 @@ struct FirstArgs {
     const float* w;      // [64][3][3][3] fp32 (OIHW as in the .bin), bias [64]
     const float* bias;
     int H, W, B;
-    __half* d16;         // plane 0 of D16[0] (64 ch per pixel)
-    float* t32;          // optional (residual_fp16 = 0)
-    float* r32;
-    float* f32;
-    uint8_t* ext;        // optional: int8 [px][64] extension of d16 (see ConvArgs::ext_in)
+    __half* d16;         // x0 of the first dense block (64 ch per pixel)
+    uint8_t* ext;        // its int8 extension [px][64] (see ConvArgs::ext_in)
+    float* f32;          // fp32 copy of Conv_0's output for the trunk add
 };
 cudaError_t launch_conv_first(const FirstArgs& a, cudaStream_t stream);
 

@@ -94,15 +94,9 @@ __global__ void __launch_bounds__(FIRST_THREADS) conv_first_kernel(const FirstAr
         }
     }
     const size_t pix = (size_t)b * npix + p;
-    float4* t = reinterpret_cast<float4*>(a.t32 + pix * 64 + quarter * 16);
-    float4* r = reinterpret_cast<float4*>(a.r32 + pix * 64 + quarter * 16);
-    float4* f = reinterpret_cast<float4*>(a.f32 + pix * 64 + quarter * 16);
+    float4* f = reinterpret_cast<float4*>(a.f32 + pix * 64 + quarter * 16);  // fp32 `fea` for the trunk add (x4.param:994-995)
 #pragma unroll
-    for (int j4 = 0; j4 < 4; j4++) {
-        const float4 o = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
-        if (a.t32) t[j4] = o;  // the fp32 copy of the RDB input only exists with residual_fp16 = 0
-        r[j4] = o; f[j4] = o;
-    }
+    for (int j4 = 0; j4 < 4; j4++) f[j4] = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
     uint4* d = reinterpret_cast<uint4*>(a.d16 + pix * 64 + quarter * 16);
     uint32_t ext[4] = {0, 0, 0, 0};  // int8 extensions of the 16 fp16 values (ConvArgs::ext_in), 4 per word
 #pragma unroll
@@ -119,7 +113,7 @@ __global__ void __launch_bounds__(FIRST_THREADS) conv_first_kernel(const FirstAr
         }
         d[j8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-    if (a.ext) *reinterpret_cast<uint4*>(a.ext + pix * 64 + quarter * 16) = make_uint4(ext[0], ext[1], ext[2], ext[3]);
+    *reinterpret_cast<uint4*>(a.ext + pix * 64 + quarter * 16) = make_uint4(ext[0], ext[1], ext[2], ext[3]);
 }
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, int in_vec_stride, uint4* __restrict__ out, int B, int H, int W)

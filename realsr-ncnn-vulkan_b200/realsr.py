@@ -19,7 +19,8 @@ class RealSRError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "librealsr_b200.so")
+    """librealsr_b200.so next to this file; RSR_LIB overrides it (A/B of two builds of the library, tools/ab_builds.sh)"""
+    return os.environ.get("RSR_LIB") or os.path.join(_HERE, "librealsr_b200.so")
 
 
 def load_library():

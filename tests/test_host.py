@@ -135,7 +135,7 @@ def test_options_and_tile_api_validate_without_gpu():
     rsr_process_tiles on a handle without a model is an error (no GPU needed for any of it)"""
     e = rb.RealSR(0)
     assert e.set_option("no_such_option", 1) != 0 and "unknown option" in e.last_error()
-    for key in ("merge_shapes", "residual_fp16", "max_batch", "time_convs"):
+    for key in ("merge_shapes", "serpentine", "max_batch", "time_convs"):
         assert e.set_option(key, 1) == 0, key
     e.tilesize = 400
     assert e.tile_count(1920, 1080) == 15

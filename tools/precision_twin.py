@@ -2,10 +2,11 @@
 """CPU model of the engine's precision choices (torch, no GPU): where do the LSBs against the reference come from, and what
 would each candidate change buy?  The network is evaluated on single-tile goldens with activations rounded to fp16 exactly
 where the engine stores fp16 (fp32 accumulation everywhere), then with one choice changed at a time:
-    engine      : what csrc/ does by default (fp32 Conv_0, fp16 dense planes, dense-block residual from fp16 x0 + its int8 extension
-                  (kernels.h res_ext_encode: 1/256 of an fp16 ulp), fp32 RRDB skip stream, fp16 tail activations)
-    res16       : residual_ext = 0 (round-1 default: dense-block residual from the fp16 operand plane alone)
-    res32       : residual_fp16 = 0 (dense-block residual from an fp32 copy)
+    engine      : what csrc/ does (fp32 Conv_0, fp16 dense planes, the residual stream -- dense-block residual x0 AND the RRDB skip R --
+                  carried as fp16 + int8 extension (kernels.h res_ext_encode: 1/256 of an fp16 ulp), fp16 tail activations)
+    rr32        : the RRDB skip stream kept in fp32 instead (round 2's first carrier version)
+    res16       : round-1 default: dense-block residual from the fp16 operand plane alone, fp32 RRDB skip
+    res32       : round-1 option: dense-block residual from an fp32 copy, fp32 RRDB skip
     tail32      : + the four tail convs (after the trunk) read and write fp32 activations ("exact tail")
     subpix      : engine precision, but the two "nearest x2 + conv" pairs collapsed into four 2x2 sub-pixel convs on the low-res
                   grid with pre-summed fp16 weights (2.25x fewer MACs for those two convs, no upsampled tensors)
@@ -127,12 +128,12 @@ def run(name, mode):
     P = 10
     x = torch.from_numpy(img.astype(np.float32)).permute(2, 0, 1)[None] * (1 / 255.0)
     x = F.pad(x, (P, P, P, P), mode="reflect")
-    q = dict(engine=(H16, EXT8, H16), rext=(H16, EXT8, H16), res16=(H16, H16, H16), res32=(H16, ID, H16), tail32=(H16, ID, ID), body32=(ID, ID, H16), all32=(ID, ID, ID),
+    q = dict(engine=(H16, EXT8, H16), rr32=(H16, EXT8, H16), res16=(H16, H16, H16), res32=(H16, ID, H16), tail32=(H16, ID, ID), body32=(ID, ID, H16), all32=(ID, ID, ID),
              hr32=(H16, H16, H16), v2hr32=(H16, H16, H16), trunk32=(H16, H16, H16), subpix=(H16, H16, H16), wino=(H16, H16, H16))[mode]
     # single tail tensors kept exact (engine precision elsewhere): which hand-off carries the error?
     q_tails = dict(hr32=(H16, H16, H16, ID), v2hr32=(H16, H16, ID, ID), trunk32=(ID, H16, H16, H16)).get(mode)
     with torch.no_grad():
-        y = net(x, convs, *q, q_tails=q_tails, collapse=(mode == "subpix"), wino=(mode == "wino"), q_rrdb=(EXT8 if mode == "rext" else None))[0, :, 4 * P:4 * P + 4 * h, 4 * P:4 * P + 4 * w]
+        y = net(x, convs, *q, q_tails=q_tails, collapse=(mode == "subpix"), wino=(mode == "wino"), q_rrdb=(EXT8 if mode == "engine" else None))[0, :, 4 * P:4 * P + 4 * h, 4 * P:4 * P + 4 * w]
     out = torch.clamp((y * 255.0 + 0.5).to(torch.int32), 0, 255).permute(1, 2, 0).numpy().astype(np.uint8)  # (int) truncation like the reference
     return diff_stats(out, gold[..., :3])
 
@@ -142,6 +143,6 @@ if __name__ == "__main__":
     for name in names:
         if "tta" in name:
             continue  # TTA goldens average 8 passes: not modelled here
-        for mode in ("engine", "rext", "res16", "res32", "tail32", "hr32", "v2hr32", "trunk32", "subpix", "wino", "body32", "all32"):
+        for mode in ("engine", "rr32", "res16", "res32", "tail32", "hr32", "v2hr32", "trunk32", "subpix", "wino", "body32", "all32"):
             s = run(name, mode)
             print("%-28s %-7s max %d  off-by-one %.3f %%  >1: %d of %d" % (name, mode, s["max"], 100 * s["frac_diff"], s["n_gt1"], s["n"]), flush=True)
