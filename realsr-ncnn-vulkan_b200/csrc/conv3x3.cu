@@ -590,10 +590,10 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                         auto dec8 = [&](const uint4 w, const uint2 e, float4 (&dst)[2]) {  // 8 x (fp16 + int8 extension) -> fp32
                             const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
                             const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
-                            dst[0].x = res_ext_decode(f0.x, (int)(e.x << 24) >> 24); dst[0].y = res_ext_decode(f0.y, (int)(e.x << 16) >> 24);
-                            dst[0].z = res_ext_decode(f1.x, (int)(e.x << 8) >> 24);  dst[0].w = res_ext_decode(f1.y, (int)e.x >> 24);
-                            dst[1].x = res_ext_decode(f2.x, (int)(e.y << 24) >> 24); dst[1].y = res_ext_decode(f2.y, (int)(e.y << 16) >> 24);
-                            dst[1].z = res_ext_decode(f3.x, (int)(e.y << 8) >> 24);  dst[1].w = res_ext_decode(f3.y, (int)e.y >> 24);
+                            dst[0].x = res_ext_decode(f0.x, e.x, 0); dst[0].y = res_ext_decode(f0.y, e.x, 1);
+                            dst[0].z = res_ext_decode(f1.x, e.x, 2); dst[0].w = res_ext_decode(f1.y, e.x, 3);
+                            dst[1].x = res_ext_decode(f2.x, e.y, 0); dst[1].y = res_ext_decode(f2.y, e.y, 1);
+                            dst[1].z = res_ext_decode(f3.x, e.y, 2); dst[1].w = res_ext_decode(f3.y, e.y, 3);
                         };
 #pragma unroll
                         for (int nb = 0; nb < 2; nb++) {
@@ -651,10 +651,8 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                                     if constexpr (RDB) {
                                         const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&p0)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&p1));
                                         const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&p2)), g3 = __half22float2(*reinterpret_cast<const __half2*>(&p3));
-                                        const uint32_t q0 = (uint32_t)(res_ext_encode(o[0].x, g0.x) & 255) | ((uint32_t)(res_ext_encode(o[0].y, g0.y) & 255) << 8) |
-                                                            ((uint32_t)(res_ext_encode(o[0].z, g1.x) & 255) << 16) | ((uint32_t)res_ext_encode(o[0].w, g1.y) << 24);
-                                        const uint32_t q1 = (uint32_t)(res_ext_encode(o[1].x, g2.x) & 255) | ((uint32_t)(res_ext_encode(o[1].y, g2.y) & 255) << 8) |
-                                                            ((uint32_t)(res_ext_encode(o[1].z, g3.x) & 255) << 16) | ((uint32_t)res_ext_encode(o[1].w, g3.y) << 24);
+                                        const uint32_t q0 = res_ext_pack4(res_ext_encode(o[0].x, g0.x), res_ext_encode(o[0].y, g0.y), res_ext_encode(o[0].z, g1.x), res_ext_encode(o[0].w, g1.y));
+                                        const uint32_t q1 = res_ext_pack4(res_ext_encode(o[1].x, g2.x), res_ext_encode(o[1].y, g2.y), res_ext_encode(o[1].z, g3.x), res_ext_encode(o[1].w, g3.y));
                                         *reinterpret_cast<uint2*>(a.ext_out + px * 64 + ch0) = make_uint2(q0, q1);
                                     }
                                 }

@@ -101,16 +101,24 @@ struct alignas(64) ConvMaps {
 // conv3x3.cu: conv3x3 s1 p1 (+ fused epilogue, see ConvMode) as implicit GEMM on tcgen05 CTA pairs.  cout_pad in {16, 32, 64}.
 cudaError_t launch_conv3x3(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
 
-// Residual carrier (ConvArgs::ext_in / ext_out): a value v travels as its round-to-nearest fp16 h (the MMA operand) plus an int8 q that
-// counts 1/256 of h's ulp: q = round((bits(v) - bits(float(h))) / 32) on the fp32 bit patterns (13 more mantissa bits in fp32 than in
-// fp16, 8 of them kept; bit-pattern arithmetic is monotonic across binades and sign-symmetric), clamped to int8.  Decoding adds q * 32
-// fp32-ulps back.  Values below the fp16 normal range simply clamp (absolute error < 2^-25 either way).
-__device__ __forceinline__ int res_ext_encode(float v, float hf)
+// Residual carrier (ConvArgs::res16 / ext_in ...): a value v travels as its round-to-nearest fp16 h (the MMA operand) plus an int8 q that
+// counts 1/256 of h's ulp: q = floor((bits(v) - bits(float(h))) / 32) on the fp32 bit patterns (13 more mantissa bits in fp32 than in
+// fp16, 8 of them kept; bit-pattern arithmetic is monotonic across binades and sign-symmetric), in [-128, 127] (the one value that can
+// exceed it, the exact round-to-even tie +4096, saturates).  Decoding adds q * 32 fp32-ulps back: |error| <= 1/256 of an fp16 ulp.
+// Below the fp16 normal range q may wrap; the absolute error there stays under 2^-25 either way.
+__device__ __forceinline__ int res_ext_encode(float v, float hf) { return min((__float_as_int(v) - __float_as_int(hf)) >> 5, 127); }
+// q = byte `byte` (0..3) of the packed word e, sign-extended
+__device__ __forceinline__ float res_ext_decode(float hf, unsigned e, int byte)
 {
-    const int d = (__float_as_int(v) - __float_as_int(hf) + 16) >> 5;
-    return max(-128, min(127, d));
+    int q;
+    asm("bfe.s32 %0, %1, %2, 8;" : "=r"(q) : "r"(e), "r"(byte * 8));
+    return __int_as_float(__float_as_int(hf) + q * 32);
 }
-__device__ __forceinline__ float res_ext_decode(float hf, int q) { return __int_as_float(__float_as_int(hf) + q * 32); }
+// the low bytes of four encoded values -> one word (byte i = value i)
+__device__ __forceinline__ unsigned res_ext_pack4(int a, int b, int c, int d)
+{
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
 constexpr int CONV_P = 32;      // position pitch of a work tile (32 px: 30 output columns + the two halo columns)
 constexpr int CONV_BW = 30;     // output columns per work tile
 // output rows per CTA of a pair and work tile: 4 for the Cout = 64 convs (one N = 192 MMA per k-step: 192 TMEM columns per M-tile),

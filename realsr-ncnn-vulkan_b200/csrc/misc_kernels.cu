@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(FIRST_THREADS) conv_first_kernel(const FirstAr
             __half2 hh = __floats2half2_rn(v0, v1);
             pk[k] = *reinterpret_cast<uint32_t*>(&hh);
             const float2 f = __half22float2(hh);
-            const uint32_t q = (uint32_t)(res_ext_encode(v0, f.x) & 255) | ((uint32_t)(res_ext_encode(v1, f.y) & 255) << 8);
+            const uint32_t q = (uint32_t)(res_ext_encode(v0, f.x) & 255) | ((uint32_t)(res_ext_encode(v1, f.y) & 255) << 8);  // floor / saturating, see kernels.h
             ext[j8 * 2 + (k >> 1)] |= q << (16 * (k & 1));
         }
         d[j8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);

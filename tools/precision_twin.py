@@ -34,7 +34,7 @@ def EXT8(t):
     res_ext_decode"""
     hf = t.half().float()
     bv, bh = t.contiguous().view(torch.int32).to(torch.int64), hf.contiguous().view(torch.int32).to(torch.int64)
-    q = torch.clamp((bv - bh + 16) >> 5, -128, 127)
+    q = torch.clamp((bv - bh) >> 5, -128, 127)
     return (bh + q * 32).to(torch.int32).view(torch.float32)
 
 
