@@ -98,8 +98,7 @@ RSR_API long long rsr_last_padded_pixels(const rsr_handle* h);
 RSR_API long long rsr_last_conv_launches(const rsr_handle* h);
 /* Engine options: "max_batch" (tiles per job, 0 = auto), "merge_shapes" (1 default: one launch per layer over all shape groups of a
  * frame; 0: one job per shape group), "serpentine" (1 default: every second conv walks its tiles backwards, L2 reuse),
- * "l2_persist_mb" (0 default; experiment: pin a share of each dense block's input plane in the L2 set-aside), "time_convs" (CUDA
- * events around every conv launch), "debug_mask" (timing experiments only, results become garbage: 1 = skip MMAs, 2 = skip
+ * "time_convs" (CUDA events around every conv launch), "debug_mask" (timing experiments only, results become garbage: 1 = skip MMAs, 2 = skip
  * activation loads, 4 = skip weight loads, 8 = skip epilogue stores).  Unknown keys return RSR_ERR_GENERIC. */
 RSR_API int rsr_set_option(rsr_handle* h, const char* key, long long value);
 

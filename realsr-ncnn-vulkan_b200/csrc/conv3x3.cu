@@ -61,9 +61,13 @@ constexpr int NEPI = 8;                       // epilogue warps
 constexpr int EPI_WARP0 = 4;                  // first epilogue warp: warps 0..3 are the control warpgroup
 constexpr int NTHREADS = (EPI_WARP0 + NEPI) * 32;
 // epilogue staging per warp: CONV_STORE16 stages one 32-pixel row of its output as a dense, swizzled TMA-store source
-// (32 x Cout fp16); the Cout = 64 residual modes transpose 32 px x 32 ch fp32 through a padded tile (row stride 36 words); the last
-// conv stores straight from registers
-__host__ __device__ constexpr int stage_bytes(int nreal, int mode) { return mode == CONV_STORE16 ? 32 * nreal * 2 : (nreal == 64 ? 32 * 36 * 4 : 1024); }
+// (32 x Cout fp16); CONV_RDB keeps one row of the residual stream there (32 px x 64 fp16 + 32 px x 64 int8: TMA-loaded input, overwritten
+// in place by the output row); CONV_TRUNK transposes 32 px x 32 ch fp32 through a padded tile (row stride 36 words); the last conv stores
+// straight from registers
+__host__ __device__ constexpr int stage_bytes(int nreal, int mode)
+{
+    return mode == CONV_STORE16 ? 32 * nreal * 2 : (mode == CONV_RDB ? 32 * 128 + 32 * 64 : (nreal == 64 ? 32 * 36 * 4 : 1024));
+}
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_MAX = 227 * 1024 - 1024;   // dynamic part; the kernel also has ~300 B of static shared memory
 __host__ __device__ constexpr int smem_fixed(int nreal, int mode) { return 1024 /*align*/ + NEPI * stage_bytes(nreal, mode) + 256 /*barriers*/; }
@@ -77,6 +81,7 @@ struct Bars {
     uint64_t a_full[NA_MAX], a_empty[NA_MAX];
     uint64_t w_full;
     uint64_t acc_full[2], acc_empty[2];
+    uint64_t epi_ld[NEPI];  // CONV_RDB: one per epilogue warp, completion of the TMA loads of its residual rows
     uint32_t tmem_ptr;
 };
 
@@ -236,13 +241,19 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
         // hand-back arrivals per accumulator set: EARLY with two M-tiles: 8 warps x 2 CTAs per tile; otherwise the 4 warps of
         // one group x 2 CTAs
         for (int i = 0; i < 2; i++) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], (EARLY && MT == 2) ? 2 * NEPI : NEPI); }
+        for (int i = 0; i < NEPI; i++) mbar_init(&bars->epi_ld[i], 1);
         mbar_fence_init();
         for (int i = 0; i < nchunk; i++) tma_prefetch_desc(&maps.m[i]);
         for (int g = 1; g < a.ngroups; g++)
             for (int i = 0; i < nchunk; i++) tma_prefetch_desc(&maps.mg[g - 1][i]);
         tma_prefetch_desc(&maps.w);
-        if (EARLY)
+        if (EARLY || MODE == CONV_RDB)
             for (int g = 0; g < (a.ngroups > 0 ? a.ngroups : 1); g++) tma_prefetch_desc(&maps.o[g]);
+        if (MODE == CONV_RDB)
+            for (int g = 0; g < (a.ngroups > 0 ? a.ngroups : 1); g++) {
+                tma_prefetch_desc(&maps.rx[g]); tma_prefetch_desc(&maps.re[g]); tma_prefetch_desc(&maps.reo[g]);
+                if (a.rrdb_end) { tma_prefetch_desc(&maps.rrx[g]); tma_prefetch_desc(&maps.rre[g]); }
+            }
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + NREAL) s_bias[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
     // rows behind each A box: read by the kx=2 taps of the last two (never stored) positions; keep them finite
@@ -443,10 +454,120 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             if (ts_on) a.dbg_ts[ti * 8 + 7] = clock64();
         }
         if (lane == 0) bulk_wait<0>();  // all of this warp's stores have been performed before the CTA retires
+      } else if constexpr (MODE == CONV_RDB) {
+        // ---------------- epilogue, CONV_RDB (conv5 of a dense block): residual stream through TMA, no transposes ----------------
+        // Two 4-warp groups alternate work tiles (one per accumulator set); warp q4 owns tile row q4: lane = pixel, registers =
+        // the 64 channels (the TMEM-native layout).  The row of the residual operand x0 (fp16 + int8 extension, kernels.h) arrives by
+        // TMA in a swizzled staging buffer while the MMAs run, every lane reads ITS pixel's 128 + 64 bytes, computes
+        // t = 0.2*(acc + b) + x0 [, t = 0.2*t + R with R fetched the same way], writes fp16(t) and its extension back over its own
+        // row, and the row leaves through two TMA stores: no per-thread global access, no predicates (the hardware clips), no smem
+        // transpose.  (The previous transposed-domain version cost ~4 k clk per tile row next to 3.5 k clk of MMAs.)
+        const int group = ew >> 2;
+        uint8_t* xb = smStage + ew * STAGE_BYTES;   // [32 px][64 fp16], SWIZZLE_128B: input x0 row, then output row
+        uint8_t* eb = xb + 32 * 128;                 // [32 px][64 int8], SWIZZLE_64B: input extension row, then output extension row
+        uint64_t* ldbar = &bars->epi_ld[ew];
+        const uint32_t acc_empty_leader = mapa_u32(smem_u32(&bars->acc_empty[group]), 0);
+        const int buf = group;
+        const int swx = lane & 7, swe = (lane >> 1) & 3;
+        constexpr uint32_t ROW_BYTES = BW * 128 + BW * 64;  // TMA bytes of one fp16 row box + one int8 row box (out-of-image parts are zero-filled but counted)
+        uint32_t phf = 0, phl = 0;  // parities: this group's acc_full, this warp's load barrier
+        int ti = group;
+        Walk geo;
+        walk_start(geo, a, cluster_id + group * nclusters, 2 * nclusters, ntiles, tiles_x, bands_y);
+        for (; geo.u < ntiles; walk_step(geo, a, 2 * nclusters, ntiles, tiles_x, bands_y), ti += 2) {
+            const int y = geo.by * BAND + (int)rank * BH + q4, xc = geo.tx * BW;
+            if (lane == 0) {  // the previous tile's stores have finished reading the staging rows: fetch this tile's x0 row
+                bulk_wait_read<0>();
+                mbar_expect_tx(ldbar, ROW_BYTES);
+                tma_load_4d(xb, &maps.rx[geo.g], ldbar, 0, xc, y, geo.b);
+                tma_load_4d(eb, &maps.re[geo.g], ldbar, 0, xc, y, geo.b);
+            }
+            const bool ts_on = a.dbg_ts != nullptr && cluster_id == 0 && ti < 64 && is_leader && (ew & 3) == 0 && lane == 0;
+            if (ts_on) a.dbg_ts[ti * 8 + 4] = clock64();
+            mbar_wait(&bars->acc_full[buf], phf);
+            phf ^= 1;
+            tc_fence_after();
+            if (ts_on) a.dbg_ts[ti * 8 + 5] = clock64();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS;
+            float t[64];
+#pragma unroll
+            for (int nb = 0; nb < 2; nb++) {
+                uint32_t v[32], u[32], w[32];  // D[c] + right neighbour's D[64 + c] + second right neighbour's D[128 + c]
+                tmem_ld32(taddr + nb * 32, v);
+                tmem_ld32(taddr + 64 + nb * 32, u);
+                tmem_ld32(taddr + 128 + nb * 32, w);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    t[nb * 32 + j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
+                                     __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(acc_empty_leader);  // early hand-back (CTA-scope release: only the TMEM reads have to be ordered)
+            if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
+            // one row of (fp16, int8) operands -> t = t * scale + operand, 8 channels per 16-B / 8-B chunk
+            auto add_row = [&](const bool first) {
+                mbar_wait(ldbar, phl);
+                phl ^= 1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint4 hw = *reinterpret_cast<const uint4*>(xb + lane * 128 + ((j ^ swx) << 4));
+                    const uint2 ew2 = *reinterpret_cast<const uint2*>(eb + lane * 64 + (((j >> 1) ^ swe) << 4) + (j & 1) * 8);
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&hw.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&hw.y));
+                    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&hw.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&hw.w));
+                    const float r0 = res_ext_decode(f0.x, ew2.x, 0), r1 = res_ext_decode(f0.y, ew2.x, 1), r2 = res_ext_decode(f1.x, ew2.x, 2), r3 = res_ext_decode(f1.y, ew2.x, 3);
+                    const float r4 = res_ext_decode(f2.x, ew2.y, 0), r5 = res_ext_decode(f2.y, ew2.y, 1), r6 = res_ext_decode(f3.x, ew2.y, 2), r7 = res_ext_decode(f3.y, ew2.y, 3);
+                    float* tt = &t[8 * j];
+                    if (first) {  // t = 0.2 * (acc + bias) + x0   (Eltwise of the dense block, x4.param:18)
+                        const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[8 * j]), b1 = *reinterpret_cast<const float4*>(&s_bias[8 * j + 4]);
+                        tt[0] = (tt[0] + b0.x) * 0.2f + r0; tt[1] = (tt[1] + b0.y) * 0.2f + r1; tt[2] = (tt[2] + b0.z) * 0.2f + r2; tt[3] = (tt[3] + b0.w) * 0.2f + r3;
+                        tt[4] = (tt[4] + b1.x) * 0.2f + r4; tt[5] = (tt[5] + b1.y) * 0.2f + r5; tt[6] = (tt[6] + b1.z) * 0.2f + r6; tt[7] = (tt[7] + b1.w) * 0.2f + r7;
+                    } else {      // t = 0.2 * t + R                 (Eltwise at the end of an RRDB, x4.param:47)
+                        tt[0] = tt[0] * 0.2f + r0; tt[1] = tt[1] * 0.2f + r1; tt[2] = tt[2] * 0.2f + r2; tt[3] = tt[3] * 0.2f + r3;
+                        tt[4] = tt[4] * 0.2f + r4; tt[5] = tt[5] * 0.2f + r5; tt[6] = tt[6] * 0.2f + r6; tt[7] = tt[7] * 0.2f + r7;
+                    }
+                }
+            };
+            add_row(true);
+            if (a.rrdb_end) {
+                // the RRDB input R comes through the same staging rows: every lane is done reading x0 (generic proxy) before the TMA
+                // (async proxy) overwrites them
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_expect_tx(ldbar, ROW_BYTES);
+                    tma_load_4d(xb, &maps.rrx[geo.g], ldbar, 0, xc, y, geo.b);
+                    tma_load_4d(eb, &maps.rre[geo.g], ldbar, 0, xc, y, geo.b);
+                }
+                add_row(false);
+            }
+            // next block's x0 = fp16(t) + int8 extension, written over this lane's own staging row
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float* tt = &t[8 * j];
+                const uint32_t p0 = pack_h2(tt[0], tt[1]), p1 = pack_h2(tt[2], tt[3]), p2 = pack_h2(tt[4], tt[5]), p3 = pack_h2(tt[6], tt[7]);
+                const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&p0)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&p1));
+                const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&p2)), g3 = __half22float2(*reinterpret_cast<const __half2*>(&p3));
+                *reinterpret_cast<uint4*>(xb + lane * 128 + ((j ^ swx) << 4)) = make_uint4(p0, p1, p2, p3);
+                *reinterpret_cast<uint2*>(eb + lane * 64 + (((j >> 1) ^ swe) << 4) + (j & 1) * 8) =
+                    make_uint2(res_ext_pack4(res_ext_encode(tt[0], g0.x), res_ext_encode(tt[1], g0.y), res_ext_encode(tt[2], g1.x), res_ext_encode(tt[3], g1.y)),
+                               res_ext_pack4(res_ext_encode(tt[4], g2.x), res_ext_encode(tt[5], g2.y), res_ext_encode(tt[6], g3.x), res_ext_encode(tt[7], g3.y)));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !dbg_noepi && y < geo.H) {
+                tma_store_4d(&maps.o[geo.g], xb, 0, xc, y, geo.b);
+                tma_store_4d(&maps.reo[geo.g], eb, 0, xc, y, geo.b);
+                bulk_commit();
+            }
+            if (ts_on) a.dbg_ts[ti * 8 + 7] = clock64();
+        }
+        if (lane == 0) bulk_wait<0>();  // all of this warp's stores have been performed before the CTA retires
       } else {
-        // ---------------- epilogue, residual / post-processing modes: warps 4..11 in two groups of four ----------------
+        // ---------------- epilogue, CONV_TRUNK and the last conv: warps 4..11 in two groups of four ----------------
         // Group g = (warp-4)/4 owns accumulator set g, i.e. every second work tile; inside a group warp q4 handles row q4 of the
-        // tile's M-tile(s).  (These convs are bounded by their MMAs or by HBM, not by the accumulator hand-over.)
+        // tile's M-tile(s).  (One launch each per frame; the last conv is HBM-bound.)
         const int group = ew >> 2;
         uint32_t* stg = reinterpret_cast<uint32_t*>(smStage + ew * STAGE_BYTES);  // [32 px][36 words]
         const int tr = lane >> 2, tc = lane & 3;
@@ -471,18 +592,11 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             bool vcol[4];
 #pragma unroll
             for (int r = 0; r < 4; r++) vcol[r] = (tr + 8 * r < BW) && (x0 + tr + 8 * r < geo.W);
-            // Residual operands of the Cout = 64 modes.  The fp32 math runs in a TRANSPOSED domain: a 32-channel block of the tile row
-            // goes through a [32 px][32 ch] smem tile, after which thread (tr, tc) holds 8 consecutive channels (tc*8..) of the four
-            // pixels tr, tr+8, tr+16, tr+24 -- every global access is then 16 B of fp16 / 32 B of fp32 / 8 B of int8 per lane and a
-            // full 64-B / 128-B / 32-B run per pixel.  CONV_RDB: ALL fp16 x0 values and int8 extensions this thread needs for the
-            // tile are requested here, before waiting for the MMAs (a memory latency per block otherwise), the RRDB-level operands of
-            // the first block too; CONV_TRUNK fetches its fp32 operands one 32-channel block ahead of use.
-            constexpr bool RDB = MODE == CONV_RDB;
+            // CONV_TRUNK (acc + b + F32): the fp32 math runs in a TRANSPOSED domain: a 32-channel block of the tile row goes through a
+            // [32 px][32 ch] smem tile, after which thread (tr, tc) holds 8 consecutive channels (tc*8..) of the four pixels tr, tr+8,
+            // tr+16, tr+24 -- every global access is then 32 B of fp32 / 16 B of fp16 per lane and a full 128-B / 64-B run per pixel.
+            // The fp32 operands are fetched one 32-channel block ahead of use.
             float4 res[4][2];             // [r][8 channels] fp32 residual operands of the current block
-            uint4 x0raw[MT][2][4];        // [i][nb][r]: 8 fp16 of the block input x0
-            uint2 x0ext[MT][2][4];        // their int8 extensions
-            uint4 rrraw[2][4];            // [nb][r]: the RRDB input R (rrdb_end only), loaded one block ahead
-            uint2 rrext[2][4];
             auto load_res = [&](int i, int nb, float4 (&dst)[4][2]) {
                 if constexpr (MODE == CONV_TRUNK) {
                     const float* base = a.f32 + rowpix[i] * 64 + nb * 32 + tc * 8;
@@ -494,33 +608,7 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                         }
                 }
             };
-            auto load_rr = [&](int i, int nb) {
-                if constexpr (RDB) {
-#pragma unroll
-                    for (int r = 0; r < 4; r++)
-                        if (vcol[r] && vrow[i]) {
-                            const size_t e = (rowpix[i] + tr + 8 * r) * 64 + nb * 32 + tc * 8;
-                            rrraw[nb][r] = *reinterpret_cast<const uint4*>(a.rr16 + e);
-                            rrext[nb][r] = *reinterpret_cast<const uint2*>(a.rr_ext + e);
-                        }
-                }
-            };
-            if constexpr (RDB) {
-#pragma unroll
-                for (int i = 0; i < MT; i++)
-#pragma unroll
-                    for (int nb = 0; nb < 2; nb++)
-#pragma unroll
-                        for (int r = 0; r < 4; r++)
-                            if (vcol[r] && vrow[i]) {
-                                const size_t e = (rowpix[i] + tr + 8 * r) * 64 + nb * 32 + tc * 8;
-                                x0raw[i][nb][r] = *reinterpret_cast<const uint4*>(a.res16 + e);
-                                x0ext[i][nb][r] = *reinterpret_cast<const uint2*>(a.ext_in + e);
-                            }
-                if (a.rrdb_end) load_rr(0, 0);
-            } else if constexpr (NREAL == 64) {
-                load_res(0, 0, res);
-            }
+            if constexpr (NREAL == 64) load_res(0, 0, res);
             const bool ts_on = a.dbg_ts != nullptr && cluster_id == 0 && ti < 64 && is_leader && (ew & 3) == 0 && lane == 0;
             if (ts_on) a.dbg_ts[ti * 8 + 4] = clock64();
             mbar_wait(&bars->acc_full[buf], phf);
@@ -528,9 +616,8 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             tc_fence_after();
             if (ts_on) a.dbg_ts[ti * 8 + 5] = clock64();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * ACC_COLS;
-            // Cout = 64 (conv5 / trunk): the accumulators go to registers first (taps combined) and the set returns to the MMA issuer
-            // before any residual math or store -- with 4-row tiles the whole epilogue (~4 k clk of memory latency per tile) would
-            // otherwise sit on the accumulator hand-over chain next to 3.5 k clk of MMAs.
+            // Cout = 64 (trunk): the accumulators go to registers first (taps combined) and the set returns to the MMA issuer before
+            // any residual math or store
             uint32_t accv[NREAL == 64 ? MT : 1][NREAL == 64 ? 64 : 1];
             if constexpr (NREAL == 64) {
 #pragma unroll
@@ -586,24 +673,14 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                             }
                         }
                     } else {
-                        // CONV_RDB / CONV_TRUNK (Cout = 64): fp32 math against the residual stream in the transposed domain
-                        auto dec8 = [&](const uint4 w, const uint2 e, float4 (&dst)[2]) {  // 8 x (fp16 + int8 extension) -> fp32
-                            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
-                            const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
-                            dst[0].x = res_ext_decode(f0.x, e.x, 0); dst[0].y = res_ext_decode(f0.y, e.x, 1);
-                            dst[0].z = res_ext_decode(f1.x, e.x, 2); dst[0].w = res_ext_decode(f1.y, e.x, 3);
-                            dst[1].x = res_ext_decode(f2.x, e.y, 0); dst[1].y = res_ext_decode(f2.y, e.y, 1);
-                            dst[1].z = res_ext_decode(f3.x, e.y, 2); dst[1].w = res_ext_decode(f3.y, e.y, 3);
-                        };
+                        // CONV_TRUNK (Cout = 64): fp32 add of `fea` in the transposed domain
 #pragma unroll
                         for (int nb = 0; nb < 2; nb++) {
                             const uint32_t* v = &accv[i][nb * 32];
                             float4 nxt[4][2];
-                            if constexpr (!RDB) {  // prefetch the residual operands of the next (M-tile, 32-channel block)
+                            {  // prefetch the operands of the next (M-tile, 32-channel block)
                                 const int ni = nb == 1 ? i + 1 : i, nnb = nb ^ 1;
                                 if (ni < MT) load_res(ni, nnb, nxt);
-                            } else {
-                                if (a.rrdb_end && nb == 0) load_rr(i, 1);
                             }
 #pragma unroll
                             for (int k = 0; k < 8; k++)  // this lane's pixel, 32 channels -> row `lane` of the tile (stride 36 words: conflict-free)
@@ -620,47 +697,21 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                             __syncwarp();
 #pragma unroll
                             for (int r = 0; r < 4; r++) {
-                                if constexpr (RDB) dec8(x0raw[i][nb][r], x0ext[i][nb][r], res[r]);
                                 float4 o[2];
 #pragma unroll
                                 for (int q = 0; q < 2; q++) {
                                     const float4 ac = acc8[r][q], bb = q ? bb1 : bb0, rs = res[r][q];
-                                    if constexpr (RDB) {
-                                        o[q].x = (ac.x + bb.x) * 0.2f + rs.x; o[q].y = (ac.y + bb.y) * 0.2f + rs.y;
-                                        o[q].z = (ac.z + bb.z) * 0.2f + rs.z; o[q].w = (ac.w + bb.w) * 0.2f + rs.w;
-                                    } else {
-                                        o[q].x = ac.x + bb.x + rs.x; o[q].y = ac.y + bb.y + rs.y;
-                                        o[q].z = ac.z + bb.z + rs.z; o[q].w = ac.w + bb.w + rs.w;
-                                    }
-                                }
-                                if constexpr (RDB) {
-                                    if (a.rrdb_end) {  // t = 0.2*t + R (Eltwise at the end of an RRDB, x4.param:47)
-                                        float4 rr[2];
-                                        dec8(rrraw[nb][r], rrext[nb][r], rr);
-#pragma unroll
-                                        for (int q = 0; q < 2; q++) {
-                                            o[q].x = o[q].x * 0.2f + rr[q].x; o[q].y = o[q].y * 0.2f + rr[q].y;
-                                            o[q].z = o[q].z * 0.2f + rr[q].z; o[q].w = o[q].w * 0.2f + rr[q].w;
-                                        }
-                                    }
+                                    o[q].x = ac.x + bb.x + rs.x; o[q].y = ac.y + bb.y + rs.y;
+                                    o[q].z = ac.z + bb.z + rs.z; o[q].w = ac.w + bb.w + rs.w;
                                 }
                                 if (vcol[r] && vrow[i]) {
                                     const size_t px = rowpix[i] + tr + 8 * r;
-                                    const uint32_t p0 = pack_h2(o[0].x, o[0].y), p1 = pack_h2(o[0].z, o[0].w), p2 = pack_h2(o[1].x, o[1].y), p3 = pack_h2(o[1].z, o[1].w);
-                                    *reinterpret_cast<uint4*>(a.out16 + px * a.out_cs + a.out_co + ch0) = make_uint4(p0, p1, p2, p3);
-                                    if constexpr (RDB) {
-                                        const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&p0)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&p1));
-                                        const float2 g2 = __half22float2(*reinterpret_cast<const __half2*>(&p2)), g3 = __half22float2(*reinterpret_cast<const __half2*>(&p3));
-                                        const uint32_t q0 = res_ext_pack4(res_ext_encode(o[0].x, g0.x), res_ext_encode(o[0].y, g0.y), res_ext_encode(o[0].z, g1.x), res_ext_encode(o[0].w, g1.y));
-                                        const uint32_t q1 = res_ext_pack4(res_ext_encode(o[1].x, g2.x), res_ext_encode(o[1].y, g2.y), res_ext_encode(o[1].z, g3.x), res_ext_encode(o[1].w, g3.y));
-                                        *reinterpret_cast<uint2*>(a.ext_out + px * 64 + ch0) = make_uint2(q0, q1);
-                                    }
+                                    *reinterpret_cast<uint4*>(a.out16 + px * a.out_cs + a.out_co + ch0) =
+                                        make_uint4(pack_h2(o[0].x, o[0].y), pack_h2(o[0].z, o[0].w), pack_h2(o[1].x, o[1].y), pack_h2(o[1].z, o[1].w));
                                 }
                             }
-                            if constexpr (!RDB) {
 #pragma unroll
-                                for (int r = 0; r < 4; r++) { res[r][0] = nxt[r][0]; res[r][1] = nxt[r][1]; }
-                            }
+                            for (int r = 0; r < 4; r++) { res[r][0] = nxt[r][0]; res[r][1] = nxt[r][1]; }
                         }
                     }
                 }

@@ -63,6 +63,7 @@ struct JobMaps {
     ConvMaps u1_4, u2_4, v2_4;      // tail inputs of the Cout=64 convs (up1 reads U1, up2 reads U2, HR conv reads V2): 6-row boxes
     ConvMaps u2_8;                  // last conv (Cout=3, 8-row tiles) reads U2
     CUtensorMap oD[4][4];           // [x1..x4][group]: output maps of the growth convs
+    CUtensorMap rX[3][4], rE[3][4]; // [X0 plane][group]: row maps of the residual stream (fp16 plane / int8 extension), conv5's epilogue
     CUtensorMap oV1[4], oV2[4], oU2[4];
 };
 inline CUtensorMap* map_slot(ConvMaps& cm, int g, int k) { return g == 0 ? &cm.m[k] : &cm.mg[g - 1][k]; }
@@ -99,9 +100,6 @@ struct rsr_handle {
     // options
     long long max_batch = 0;  // 0 = auto
     int merge_shapes = 1;     // one launch per layer over all shape groups of a job (see run_job); 0 = one job per shape group
-    // > 0: MB of L2 set aside for persisting lines; every dense block then pins that share of its input plane x0 (read by all five
-    // convs and by the residual) through the stream's access-policy window.  The 32-output-channel convs are HBM-bound (ncu: 5.3-6.2 TB/s).
-    long long l2_persist_mb = 0;
     int serpentine = 1;  // every second conv walks its work tiles backwards: it starts on the pixels the previous conv touched last, which are still in L2
     int debug_mask = 0;  // timing experiments only (see include/realsr_b200.h)
     int time_convs = 0;
@@ -195,6 +193,21 @@ int make_omap(rsr_handle* h, CUtensorMap* m, const void* base, int W, int H, int
     return 0;
 }
 
+// row map of an int8 extension plane [B][H][W][64 B]: box = one 30-pixel row segment, SWIZZLE_64B (conv5's epilogue, conv3x3.cu)
+int make_emap(rsr_handle* h, CUtensorMap* m, const void* base, int W, int H, int B)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {64, (cuuint64_t)W * 64, (cuuint64_t)H * W * 64};
+    cuuint32_t box[4] = {64, (cuuint32_t)CONV_BW, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(h, RSR_ERR_CUDA, "cuTensorMapEncodeTiled failed for an extension map");
+    return 0;
+}
+
 Workspace* acquire_ws(rsr_handle* h)
 {
     {
@@ -241,8 +254,11 @@ struct BatchCtx {
     size_t nconv_ev = 0;
 };
 
+// residual-stream row maps of a CONV_RDB launch, one per shape group each: block input, RRDB input, output (fp16 plane, extension)
+struct RdbMaps { const CUtensorMap *x, *e, *rrx, *rre, *ox, *oe; };
+
 // omaps: the launch's output maps (one per shape group; CONV_STORE16 only)
-int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx, const CUtensorMap* omaps = nullptr, int nomaps = 0)
+int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx, const CUtensorMap* omaps = nullptr, int nomaps = 0, const RdbMaps* rm = nullptr)
 {
     rsr_handle* h = c.h;
     const DeviceModel& dm = h->dm;
@@ -267,6 +283,13 @@ int conv(BatchCtx& c, const ConvMaps* map, ConvArgs a, int conv_idx, const CUten
     mm.w = dm.wmap[conv_idx];
     for (int g = 0; g < nomaps && g < 4; g++) mm.o[g] = omaps[g];
     if (a.mode == CONV_STORE16 && nomaps < (a.ngroups > 0 ? a.ngroups : 1)) return set_err(h, RSR_ERR_GENERIC, "conv: missing output maps");
+    if (a.mode == CONV_RDB) {
+        if (!rm) return set_err(h, RSR_ERR_GENERIC, "conv: missing residual maps");
+        for (int g = 0; g < (a.ngroups > 0 ? a.ngroups : 1) && g < 4; g++) {
+            mm.rx[g] = rm->x[g]; mm.re[g] = rm->e[g]; mm.rrx[g] = rm->rrx[g]; mm.rre[g] = rm->rre[g];
+            mm.o[g] = rm->ox[g]; mm.reo[g] = rm->oe[g];
+        }
+    }
     CK(launch_conv3x3(&mm, a, dm.cout_pad[conv_idx], c.ws->stream));
     if (e1) CK(cudaEventRecord(e1, c.ws->stream));
     c.launches++;
@@ -334,6 +357,10 @@ int run_job(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, 
             }
         for (int k = 1; k <= 4; k++)
             if ((r = make_omap(h, &jm->oD[k - 1][g], xplane(k) + gr.px_off * 32, gr.W, gr.H, gr.n, 32, 32))) return r;
+        for (int i = 0; i < 3; i++) {
+            if ((r = make_omap(h, &jm->rX[i][g], X0[i] + gr.px_off * 64, gr.W, gr.H, gr.n, 64))) return r;
+            if ((r = make_emap(h, &jm->rE[i][g], E8[i] + gr.px_off * 64, gr.W, gr.H, gr.n))) return r;
+        }
         struct { ConvMaps* cm; void* base; int s; int rows; } tails[4] = {{&jm->u1_4, ws->u1.p, 2, rows4}, {&jm->u2_4, ws->u2.p, 4, rows4},
                                                                           {&jm->v2_4, ws->v2.p, 4, rows4}, {&jm->u2_8, ws->u2.p, 4, rows8}};
         for (auto& t : tails) {
@@ -379,31 +406,8 @@ int run_job(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, 
     ConvArgs base{};
     base.f32 = (const float*)ws->f32.p;
     base.tiles = d_tiles_all;
-    size_t persist_bytes = 0;
-    if (h->l2_persist_mb > 0) {
-        int dev = 0, maxp = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        persist_bytes = std::min((size_t)h->l2_persist_mb << 20, (size_t)maxp);
-        if (persist_bytes) CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist_bytes));
-    }
-    auto pin_x0 = [&](const void* base) -> int {  // the stream's launches from here on keep a share of this plane in the L2 set-aside
-        if (!persist_bytes) return 0;
-        int dev = 0, maxw = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        cudaStreamAttrValue v{};
-        v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-        v.accessPolicyWindow.num_bytes = std::min(npx * 128, (size_t)maxw);
-        v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist_bytes / (double)v.accessPolicyWindow.num_bytes);
-        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
-        return 0;
-    };
     // X0 plane rotation: `cur` holds the current block's input, `rin` the input of the enclosing RRDB (kept until its last block)
     int cur = 0;
-    if ((r = pin_x0(X0[cur]))) return r;
     for (int rrdb = 0; rrdb < m.num_rrdb; rrdb++) {
         const int rin = cur;
         for (int rdb = 0; rdb < 3; rdb++) {
@@ -421,15 +425,10 @@ int run_job(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, 
             a.res16 = X0[cur]; a.ext_in = E8[cur];
             a.rr16 = X0[rin]; a.rr_ext = E8[rin];
             a.out16 = X0[nxt]; a.ext_out = E8[nxt]; a.out_cs = 64; a.out_co = 0;
-            if ((r = pin_x0(X0[nxt]))) return r;  // conv5 writes the next block's x0: those lines are the ones to keep from now on
-            if ((r = conv(c, &jm->d4[cur], a, m.idx_rdb(rrdb, rdb, 4)))) return r;
+            const RdbMaps rm{jm->rX[cur], jm->rE[cur], jm->rX[rin], jm->rE[rin], jm->rX[nxt], jm->rE[nxt]};
+            if ((r = conv(c, &jm->d4[cur], a, m.idx_rdb(rrdb, rdb, 4), nullptr, 0, &rm))) return r;
             cur = nxt;
         }
-    }
-    if (persist_bytes) {  // back to normal caching for the tail
-        cudaStreamAttrValue v{};
-        v.accessPolicyWindow.num_bytes = 0;
-        CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
     }
     const int tr_out = (cur + 1) % 3;
     {   // trunk conv + fea (BinaryOp ADD), result in another X0 plane
@@ -817,7 +816,6 @@ int rsr_set_option(rsr_handle* h, const char* key, long long value)
     if (!h || !key) return RSR_ERR_GENERIC;
     if (!strcmp(key, "max_batch")) h->max_batch = value;
     else if (!strcmp(key, "serpentine")) h->serpentine = value ? 1 : 0;
-    else if (!strcmp(key, "l2_persist_mb")) h->l2_persist_mb = value < 0 ? 0 : value;
     else if (!strcmp(key, "merge_shapes")) h->merge_shapes = value ? 1 : 0;
     else if (!strcmp(key, "debug_mask")) h->debug_mask = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
@@ -905,6 +903,11 @@ int rsr_debug_conv(rsr_handle* h, int conv_index, const uint16_t* in16, int H, i
         a.rr16 = d_in; a.rr_ext = d_ext;
         a.ext_out = d_ext + npx * 64;
         a.rrdb_end = atoi(getenv("RSR_DBG_RDB")) > 1;
+        if ((r = make_omap(h, &map.rx[0], d_in, W, H, 1, 64)) || (r = make_emap(h, &map.re[0], d_ext, W, H, 1)) ||
+            (r = make_emap(h, &map.reo[0], d_ext + npx * 64, W, H, 1)))
+            return r;
+        map.rrx[0] = map.rx[0];
+        map.rre[0] = map.re[0];
     }
     if (getenv("RSR_DBG_TS")) {
         CK(cudaMalloc(&d_ts, 64 * 8 * sizeof(long long)));

@@ -95,8 +95,11 @@ struct alignas(64) ConvMaps {
     CUtensorMap m[CONV_MAX_KBLOCKS];
     CUtensorMap w;         // 2-D map over the conv's weight rows [rows][64 ch], box {32 ch, N/2 rows} (N = 192 / 96 / 64), SWIZZLE_64B
     CUtensorMap mg[3][CONV_MAX_KBLOCKS];  // merged multi-shape launch: the K-block maps of groups 1..3 (group 0 uses m[])
-    CUtensorMap o[4];      // CONV_STORE16: the OUTPUT plane of group g, box {cout_pad ch, 30 px, 1 row}, SWIZZLE_64B (Cout=32: a
-                           // 32-channel plane) / SWIZZLE_128B (Cout=64: a 64-channel plane): the epilogue leaves through TMA stores
+    CUtensorMap o[4];      // CONV_STORE16 / CONV_RDB: the OUTPUT plane of group g, box {cout_pad ch, 30 px, 1 row}, SWIZZLE_64B (Cout=32:
+                           // a 32-channel plane) / SWIZZLE_128B (Cout=64: a 64-channel plane): the epilogue leaves through TMA stores
+    // CONV_RDB: row boxes {64, 30 px, 1 row} of the residual stream of group g (ConvArgs::res16 ...): rx / re = this block's input x0
+    // (fp16, SWIZZLE_128B) and its int8 extension (SWIZZLE_64B), rrx / rre = the enclosing RRDB's input, reo = the output extension
+    CUtensorMap rx[4], re[4], rrx[4], rre[4], reo[4];
 };
 // conv3x3.cu: conv3x3 s1 p1 (+ fused epilogue, see ConvMode) as implicit GEMM on tcgen05 CTA pairs.  cout_pad in {16, 32, 64}.
 cudaError_t launch_conv3x3(const ConvMaps* in_maps, const ConvArgs& a, int cout_pad, cudaStream_t stream);
