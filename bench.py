@@ -6,16 +6,16 @@
 
 Workload at any N: BASELINE.json configs[1] -- one 1920x1080 RGB image, models-DF2K, scale 4, tile 400 -- per GPU per step
 (weak scaling: every rank upscales its own synthetic image; images/tiles shard with no data-path collective).
-A "step" is one pass of the hot path (RealSR::process) over that image: 15 padded tiles, 353 kernel launches per
-shape batch.
+A "step" is one pass of the hot path (RealSR::process) over that image: 15 padded tiles in four padded shapes, ONE launch
+per layer over all of them -- 362 kernel launches per step, 350 of them the tensor-core conv kernel (+ Conv_0).
 
   value  : whole-job output MP/s with the source image already resident in HBM and the result left in HBM
            (rsr_process_device), device time from CUDA events on the engine's stream, max over ranks.
   e2e    : the same metric through the reference-facing call (rsr_process == RealSR::process) with pinned HOST buffers:
            H2D of the u8 source and D2H of the 16x larger u8 result are inside the timed region.
-  roofline: the dominant kernel (conv3x3_tc2_kernel, 350 launches per batch): algorithmic FLOPs (35.853696 MFLOP per
-           network-input pixel) / summed CUDA-event duration of those launches, against the measured bf16
-           peak in MEASURED_PEAKS.json (sustained figure: the kernel is timed inside a long step).
+  roofline: the dominant kernel (conv3x3_kernel, csrc/conv3x3.cu; 350 launches per step): algorithmic FLOPs (35.853696
+           MFLOP per network-input pixel) / summed CUDA-event duration of those launches, against the measured
+           bf16 peak in MEASURED_PEAKS.json (sustained figure: the kernel is timed inside a long step).
   cpu_baseline: the REAL reference CPU path (oracle/_ref = reference process_cpu + ncnn b4ba207) on this box's host
            cores, on a bounded sample (one 400x400 tile = same padded shape as 8 of the 15 tiles of the workload).
 
@@ -181,8 +181,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: warm-up + the device-resident timed steps only "
                     "(no e2e leg, no per-conv event pass, no CPU baseline), prints no bench line")
-    ap.add_argument("--opts", default="", help="engine options for A/B runs, e.g. epilogue_split=1,merge_shapes=1 (default: none; "
-                                               "recorded under config.engine_options)")
+    ap.add_argument("--opts", default="", help="engine options for A/B runs, e.g. merge_shapes=0,serpentine=0 (default: none; "
+                                               "recorded under engine_options)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -315,7 +315,7 @@ def main():
             "data": "synthetic",
             "config": workload_config(world),
             "engine_options": engine_options or "defaults",
-            "precision": "fp16 operands / fp32 accumulate on tcgen05, fp32 Conv_0, fp32 RRDB skip stream",
+            "precision": "fp16 operands / fp32 accumulate on tcgen05, fp32 Conv_0, residual streams carried as fp16 + int8 extension (19 mantissa bits)",
             "timing": "CUDA events on the engine's stream around every call, summed over the K steps, max over ranks; "
                       "wall clock of the same region %.2f ms/step" % (wall_ms / args.steps),
             "e2e": {"value": OUT_MP * world / (e2e_dev_ms / args.steps * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": IMG_W * IMG_H * 3,
