@@ -3,31 +3,38 @@
 // NHWC boxes, accumulators in TMEM, everything that follows the conv in the graph (bias, LeakyReLU, Concat slice, Eltwise /
 // BinaryOp residuals, post-processing) fused into the epilogue.  This is the only tensor-core kernel of the engine.
 //
-// GEMM view: M = pixels, N = Cout (x taps, see below), K = 9 * Cin; fp16 x fp16 -> fp32.
-//   * Work tile = 16 rows x 30 columns of output pixels, owned by a cluster of 2 CTAs; CTA r computes rows 8r..8r+7 as two
-//     M-tiles of 128 "positions" (4 rows x pitch 32).  One cta_group::2 MMA (M = 256) covers one M-tile in each CTA.
-//   * A operand: per K-block (KB = 64 or 32 input channels) one haloed TMA box {KB ch, 32 px, 10 rows} (out-of-bounds =
-//     zero fill = the conv's padding).  With a fixed pitch of 32 px the A rows of tap (ky,kx) for 128 consecutive positions
-//     are the 128 consecutive smem rows starting at q + 32*ky + kx: row-shifted UMMA descriptors instead of im2col
-//     (SWIZZLE_128B/64B is a function of the absolute smem address, so any 128-B / 64-B aligned start works).
-//   * Horizontal tap grouping keeps the MMAs wide (an MMA re-reads its 4 KB A tile from smem, so narrow N is feed-bound,
-//     tools/ubench.cu): Cout=32 stacks the three kx taps of a kernel row along N (one N=96 MMA instead of three N=32);
-//     Cout=64 stacks kx=0,1 (N=128) and runs kx=2 as N=64 with the A window shifted by 2; Cout=3 (padded 16): N=64.
-//     Column group g of position q then holds tap (ky,g)'s contribution to the output at q-g; the 32 lanes of an epilogue
-//     warp are 32 consecutive positions of one tile row, so the epilogue fetches it with __shfl_down.
+// GEMM view: M = pixels, N = Cout x 3 stacked taps (see below), K = 9 * Cin; fp16 x fp16 -> fp32.
+//   * Work tile = 30 columns x 16 rows (Cout <= 32) or 8 rows (Cout = 64) of output pixels, owned by a cluster of 2 CTAs; CTA r
+//     computes its half of the rows as M-tiles of 128 "positions" (4 rows x pitch 32): two M-tiles (Cout <= 32) or one (Cout = 64,
+//     whose N = 192 accumulators need 192 TMEM columns per M-tile: two accumulator sets = 384 of the 512 columns).  One
+//     cta_group::2 MMA (M = 256) covers one M-tile in each CTA.
+//   * A operand: per 32-channel K-block one haloed TMA box {32 ch, 32 px, 10 or 6 rows} (out-of-bounds = zero fill = the conv's
+//     padding); K-block k of a conv's input has its own tensor map (ConvMaps::m[k]: the two halves of the 64-channel x0 plane, then
+//     one 32-channel plane per growth tensor x1..x4), so a conv reads exactly the channels it needs.  With a fixed pitch of 32 px
+//     the A rows of tap (ky,kx) for 128 consecutive positions are the 128 consecutive smem rows starting at q + 32*ky + kx:
+//     row-shifted UMMA descriptors instead of im2col (SWIZZLE_64B is a function of the absolute smem address, so any 64-B aligned
+//     start works).
+//   * Horizontal tap stacking keeps the MMAs wide (an MMA re-reads its 4 KB A tile from smem, so narrow N is feed-bound,
+//     tools/ubench2.cu): the three kx taps of a kernel row are stacked along N -- Cout=32: one N=96 MMA per k-step, Cout=64: one
+//     N=192 MMA, Cout=3 (padded 16): N=64.  Column group g of position q then holds tap (ky,g)'s contribution to the output at
+//     q-g; the 32 lanes of an epilogue warp are 32 consecutive positions of one tile row, so the epilogue fetches it with
+//     __shfl_down.
 //   * B operand: each CTA keeps ITS half of the conv's weights resident in smem for the whole launch (B is split N/2 + N/2
 //     between the two CTAs of a pair), fetched once by TMA before the grid dependency is resolved.
 //   * Warp roles (12 warps): warp 0 A producer (TMA), warp 1 MMA issuer (leader CTA), warp 2 weight fetch, warps 4..11
 //     epilogue.  setmaxnreg moves registers from the control warpgroup to the epilogue warpgroups.
-//   * Epilogue of the bias/activation convs (CONV_STORE16: 4 of the 5 convs of a dense block + the tail): one (M-tile, row)
-//     unit per warp, EARLY accumulator hand-back -- the warp pulls its 32 positions x 96/128 columns into registers (taps
-//     combined), returns the set to the MMA issuer and only then does activation / pack / store -- and the row leaves through
-//     a swizzled staging buffer and one TMA store.  Per-tile timestamps of the round-1 scheme showed the chain "MMAs done ->
-//     whole epilogue -> hand-back" bounding the Cout=32 convs at 2.6 k clk per tile where their MMAs need 1.2 k.
-//     The residual / post-processing modes (conv5, trunk, last conv: bounded by their MMAs or by HBM) keep two 4-warp groups
-//     that alternate work tiles, one per accumulator set.
+//   * Epilogues, all with EARLY accumulator hand-back (pull the columns into registers, combine the taps, return the set to the
+//     MMA issuer, only then do the math and the stores; per-tile timestamps of the round-1 scheme showed the chain "MMAs done ->
+//     whole epilogue -> hand-back" bounding the Cout=32 convs at 2.6 k clk per tile where their MMAs need 1.2 k):
+//       CONV_STORE16 (bias + LeakyReLU: 4 of the 5 convs of a dense block, the tail): one (M-tile, row) unit per warp; the row is
+//         packed to fp16 into a swizzled staging buffer and leaves through ONE TMA store.
+//       CONV_RDB (conv5 of a dense block): the residual stream (fp16 + int8 extension, kernels.h) ALSO moves by TMA: the operand
+//         row boxes arrive in the warp's staging buffer while the MMAs run, every lane works on its own pixel (the TMEM-native
+//         layout), the result row and its extension leave through two TMA stores.  No per-thread global access.
+//       CONV_TRUNK / last conv (one launch per frame each): two 4-warp groups alternate tiles; fp32 operands go through a per-warp
+//         smem transpose so that global accesses are 64-B runs.
 //   * Tile geometry is walked incrementally (add-with-carry per tile; integer divisions only when a merged launch enters a
-//     new shape group).
+//     new shape group); every second conv of a job walks its tiles backwards (ConvArgs::reverse).
 //   * The MMA issuer's loop carries no divisions, no tile geometry and no 64-bit descriptor arithmetic: stage index and
 //     barrier parities are counters, descriptors are {lo32 = base + immediate, hi32 = constant}.
 //   * Merged multi-shape launches: one launch per layer covers up to four same-shape tile groups (ConvArgs::grp), so a frame
