@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Interleaved A/B/... of engine option sets on one box (device-resident, CUDA-event ms per call):
-   ab.py [--tile T] [--size WxH] [--tta] "conv_impl=2" "conv_impl=4,merge_shapes=1" ...
+   ab.py [--tile T] [--size WxH] [--tta] "" "merge_shapes=0" "serpentine=0,max_batch=8" ...
 Prints the median / min ms of every set, the conv-kernel share (time_convs run) and whether the outputs are identical."""
 import os, sys
 import numpy as np, torch

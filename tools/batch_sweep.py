@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import realsr_ncnn_vulkan_b200 as rb
 e = rb.RealSR(0)
 assert e.load(os.path.join(ROOT, "models/models-DF2K/x4.param"), os.path.join(ROOT, "models/models-DF2K/x4.bin")) == 0
-for kv in os.environ.get("RSR_OPTS", "").split(","):  # e.g. RSR_OPTS=serpentine=1,epilogue_split=1
+for kv in os.environ.get("RSR_OPTS", "").split(","):  # e.g. RSR_OPTS=serpentine=0,merge_shapes=0
     if "=" in kv:
         k, v = kv.split("=")
         assert e.set_option(k, int(v)) == 0, e.last_error()

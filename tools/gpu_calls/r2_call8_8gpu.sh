@@ -1,5 +1,5 @@
 #!/bin/bash
-# BASELINE configs[2] on the 8-GPU box: gpurun --gpus 8 -- 'bash tools/r2_call8_8gpu.sh'
+# BASELINE configs[2] on the 8-GPU box: gpurun --gpus 8 -- 'bash tools/gpu_calls/r2_call8_8gpu.sh'
 t0=$(date +%s); mark() { echo "[call8] $1 @ $(( $(date +%s) - t0 )) s"; }
 nvidia-smi -L | head -8; df -h /dev/shm /tmp | tail -2; nproc
 N=${RSR_GPUS:-8}

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Parity of the engine against every committed golden (outputs of the real reference CPU path), per option set:
-   parity_report.py "conv_impl=5,merge_shapes=1" "conv_impl=5,merge_shapes=1,residual_fp16=0" ...
+   parity_report.py "" "merge_shapes=0" ...
 Prints max |diff|, % of bytes that differ and bytes beyond 1 LSB per case; writes gpurun_out/parity_report.json."""
 import json, os, sys
 import numpy as np
