@@ -34,86 +34,106 @@ __device__ __forceinline__ void variant_to_base(int variant, int a, int b, int p
 }
 
 constexpr int FIRST_THREADS = 256;
+constexpr int FIRST_TW = 32, FIRST_TH = 8;       // output pixels of a block: 32 columns x 8 rows
+constexpr int FIRST_PW = FIRST_TW + 2 + 2;       // patch row pitch in floats (34 used)
 
+// One block = a 32 x 8 patch of one padded tile.  The 34 x 10 x 3 source patch is gathered ONCE (reflect-101, TTA variant, u8 -> float
+// x 1/255) into shared memory -- the first version gathered it per output thread, 36 times per pixel, and was bound by that index
+// arithmetic (1.6 TB/s of stores).  Thread (pl, quarter) then computes 16 output channels of 4 pixels: every weight float4 fetched
+// from shared memory feeds 16 FMAs.  Summation order per output = the naive layer's (bias, then input-channel major, tap minor).
 __global__ void __launch_bounds__(FIRST_THREADS) conv_first_kernel(const FirstArgs a)
 {
-    // weights re-ordered to [c][tap][oc] so that 4 consecutive output channels are one float4
-    __shared__ float4 sw[27 * 16];
+    __shared__ float4 sw[27 * 16];  // weights re-ordered to [c][tap][oc]: 4 consecutive output channels are one float4
     __shared__ float sb[64];
+    __shared__ float sp[3][FIRST_TH + 2][FIRST_PW];
     for (int i = threadIdx.x; i < 27 * 64; i += FIRST_THREADS) {
         const int oc = i & 63, ct = i >> 6;  // ct = c*9 + tap
         reinterpret_cast<float*>(sw)[ct * 64 + oc] = a.w[oc * 27 + ct];
     }
     if (threadIdx.x < 64) sb[threadIdx.x] = a.bias[threadIdx.x];
-    __syncthreads();
 
     const int b = blockIdx.y;
     const TileDesc td = a.tiles[b];
-    const long long gid = (long long)blockIdx.x * FIRST_THREADS + threadIdx.x;
-    const long long npix = (long long)a.H * a.W;
-    const long long p = gid >> 2;
-    const int quarter = (int)(gid & 3);
-    if (p >= npix) return;
-    const int y = (int)(p / a.W), x = (int)(p - (long long)y * a.W);
+    const int tiles_x = (a.W + FIRST_TW - 1) / FIRST_TW;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int x0 = tx * FIRST_TW, y0 = ty * FIRST_TH;
+    for (int i = threadIdx.x; i < (FIRST_TH + 2) * (FIRST_TW + 2); i += FIRST_THREADS) {
+        const int py = i / (FIRST_TW + 2), px = i - py * (FIRST_TW + 2);
+        const int aa = y0 + py - 1, bb = x0 + px - 1;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        if (aa >= 0 && aa < a.H && bb >= 0 && bb < a.W) {  // zero padding of the conv at the padded-tile border
+            int ii, jj;
+            variant_to_base(td.variant, aa, bb, td.base_h, td.base_w, ii, jj);
+            const int X = reflect101(td.in_x0 + jj, a.img_w);
+            const int Y = reflect101(td.in_y0 + ii, a.img_h);
+            const uint8_t* src = a.img + ((size_t)Y * a.img_w + X) * a.img_c;
+            v0 = (float)src[0] * (1 / 255.f);
+            v1 = (float)src[1] * (1 / 255.f);
+            v2 = (float)src[2] * (1 / 255.f);
+        }
+        sp[0][py][px] = v0;
+        sp[1][py][px] = v1;
+        sp[2][py][px] = v2;
+    }
+    __syncthreads();
 
-    float in[27];
+    const int quarter = threadIdx.x & 3, pl = threadIdx.x >> 2;  // pixels pl + 64 i: row 2 i + (pl >> 5), column pl & 31
+    const int col = pl & 31, row0 = pl >> 5;
+    float acc[4][16];
 #pragma unroll
-    for (int ky = 0; ky < 3; ky++) {
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int kx = 0; kx < 3; kx++) {
-            const int aa = y + ky - 1, bb = x + kx - 1;
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-            if (aa >= 0 && aa < a.H && bb >= 0 && bb < a.W) {  // zero padding of the conv at the padded-tile border
-                int i, j;
-                variant_to_base(td.variant, aa, bb, td.base_h, td.base_w, i, j);
-                const int X = reflect101(td.in_x0 + j, a.img_w);
-                const int Y = reflect101(td.in_y0 + i, a.img_h);
-                const uint8_t* px = a.img + ((size_t)Y * a.img_w + X) * a.img_c;
-                v0 = (float)px[0] * (1 / 255.f);
-                v1 = (float)px[1] * (1 / 255.f);
-                v2 = (float)px[2] * (1 / 255.f);
+        for (int j = 0; j < 16; j++) acc[i][j] = sb[quarter * 16 + j];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                const int ct = c * 9 + ky * 3 + kx;
+                float4 w[4];
+#pragma unroll
+                for (int j4 = 0; j4 < 4; j4++) w[j4] = sw[ct * 16 + quarter * 4 + j4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float v = sp[c][2 * i + row0 + ky][col + kx];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        acc[i][j4 * 4 + 0] = fmaf(v, w[j4].x, acc[i][j4 * 4 + 0]);
+                        acc[i][j4 * 4 + 1] = fmaf(v, w[j4].y, acc[i][j4 * 4 + 1]);
+                        acc[i][j4 * 4 + 2] = fmaf(v, w[j4].z, acc[i][j4 * 4 + 2]);
+                        acc[i][j4 * 4 + 3] = fmaf(v, w[j4].w, acc[i][j4 * 4 + 3]);
+                    }
+                }
             }
-            in[0 * 9 + ky * 3 + kx] = v0;
-            in[1 * 9 + ky * 3 + kx] = v1;
-            in[2 * 9 + ky * 3 + kx] = v2;
+    const int x = x0 + col;
+    if (x >= a.W) return;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int y = y0 + 2 * i + row0;
+        if (y >= a.H) continue;
+        const size_t pix = ((size_t)b * a.H + y) * a.W + x;
+        float4* f = reinterpret_cast<float4*>(a.f32 + pix * 64 + quarter * 16);  // fp32 `fea` for the trunk add (x4.param:994-995)
+#pragma unroll
+        for (int j4 = 0; j4 < 4; j4++) f[j4] = make_float4(acc[i][j4 * 4], acc[i][j4 * 4 + 1], acc[i][j4 * 4 + 2], acc[i][j4 * 4 + 3]);
+        uint4* d = reinterpret_cast<uint4*>(a.d16 + pix * 64 + quarter * 16);
+        uint32_t ext[4] = {0, 0, 0, 0};  // int8 extensions of the 16 fp16 values (ConvArgs::ext_in), 4 per word
+#pragma unroll
+        for (int j8 = 0; j8 < 2; j8++) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float v0 = acc[i][j8 * 8 + 2 * k], v1 = acc[i][j8 * 8 + 2 * k + 1];
+                __half2 hh = __floats2half2_rn(v0, v1);
+                pk[k] = *reinterpret_cast<uint32_t*>(&hh);
+                const float2 g = __half22float2(hh);
+                const uint32_t q = (uint32_t)(res_ext_encode(v0, g.x) & 255) | ((uint32_t)(res_ext_encode(v1, g.y) & 255) << 8);  // floor / saturating, see kernels.h
+                ext[j8 * 2 + (k >> 1)] |= q << (16 * (k & 1));
+            }
+            d[j8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+        *reinterpret_cast<uint4*>(a.ext + pix * 64 + quarter * 16) = make_uint4(ext[0], ext[1], ext[2], ext[3]);
     }
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; j++) acc[j] = sb[quarter * 16 + j];
-#pragma unroll
-    for (int ct = 0; ct < 27; ct++) {  // input-channel major, tap minor: the naive layer's summation order
-        const float v = in[ct];
-#pragma unroll
-        for (int j4 = 0; j4 < 4; j4++) {
-            const float4 w = sw[ct * 16 + quarter * 4 + j4];
-            acc[j4 * 4 + 0] = fmaf(v, w.x, acc[j4 * 4 + 0]);
-            acc[j4 * 4 + 1] = fmaf(v, w.y, acc[j4 * 4 + 1]);
-            acc[j4 * 4 + 2] = fmaf(v, w.z, acc[j4 * 4 + 2]);
-            acc[j4 * 4 + 3] = fmaf(v, w.w, acc[j4 * 4 + 3]);
-        }
-    }
-    const size_t pix = (size_t)b * npix + p;
-    float4* f = reinterpret_cast<float4*>(a.f32 + pix * 64 + quarter * 16);  // fp32 `fea` for the trunk add (x4.param:994-995)
-#pragma unroll
-    for (int j4 = 0; j4 < 4; j4++) f[j4] = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
-    uint4* d = reinterpret_cast<uint4*>(a.d16 + pix * 64 + quarter * 16);
-    uint32_t ext[4] = {0, 0, 0, 0};  // int8 extensions of the 16 fp16 values (ConvArgs::ext_in), 4 per word
-#pragma unroll
-    for (int j8 = 0; j8 < 2; j8++) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float v0 = acc[j8 * 8 + 2 * k], v1 = acc[j8 * 8 + 2 * k + 1];
-            __half2 hh = __floats2half2_rn(v0, v1);
-            pk[k] = *reinterpret_cast<uint32_t*>(&hh);
-            const float2 f = __half22float2(hh);
-            const uint32_t q = (uint32_t)(res_ext_encode(v0, f.x) & 255) | ((uint32_t)(res_ext_encode(v1, f.y) & 255) << 8);  // floor / saturating, see kernels.h
-            ext[j8 * 2 + (k >> 1)] |= q << (16 * (k & 1));
-        }
-        d[j8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    }
-    *reinterpret_cast<uint4*>(a.ext + pix * 64 + quarter * 16) = make_uint4(ext[0], ext[1], ext[2], ext[3]);
 }
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, int in_vec_stride, uint4* __restrict__ out, int B, int H, int W)
@@ -213,8 +233,16 @@ __global__ void __launch_bounds__(256) alpha_bicubic4x_kernel(const AlphaArgs a)
     a.img_out[((size_t)Y * a.img_w * 4 + X) * 4 + 3] = (uint8_t)min(max(iv, 0), 255);
 }
 
+// grid / block of conv_first_kernel (shared with the host emulation in tests/emu)
+inline void conv_first_launch_dims(const FirstArgs& a, dim3& grid, dim3& block)
+{
+    grid = dim3((unsigned)(((a.W + FIRST_TW - 1) / FIRST_TW) * ((a.H + FIRST_TH - 1) / FIRST_TH)), a.B);
+    block = dim3(FIRST_THREADS);
+}
+
 }  // namespace
 
+#ifndef RSR_HOST_EMULATION  // tests/emu includes this file on the host: the <<<>>> launchers are device-build only
 cudaError_t launch_alpha_bicubic4x(const AlphaArgs& a, cudaStream_t stream)
 {
     dim3 block(32, 8);
@@ -225,9 +253,9 @@ cudaError_t launch_alpha_bicubic4x(const AlphaArgs& a, cudaStream_t stream)
 
 cudaError_t launch_conv_first(const FirstArgs& a, cudaStream_t stream)
 {
-    const long long nthreads = (long long)a.H * a.W * 4;
-    dim3 grid((unsigned)((nthreads + FIRST_THREADS - 1) / FIRST_THREADS), a.B);
-    conv_first_kernel<<<grid, FIRST_THREADS, 0, stream>>>(a);
+    dim3 grid, block;
+    conv_first_launch_dims(a, grid, block);
+    conv_first_kernel<<<grid, block, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -247,5 +275,6 @@ cudaError_t launch_tta_gather(const TtaGatherArgs& a, int max_crop_w, int max_cr
     tta_gather_kernel<<<grid, block, 0, stream>>>(a);
     return cudaGetLastError();
 }
+#endif  // RSR_HOST_EMULATION
 
 }  // namespace rsr
