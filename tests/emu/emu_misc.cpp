@@ -29,5 +29,28 @@ int emu_upsample2x(const uint16_t* in, int in_cs, uint16_t* out, int B, int H, i
     return 0;
 }
 
+#ifndef RSR_EMU_CONV_FIRST_ONLY  // the conv_first_simple fixture has only that kernel
+// alpha_bicubic4x_kernel over a whole RGBA image (all tiles): writes byte 3 of every output pixel
+int emu_alpha_bicubic4x(const uint8_t* img, int img_w, int img_h, int tilesize, int tile_first, int tile_count, uint8_t* out)
+{
+    AlphaArgs a{};
+    a.img = img; a.img_out = out; a.img_w = img_w; a.img_h = img_h; a.tilesize = tilesize; a.tile_first = tile_first; a.tile_count = tile_count;
+    cuda_emu::launch(dim3((img_w * 4 + 31) / 32, (img_h * 4 + 7) / 8), dim3(32, 8), [=] { alpha_bicubic4x_kernel(a); });
+    return 0;
+}
+
+// tta_gather_kernel: ngroups tiles x 8 variant planes [slot][4H][4W][4] fp32 -> averaged, post-processed u8 crop in the output image
+int emu_tta_gather(const float* tta_out, const TileDesc* td, int ngroups, long long slot_stride, uint8_t* img_out, int img_w, int img_h, int img_c,
+                   int prepad_s, int max_crop_w, int max_crop_h)
+{
+    TtaGatherArgs a{};
+    a.tta_out = tta_out; a.tiles = td; a.ngroups = ngroups; a.slot_stride = (size_t)slot_stride; a.img_out = img_out; a.img_w = img_w; a.img_h = img_h;
+    a.img_c = img_c; a.prepad_s = prepad_s;
+    cuda_emu::launch(dim3((max_crop_w + 31) / 32, (max_crop_h + 7) / 8, ngroups), dim3(32, 8), [=] { tta_gather_kernel(a); });
+    return 0;
+}
+
+#endif
+
 int emu_sizeof_tiledesc() { return (int)sizeof(TileDesc); }
 }
