@@ -9,8 +9,9 @@
 // GPUs (BASELINE configs[2] uses `-j 4:8:4` with 8 GPUs, which the reference itself rejects, main.cpp:560-564); auto
 // tile size (-t 0) is 200, the reference's pick on any GPU with more than 1.9 GB (main.cpp:753-774: tile geometry is part of the
 // numerical contract); codecs: PNG (host/png_codec.h on zlib), JPEG (host/jpeg_codec.h: sequential + progressive reader,
-// baseline writer) and lossless WebP (host/webp_codec.h), all written for this repo -- the reference's stb / libwebp files
-// are not copied; lossy (VP8) WebP inputs go through the Python CLI (`python -m realsr_ncnn_vulkan_b200.cli`, Pillow).  Host plumbing only: every pixel goes through RealSR::process.
+// baseline writer) and WebP (host/webp_codec.h: lossless reader + writer; host/vp8_codec.h: lossy reader incl. alpha planes), all
+// written for this repo -- the reference's stb / libwebp files are not copied.  Host plumbing only: every pixel goes through
+// RealSR::process.
 #include <dirent.h>
 #include <stdio.h>
 #include <stdlib.h>

@@ -1,11 +1,13 @@
-// webp_codec.h -- lossless WebP (VP8L) reader / writer for the C++ command line (host/realsr_cli.cpp).
+// webp_codec.h -- WebP reader (lossless VP8L here, lossy VP8 in vp8_codec.h, alpha planes of lossy files) and lossless writer for
+// the C++ command line (host/realsr_cli.cpp).
 //
 // The reference links libwebp: it decodes any WebP input and always SAVES lossless (src/webp_image.h:60-77,
 // WebPEncodeLosslessRGB / RGBA).  libwebp is not copied; this is an independent implementation of the "WebP Lossless
 // Bitstream Specification":
 //   decode: RIFF / VP8L (also inside a VP8X container), all four transforms (predictor with its 14 modes, cross-colour,
 //           subtract-green, colour indexing with pixel packing), meta prefix codes, colour cache, LZ77 backward
-//           references with the 2-D distance map; lossy (VP8) files are refused with a message -- use the Python CLI;
+//           references with the 2-D distance map; lossy files: the VP8 key frame (vp8_codec.h) plus, inside a VP8X container, the
+//           ALPH chunk (raw or VP8L-coded alpha with the horizontal / vertical / gradient prediction filters);
 //   encode: subtract-green + predictor transform (mode chosen per 16x16 block by the residual entropy proxy) and one set of
 //           length-limited Huffman codes; backward references only as run-length copies of the previous pixel (flat areas
 //           of drawings) -- super-resolved photographs have few longer exact repeats.
@@ -19,6 +21,8 @@
 #include <algorithm>
 #include <string>
 #include <vector>
+
+#include "vp8_codec.h"
 
 namespace rsrhost {
 
@@ -294,39 +298,12 @@ inline uint32_t predict_at(const uint32_t* px, int w, int x, int y, int mode)
 
 }  // namespace vp8l
 
-inline bool webp_decode_file(const std::string& path, int& w, int& h, int& c, std::vector<uint8_t>& pixels, std::string* why = nullptr)
+namespace vp8l {
+
+// the image stream after the 5-byte VP8L header (also the payload of a compressed ALPH chunk): transforms + entropy-coded ARGB
+inline bool decode_stream(BitReader& br, int w, int h, std::vector<uint32_t>& px, const char** why)
 {
-    using namespace vp8l;
-    auto fail = [&](const char* m) { if (why) *why = m; return false; };
-    FILE* fp = fopen(path.c_str(), "rb");
-    if (!fp) return fail("cannot open");
-    std::vector<uint8_t> f;
-    {
-        uint8_t buf[65536];
-        size_t n;
-        while ((n = fread(buf, 1, sizeof buf, fp)) > 0) f.insert(f.end(), buf, buf + n);
-        fclose(fp);
-    }
-    if (f.size() < 20 || memcmp(f.data(), "RIFF", 4) || memcmp(f.data() + 8, "WEBP", 4)) return fail("not a WebP file");
-    size_t pos = 12;
-    const uint8_t* vp8l = nullptr;
-    size_t vp8l_len = 0;
-    while (pos + 8 <= f.size()) {
-        const uint32_t len = (uint32_t)f[pos + 4] | ((uint32_t)f[pos + 5] << 8) | ((uint32_t)f[pos + 6] << 16) | ((uint32_t)f[pos + 7] << 24);
-        if (len > f.size() - pos - 8) return fail("truncated chunk");
-        if (!memcmp(&f[pos], "VP8L", 4)) { vp8l = &f[pos + 8]; vp8l_len = len; break; }
-        if (!memcmp(&f[pos], "VP8 ", 4)) return fail("lossy WebP (VP8) is not supported by the C++ command line (use the Python CLI)");
-        if (!memcmp(&f[pos], "ANIM", 4)) return fail("animated WebP is not supported");
-        pos += 8 + (size_t)len + (len & 1);
-    }
-    if (!vp8l || vp8l_len < 5 || vp8l[0] != 0x2f) return fail("no VP8L bitstream");
-    BitReader br;
-    br.p = vp8l + 1;
-    br.n = vp8l_len - 1;
-    w = (int)br.get(14) + 1;
-    h = (int)br.get(14) + 1;
-    const bool alpha_hint = br.get(1) != 0;
-    if (br.get(3) != 0) return fail("unknown VP8L version");
+    auto fail = [&](const char* m) { *why = m; return false; };
     // transforms, in bitstream order
     struct Xf { int type, bits, xs; std::vector<uint32_t> data; };
     std::vector<Xf> xfs;
@@ -353,7 +330,6 @@ inline bool webp_decode_file(const std::string& path, int& w, int& h, int& c, st
         xfs.push_back(std::move(t));
         if (br.eos) return fail("truncated bitstream");
     }
-    std::vector<uint32_t> px;
     if (!decode_image(br, xs, h, true, px)) return fail("corrupt image data");
     // inverse transforms, last one first
     for (size_t ti = xfs.size(); ti-- > 0;) {
@@ -400,6 +376,104 @@ inline bool webp_decode_file(const std::string& path, int& w, int& h, int& c, st
         }
     }
     if (px.size() != (size_t)w * h) return fail("transform geometry");
+    return true;
+}
+
+// ALPH chunk of a lossy file (WebP container spec): 1 header byte (bits 0-1 compression: 0 raw / 1 VP8L stream with the alpha in
+// green, bits 2-3 prediction filter), then the plane; the filter is undone row by row
+inline bool decode_alpha(const uint8_t* d, size_t n, int w, int h, std::vector<uint8_t>& a, const char** why)
+{
+    auto fail = [&](const char* m) { *why = m; return false; };
+    if (n < 1) return fail("empty ALPH chunk");
+    const int method = d[0] & 3, filter = (d[0] >> 2) & 3;
+    a.assign((size_t)w * h, 255);
+    if (method == 0) {
+        if (n - 1 < (size_t)w * h) return fail("truncated ALPH chunk");
+        memcpy(a.data(), d + 1, (size_t)w * h);
+    } else if (method == 1) {
+        BitReader br;
+        br.p = d + 1;
+        br.n = n - 1;
+        std::vector<uint32_t> px;
+        if (!decode_stream(br, w, h, px, why)) return false;
+        for (size_t i = 0; i < px.size(); i++) a[i] = (uint8_t)(px[i] >> 8);
+    } else
+        return fail("unknown alpha compression");
+    if (filter)
+        for (int y = 0; y < h; y++) {
+            uint8_t* row = &a[(size_t)y * w];
+            const uint8_t* prev = y ? row - w : nullptr;
+            if (filter == 1 || !prev) {  // horizontal (also the first row of the other two): left neighbour, first pixel from above
+                int pred = prev ? prev[0] : 0;
+                for (int x = 0; x < w; x++) pred = row[x] = (uint8_t)(row[x] + pred);
+            } else if (filter == 2) {    // vertical
+                for (int x = 0; x < w; x++) row[x] = (uint8_t)(row[x] + prev[x]);
+            } else {                     // gradient: clip(left + top - top-left)
+                int left = prev[0], tl = prev[0];
+                for (int x = 0; x < w; x++) {
+                    const int top = prev[x];
+                    const int g = left + top - tl;
+                    left = row[x] = (uint8_t)(row[x] + (g < 0 ? 0 : (g > 255 ? 255 : g)));
+                    tl = top;
+                }
+            }
+        }
+    return true;
+}
+
+}  // namespace vp8l
+
+inline bool webp_decode_file(const std::string& path, int& w, int& h, int& c, std::vector<uint8_t>& pixels, std::string* why = nullptr)
+{
+    using namespace vp8l;
+    auto fail = [&](const char* m) { if (why) *why = m; return false; };
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) return fail("cannot open");
+    std::vector<uint8_t> f;
+    {
+        uint8_t buf[65536];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof buf, fp)) > 0) f.insert(f.end(), buf, buf + n);
+        fclose(fp);
+    }
+    if (f.size() < 20 || memcmp(f.data(), "RIFF", 4) || memcmp(f.data() + 8, "WEBP", 4)) return fail("not a WebP file");
+    size_t pos = 12;
+    const uint8_t *vp8l = nullptr, *vp8 = nullptr, *alph = nullptr;
+    size_t vp8l_len = 0, vp8_len = 0, alph_len = 0;
+    while (pos + 8 <= f.size()) {
+        const uint32_t len = (uint32_t)f[pos + 4] | ((uint32_t)f[pos + 5] << 8) | ((uint32_t)f[pos + 6] << 16) | ((uint32_t)f[pos + 7] << 24);
+        if (len > f.size() - pos - 8) return fail("truncated chunk");
+        if (!memcmp(&f[pos], "VP8L", 4)) { vp8l = &f[pos + 8]; vp8l_len = len; break; }
+        if (!memcmp(&f[pos], "VP8 ", 4)) { vp8 = &f[pos + 8]; vp8_len = len; break; }
+        if (!memcmp(&f[pos], "ALPH", 4)) { alph = &f[pos + 8]; alph_len = len; }
+        if (!memcmp(&f[pos], "ANIM", 4)) return fail("animated WebP is not supported");
+        pos += 8 + (size_t)len + (len & 1);
+    }
+    const char* err = "corrupt WebP";
+    if (vp8) {  // lossy: VP8 key frame [+ alpha plane]
+        vp8::Frame fr;
+        if (!vp8::decode_frame(vp8, vp8_len, fr, &err)) return fail(err);
+        w = fr.width;
+        h = fr.height;
+        std::vector<uint8_t> a;
+        if (alph && !decode_alpha(alph, alph_len, w, h, a, &err)) return fail(err);
+        c = alph ? 4 : 3;
+        pixels.resize((size_t)w * h * c);
+        vp8::frame_to_rgb(fr, pixels.data(), c);
+        if (alph)
+            for (size_t i = 0; i < a.size(); i++) pixels[i * 4 + 3] = a[i];
+        return true;
+    }
+    if (!vp8l || vp8l_len < 5 || vp8l[0] != 0x2f) return fail("no VP8 / VP8L bitstream");
+    BitReader br;
+    br.p = vp8l + 1;
+    br.n = vp8l_len - 1;
+    w = (int)br.get(14) + 1;
+    h = (int)br.get(14) + 1;
+    const bool alpha_hint = br.get(1) != 0;
+    if (br.get(3) != 0) return fail("unknown VP8L version");
+    std::vector<uint32_t> px;
+    if (!decode_stream(br, w, h, px, &err)) return fail(err);
     bool has_alpha = false;
     if (alpha_hint)
         for (uint32_t p : px)

@@ -199,7 +199,7 @@ def test_jpeg_encode_quality_100(bins, tmp_path):
 
 def test_webp_lossless_reader_and_writer(bins, tmp_path):
     """VP8L: files written by libwebp (Pillow) at several effort levels -- palette / pixel packing, colour cache, LZ77,
-    all transforms -- decode bit-exactly; files written here are decoded bit-exactly by libwebp; lossy files are refused"""
+    all transforms -- decode bit-exactly; files written here are decoded bit-exactly by libwebp"""
     rng = np.random.default_rng(31)
     yy, xx = np.mgrid[0:75, 0:101]
     img = np.stack([np.sin(xx / 9.) * 80 + 128 + yy / 2, np.cos(yy / 7.) * 70 + 120 + xx / 3, ((xx * yy) % 200) + 20.], -1)
@@ -223,10 +223,114 @@ def test_webp_lossless_reader_and_writer(bins, tmp_path):
         subprocess.run([os.path.join(bins, "png_tool"), "encode", raw, str(arr.shape[1]), str(arr.shape[0]), str(arr.shape[2]), out], check=True)
         assert np.array_equal(np.asarray(Image.open(out).convert(mode)), arr), name
         assert np.array_equal(decode(bins, out, str(tmp_path)), arr), name
-    p = str(tmp_path / "lossy.webp")
-    Image.fromarray(img).save(p, quality=80)
-    r = subprocess.run([os.path.join(bins, "png_tool"), "decode", p, str(tmp_path / "x.raw")], capture_output=True, text=True)
-    assert r.returncode == 1 and "lossy" in r.stderr
+
+
+def libwebp_encoder():
+    """libwebp's advanced encoder API (WebPConfig / WebPPicture / WebPEncode) of the libwebp that ships with Pillow, through ctypes: Pillow's
+    own save() exposes only quality / method, the bitstream features a decoder has to get right need more knobs"""
+    import ctypes
+    import glob
+    import PIL
+    libs = os.path.join(os.path.dirname(PIL.__file__), "..", "pillow.libs")
+    so = glob.glob(os.path.join(libs, "libwebp-*.so*"))
+    if not so:
+        return None
+    for dep in glob.glob(os.path.join(libs, "libsharpyuv-*.so*")):
+        ctypes.CDLL(dep, mode=ctypes.RTLD_GLOBAL)
+    L = ctypes.CDLL(so[0])
+    if (L.WebPGetEncoderVersion() >> 16) != 1:
+        return None  # the struct layouts below are those of libwebp 1.x
+    fields = ["lossless", "quality", "method", "image_hint", "target_size", "target_PSNR", "segments", "sns_strength", "filter_strength",
+              "filter_sharpness", "filter_type", "autofilter", "alpha_compression", "alpha_filtering", "alpha_quality", "pass_", "show_compressed",
+              "preprocessing", "partitions", "partition_limit", "emulate_jpeg_size", "thread_level", "low_memory", "near_lossless", "exact",
+              "use_delta_palette", "use_sharp_yuv", "qmin", "qmax"]
+
+    class Config(ctypes.Structure):
+        _fields_ = [(n, ctypes.c_float if n in ("quality", "target_PSNR") else ctypes.c_int) for n in fields]
+
+    class MemWriter(ctypes.Structure):
+        _fields_ = [("mem", ctypes.c_void_p), ("size", ctypes.c_size_t), ("max_size", ctypes.c_size_t), ("pad", ctypes.c_uint32 * 1)]
+
+    L.WebPConfigInitInternal.argtypes = [ctypes.POINTER(Config), ctypes.c_int, ctypes.c_float, ctypes.c_int]
+    abi = 0x020f  # WEBP_ENCODER_ABI_VERSION: only the major byte is compared
+
+    def encode(arr, quality=75, **kw):
+        cfg = Config()
+        assert L.WebPConfigInitInternal(ctypes.byref(cfg), 0, ctypes.c_float(quality), abi)
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        assert L.WebPValidateConfig(ctypes.byref(cfg)), kw
+        pic = (ctypes.c_uint8 * 512)()  # WebPPicture: width / height are ints 2 and 3, writer and custom_ptr sit at bytes 96 and 104
+        assert L.WebPPictureInitInternal(pic, abi)
+        h, w, c = arr.shape
+        ints = ctypes.cast(pic, ctypes.POINTER(ctypes.c_int))
+        ints[2], ints[3] = w, h
+        arr = np.ascontiguousarray(arr)
+        assert (L.WebPPictureImportRGBA if c == 4 else L.WebPPictureImportRGB)(pic, arr.ctypes.data_as(ctypes.c_void_p), w * c)
+        mw = MemWriter()
+        L.WebPMemoryWriterInit(ctypes.byref(mw))
+        ctypes.cast(ctypes.addressof(pic) + 96, ctypes.POINTER(ctypes.c_void_p))[0] = ctypes.cast(L.WebPMemoryWrite, ctypes.c_void_p).value
+        ctypes.cast(ctypes.addressof(pic) + 104, ctypes.POINTER(ctypes.c_void_p))[0] = ctypes.addressof(mw)
+        assert L.WebPEncode(ctypes.byref(cfg), pic), "WebPEncode failed"
+        data = ctypes.string_at(mw.mem, mw.size)
+        L.WebPPictureFree(pic)
+        return data
+
+    return encode
+
+
+def test_webp_lossy_reader_matches_libwebp(bins, tmp_path):
+    """VP8 key frames (host/vp8_codec.h) + ALPH planes: bit-exact RGB(A) against libwebp's WebPDecodeRGB(A) (through Pillow) -- intra
+    prediction incl. the frame-edge rules, token contexts, segments, 1..8 token partitions, simple and normal loop filter at several
+    strengths / sharpness, the 9-3-3-1 chroma upsampler and the fixed-point YUV->RGB; alpha raw / VP8L-coded with every prediction filter"""
+    rng = np.random.default_rng(41)
+    yy, xx = np.mgrid[0:90, 0:121]
+    smooth = np.stack([np.sin(xx / 9.) * 80 + 128 + yy / 2, np.cos(yy / 7.) * 70 + 120 + xx / 3, ((xx * yy) % 200) + 20.], -1)
+    smooth = np.clip(smooth + rng.normal(0, 4, smooth.shape), 0, 255).astype(np.uint8)
+    noise = rng.integers(0, 256, (70, 83, 3), dtype=np.uint8)
+    n = [0]
+
+    def check(data_or_arr, name, **save_kw):
+        p = str(tmp_path / (name + ".webp"))
+        if isinstance(data_or_arr, bytes):
+            open(p, "wb").write(data_or_arr)
+        else:
+            Image.fromarray(data_or_arr).save(p, "WEBP", **save_kw)
+        im = Image.open(p)
+        want = np.asarray(im.convert("RGBA" if im.mode == "RGBA" else "RGB"))
+        got = decode(bins, p, str(tmp_path))
+        assert got.shape == want.shape and np.array_equal(got, want), name
+        n[0] += 1
+
+    for src, sname in ((smooth, "smooth"), (noise, "noise"), (smooth[:5, :3], "tiny"), (smooth[:16, :16], "onemb"), (smooth[:17, :33], "ragged")):
+        for q in (0, 30, 75, 100):
+            for m in (0, 4, 6):
+                check(src, "%s_q%d_m%d" % (sname, q, m), quality=q, method=m)
+    rgba = np.dstack([smooth, (xx * 2 % 256).astype(np.uint8)])
+    rgba[:40, :50, 3] = 255
+    for aq in (100, 50):
+        check(rgba, "rgba_aq%d" % aq, quality=60, alpha_quality=aq)
+    enc = libwebp_encoder()
+    if enc is not None:
+        for src, sname in ((smooth, "smooth"), (noise, "noise")):
+            for ft in (0, 1):
+                for sharp, fs in ((0, 0), (0, 60), (3, 20), (7, 100)):
+                    check(enc(src, quality=40, filter_type=ft, filter_sharpness=sharp, filter_strength=fs, method=4), "%s_ft%d_sh%d_fs%d" % (sname, ft, sharp, fs))
+            for parts in (1, 2, 3):
+                check(enc(src, quality=60, partitions=parts, method=3), "%s_parts%d" % (sname, parts))
+            for seg, sns in ((1, 0), (2, 50), (4, 100)):
+                check(enc(src, quality=30, segments=seg, sns_strength=sns, method=5), "%s_seg%d" % (sname, seg))
+        for ac in (0, 1):
+            for af in (0, 1, 2):
+                check(enc(rgba, quality=50, alpha_compression=ac, alpha_filtering=af, alpha_quality=100 - 40 * af, method=4), "alpha_c%d_f%d" % (ac, af))
+    assert n[0] >= 62
+    # corrupt input is an error, not a crash
+    bad = bytearray(open(str(tmp_path / "smooth_q75_m4.webp"), "rb").read())
+    bad[23] ^= 0xff  # the VP8 start code
+    badp = str(tmp_path / "bad.webp")
+    open(badp, "wb").write(bytes(bad))
+    r = subprocess.run([os.path.join(bins, "png_tool"), "decode", badp, str(tmp_path / "x.raw")], capture_output=True, text=True)
+    assert r.returncode == 1 and "VP8" in r.stderr
 
 
 def cli(bins, *args):
@@ -294,6 +398,12 @@ def test_cli_pipeline_directory_mode(bins, tmp_path):
     r = cli(bins, "-i", wj, "-o", str(tmp_path / "w4.webp"), "-m", "models-DF2K")
     assert r.returncode == 0, r.stderr
     assert np.array_equal(np.asarray(Image.open(str(tmp_path / "w4.webp")).convert("RGB")), np.repeat(np.repeat(imgs["img05.png"], 4, 0), 4, 1))
+    # lossy webp in (VP8 key frame, host/vp8_codec.h), png out: the pixels the engine sees are libwebp's
+    wl = str(tmp_path / "lossy.webp")
+    Image.fromarray(smooth).save(wl, quality=70)
+    r = cli(bins, "-i", wl, "-o", str(tmp_path / "lossy4.png"), "-m", "models-DF2K")
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.asarray(Image.open(str(tmp_path / "lossy4.png"))), np.repeat(np.repeat(np.asarray(Image.open(wl).convert("RGB")), 4, 0), 4, 1))
     # file -> file
     one = str(tmp_path / "one.png")
     r = cli(bins, "-i", str(din / "img05.png"), "-o", one, "-m", "x/models-DF2K_JPEG")
