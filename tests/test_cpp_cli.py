@@ -142,6 +142,49 @@ def test_png_encode_roundtrip(bins, tmp_path, c):
     assert os.path.getsize(str(tmp_path / "smooth.png")) < smooth.size // 3  # filters + deflate do compress gradients
 
 
+def test_png_fast_writer_blocks_runs_and_stored_fallback(bins, tmp_path):
+    """the level-1 writer's own deflate (png_codec.h fastz: run-length matches + one dynamic Huffman code per 128-KB block, stored blocks
+    for incompressible data, bands spliced into one zlib stream): inflates bit-exactly with zlib (Pillow) and with the own reader over
+    degenerate sizes, long runs across block and band borders, noise, sparse and mixed content; and it is not larger than zlib level 1"""
+    rng = np.random.default_rng(77)
+
+    def rt(arr, name, threads):
+        h, w, c = arr.shape
+        raw, png = str(tmp_path / "rt.raw"), str(tmp_path / "rt.png")
+        np.ascontiguousarray(arr).tofile(raw)
+        subprocess.run([os.path.join(bins, "png_tool"), "encode", raw, str(w), str(h), str(c), png, "1", str(threads)], check=True)
+        got = np.asarray(Image.open(png))
+        assert got.shape == arr.shape and np.array_equal(got, arr), name
+        assert np.array_equal(decode(bins, png, str(tmp_path)), arr), name
+        return os.path.getsize(png)
+
+    for c in (3, 4):
+        for (h, w) in ((1, 1), (2, 1), (3, 5), (64, 300), (33, 5000)):
+            yy, xx = np.mgrid[0:h, 0:w]
+            sparse = np.zeros((h, w, c), np.uint8)
+            m = rng.random((h, w)) < 0.01
+            sparse[m] = rng.integers(0, 256, (int(m.sum()), c), dtype=np.uint8)
+            cases = {"noise": rng.integers(0, 256, (h, w, c), dtype=np.uint8), "flat": np.full((h, w, c), 200, np.uint8), "sparse": sparse,
+                     "runs": np.repeat(rng.integers(0, 256, (h, (w + 40) // 41, c), dtype=np.uint8), 41, axis=1)[:, :w],
+                     "smooth": np.stack([(xx * 3 + yy) % 256, (xx + yy * 2) // 3 % 256, (xx * yy) % 251, (xx + yy) % 256][:c], -1).astype(np.uint8)}
+            for name, a in cases.items():
+                for th in (1, 3):
+                    size = rt(a, "%s %dx%dx%d t%d" % (name, w, h, c, th), th)
+                if name == "flat":
+                    assert size < 200 + a.size // 200
+                if name == "noise" and a.size > 10000:
+                    assert size < a.size + a.size // 100 + 200  # stored blocks: no expansion beyond the headers
+    mixed = np.zeros((600, 1000, 3), np.uint8)  # several 128-KB blocks per band, runs that cross block and band borders
+    mixed[100:500, 200:800] = rng.integers(0, 256, (400, 600, 3), dtype=np.uint8)
+    s1, s4 = rt(mixed, "mixed", 1), rt(mixed, "mixed", 4)
+    assert abs(s1 - s4) < 2000
+    photo = np.asarray(Image.fromarray(rng.integers(0, 256, (60, 80, 3), dtype=np.uint8)).resize((640, 480), Image.BICUBIC))  # smooth, like an SR result
+    import io
+    buf = io.BytesIO()
+    Image.fromarray(photo).save(buf, "PNG", compress_level=1)
+    assert rt(photo, "photo", 2) < len(buf.getvalue())
+
+
 def test_jpeg_decode_matches_libjpeg(bins, tmp_path):
     """JPEG reader (sequential and progressive) vs Pillow (libjpeg-turbo): IDCT / upsampling / colour rounding differ by a
     few LSB at most"""
