@@ -115,6 +115,14 @@ RSR_API int rsr_check_model(const char* parampath, const char* modelpath, int* n
  * Returns the number of rows (packed may be NULL), or a negative code. */
 RSR_API long long rsr_debug_pack_rows(const char* parampath, const char* modelpath, int conv_index, uint16_t* packed, long long capacity);
 
+/* Host-only: the schedule rsr_process* would run for a w x h image with the handle's current tile size, prepadding, TTA mode and options
+ * (tiles [tile_first, tile_first + tile_count) of the row-major tile grid; tile_count < 0 = all): serialised as 64-bit integers
+ *   njobs, ndescs, padded_pixels, tta_bytes,
+ *   per job: ngroups, ngathers, tta_float4, ngroups x {first_desc, ntiles, H, W, first_pixel, tta_offset}, ngathers x {first_desc, ntiles, max_crop_w, max_crop_h, slot_stride, tta_offset},
+ *   ndescs x {in_x0, in_y0, out_x0, out_y0, crop_w, crop_h, variant, base_h, base_w, tta_slot}.
+ * Returns the number of integers (out may be NULL), or a negative code.  No model and no GPU needed. */
+RSR_API long long rsr_debug_plan(rsr_handle* h, int w, int h_, int tile_first, int tile_count, long long* out, long long capacity);
+
 #ifdef __cplusplus
 }
 #endif

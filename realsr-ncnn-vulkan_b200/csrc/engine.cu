@@ -473,10 +473,22 @@ int run_job(BatchCtx& c, const uint8_t* d_img, int img_w, int img_h, int img_c, 
     return 0;
 }
 
+// The schedule of one process() call, computed on the host before anything is enqueued (no CUDA involved: rsr_debug_plan exposes it to the
+// CPU tests): the tile grid of the reference, the tiles grouped by padded shape, the groups packed into jobs.
+struct CallPlan {
+    std::vector<TileDesc> flat;   // every descriptor the kernels index, in device order
+    std::vector<MJob> mjobs;      // every job = up to max_groups shape groups, one launch per layer
+    size_t max_tta_bytes = 0;
+    long long padded = 0;         // network-input pixels of the call
+};
+
 // tiles [tile_first, tile_first + tile_count) of the reference's row-major tile grid; `done` (optional) receives their descriptors
-int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, int hh, int ch, uint8_t* d_out, long long* padded_out,
-                      long long* launches_out, int tile_first, int tile_count, std::vector<TileDesc>* done, size_t* nconv_ev_out, long long* conv_launches_out, int T, int P)
+void plan_call(const rsr_handle* h, int w, int hh, int T, int P, int tile_first, int tile_count, CallPlan& pl, std::vector<TileDesc>* done)
 {
+    std::vector<TileDesc>& flat = pl.flat;
+    std::vector<MJob>& mjobs = pl.mjobs;
+    size_t& max_tta_bytes = pl.max_tta_bytes;
+    long long& padded = pl.padded;
     const int xtiles = (w + T - 1) / T, ytiles = (hh + T - 1) / T;
     // tile grid: reference src/realsr.cpp:170-171,:176-187,:235-241 (GPU) == :537-553 (CPU)
     std::map<std::pair<int, int>, std::vector<TileDesc>> groups;
@@ -493,15 +505,9 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
             groups[{t.base_h, t.base_w}].push_back(t);
             if (done) done->push_back(t);
         }
-    BatchCtx c{h, ws, T, P};
-    long long padded = 0;
-    int r;
     // Every batch of the call is planned first, so that all tile descriptors go to the device in ONE copy from pinned memory
     // and the batches then run back to back on the stream with no host synchronisation in between (same-stream order makes
     // the reuse of the activation buffers safe).  Larger shapes first: the workspace is sized once.
-    std::vector<TileDesc> flat;
-    std::vector<MJob> mjobs;  // every job = up to max_groups shape groups, one launch per layer
-    size_t max_tta_bytes = 0;
     {
         const double budget = 16e9;  // workspace bytes per job
         const int per_tile = h->tta ? 8 : 1;   // network passes per tile
@@ -572,6 +578,19 @@ int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, 
         }
         flush();
     }
+}
+
+int process_on_device(rsr_handle* h, Workspace* ws, const uint8_t* d_in, int w, int hh, int ch, uint8_t* d_out, long long* padded_out,
+                      long long* launches_out, int tile_first, int tile_count, std::vector<TileDesc>* done, size_t* nconv_ev_out, long long* conv_launches_out, int T, int P)
+{
+    BatchCtx c{h, ws, T, P};
+    int r;
+    CallPlan pl;
+    plan_call(h, w, hh, T, P, tile_first, tile_count, pl, done);
+    const std::vector<TileDesc>& flat = pl.flat;
+    const std::vector<MJob>& mjobs = pl.mjobs;
+    const size_t max_tta_bytes = pl.max_tta_bytes;
+    const long long padded = pl.padded;
     if (flat.size() > ws->h_tiles_cap) {
         if (ws->h_tiles) cudaFreeHost(ws->h_tiles);
         ws->h_tiles = nullptr;
@@ -833,6 +852,40 @@ int rsr_check_model(const char* parampath, const char* modelpath, int* num_rrdb,
     if (num_rrdb) *num_rrdb = m.num_rrdb;
     if (num_convs) *num_convs = (int)m.convs.size();
     return 0;
+}
+
+long long rsr_debug_plan(rsr_handle* h, int w, int hh, int tile_first, int tile_count, long long* out, long long capacity)
+{
+    if (!h || w <= 0 || hh <= 0 || tile_first < 0) return RSR_ERR_GENERIC;
+    int T, P;
+    {
+        std::lock_guard<std::mutex> g(h->mu);
+        T = h->tilesize;
+        P = h->prepadding;
+    }
+    if (tile_count < 0) tile_count = ((w + T - 1) / T) * ((hh + T - 1) / T);
+    CallPlan pl;
+    plan_call(h, w, hh, T, P, tile_first, tile_count, pl, nullptr);
+    std::vector<long long> v = {(long long)pl.mjobs.size(), (long long)pl.flat.size(), pl.padded, (long long)pl.max_tta_bytes};
+    for (const MJob& j : pl.mjobs) {
+        v.push_back((long long)j.gs.size());
+        v.push_back((long long)j.gathers.size());
+        v.push_back((long long)j.tta_float4);
+        for (const Grp& g : j.gs) {
+            const long long e[6] = {(long long)g.off, g.n, g.H, g.W, (long long)g.px_off, (long long)g.tta_off};
+            v.insert(v.end(), e, e + 6);
+        }
+        for (const GatherJob& g : j.gathers) {
+            const long long e[6] = {(long long)g.off, g.n, g.mw, g.mh, (long long)g.slot_stride, (long long)g.tta_off};
+            v.insert(v.end(), e, e + 6);
+        }
+    }
+    for (const TileDesc& t : pl.flat) {
+        const long long e[10] = {t.in_x0, t.in_y0, t.out_x0, t.out_y0, t.crop_w, t.crop_h, t.variant, t.base_h, t.base_w, t.tta_slot};
+        v.insert(v.end(), e, e + 10);
+    }
+    if (out && capacity >= (long long)v.size()) memcpy(out, v.data(), v.size() * sizeof(long long));
+    return (long long)v.size();
 }
 
 long long rsr_debug_pack_rows(const char* parampath, const char* modelpath, int conv_index, uint16_t* packed, long long capacity)

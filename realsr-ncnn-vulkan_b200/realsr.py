@@ -64,6 +64,8 @@ def load_library():
     lib.rsr_set_option.argtypes = [vp, cc, ll]
     lib.rsr_debug_conv.restype = ci
     lib.rsr_debug_conv.argtypes = [vp, ci, vp, ci, ci, vp]
+    lib.rsr_debug_plan.restype = ll
+    lib.rsr_debug_plan.argtypes = [vp, ci, ci, ci, ci, vp, ll]
     _LIB = lib
     return lib
 
@@ -156,6 +158,32 @@ class RealSR:
 
     def last_conv_launches(self):
         return int(self._lib.rsr_last_conv_launches(self._h))
+
+    def plan(self, w, h, tile_first=0, tile_count=-1):
+        """the schedule process() would run for a w x h image with the current parameters / options (host only, no model or GPU needed):
+        {"padded": px, "tta_bytes": n, "descs": (n, 10) int array of tile descriptors [in_x0, in_y0, out_x0, out_y0, crop_w, crop_h, variant,
+        base_h, base_w, tta_slot], "jobs": [{"groups": [dict(off, n, H, W, px_off, tta_off)], "gathers": [dict(off, n, mw, mh, slot_stride,
+        tta_off)], "tta_float4": n}]}"""
+        self._push_params()
+        n = self._lib.rsr_debug_plan(self._h, w, h, tile_first, tile_count, None, 0)
+        if n < 0:
+            raise RealSRError("rsr_debug_plan failed: %d" % n)
+        buf = np.zeros(n, dtype=np.int64)
+        assert self._lib.rsr_debug_plan(self._h, w, h, tile_first, tile_count, buf.ctypes.data, n) == n
+        v = buf.tolist()
+        njobs, ndesc, padded, tta_bytes = v[:4]
+        pos, jobs = 4, []
+        for _ in range(njobs):
+            ng, nga, tta4 = v[pos:pos + 3]
+            pos += 3
+            groups = [dict(zip(("off", "n", "H", "W", "px_off", "tta_off"), v[pos + 6 * i:pos + 6 * i + 6])) for i in range(ng)]
+            pos += 6 * ng
+            gathers = [dict(zip(("off", "n", "mw", "mh", "slot_stride", "tta_off"), v[pos + 6 * i:pos + 6 * i + 6])) for i in range(nga)]
+            pos += 6 * nga
+            jobs.append({"groups": groups, "gathers": gathers, "tta_float4": tta4})
+        descs = np.array(v[pos:pos + 10 * ndesc], dtype=np.int64).reshape(ndesc, 10)
+        assert pos + 10 * ndesc == n
+        return {"padded": padded, "tta_bytes": tta_bytes, "descs": descs, "jobs": jobs}
 
     def debug_conv(self, conv_index, x16, cout):
         """runs one conv layer of the loaded model on the tensor-core kernel: x16 (H, W, cin) float16 -> (H, W, cout) float32"""
