@@ -22,6 +22,13 @@ echo "built $(realpath $OUT)"
 # reference's proc stage
 /usr/bin/g++ -O2 -std=c++11 -Wall -o ../realsr_raw_cli ../host/realsr_raw_cli.cpp -L.. -lrealsr_b200 -Wl,-rpath,'$ORIGIN' -lpthread
 echo "built $(realpath ../realsr_raw_cli)"
-# the reference-shaped C++ command line (PNG through zlib)
+# the reference-shaped C++ command line (own PNG / JPEG / WebP codecs; zlib for inflate and checksums)
 /usr/bin/g++ -O2 -std=c++11 -Wall -o ../realsr-b200 ../host/realsr_cli.cpp -L.. -lrealsr_b200 -Wl,-rpath,'$ORIGIN' -lz -lpthread
 echo "built $(realpath ../realsr-b200)"
+# optional build variants for A/B runs on hardware (tools/ab_builds.py picks a library through RSR_LIB); never the default product
+if [ -n "$RSR_BUILD_VARIANTS" ]; then
+  $NVCC $FLAGS -DRSR_EARLY_HANDBACK -c conv3x3.cu -o build/conv3x3_early.o
+  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../librealsr_b200_early.so.tmp build/conv3x3_early.o build/misc_kernels.o build/engine.o build/model.o -ccbin /usr/bin/g++
+  mv -f ../librealsr_b200_early.so.tmp ../librealsr_b200_early.so
+  echo "built $(realpath ../librealsr_b200_early.so) (-DRSR_EARLY_HANDBACK: accumulator hand-back before the tap shuffles; not validated on hardware)"
+fi

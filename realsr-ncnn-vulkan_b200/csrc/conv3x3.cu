@@ -65,6 +65,20 @@ __host__ __device__ constexpr int a_bytes(int bh) { return (bh + 2) * P * KB * 2
 constexpr int A_SLACK = 512;                  // zeroed rows behind the box (kx taps of the last, never stored, positions)
 __host__ __device__ constexpr int a_stage(int bh) { return a_bytes(bh) + A_SLACK; }
 constexpr int NEPI = 8;                       // epilogue warps
+// Build variant -DRSR_EARLY_HANDBACK (librealsr_b200_early.so, NOT the default and never run on hardware so far): the epilogue returns
+// the accumulator set right after its last tcgen05.ld, BEFORE the tap-combining shuffles (~570 clk of the SM's shuffle unit per tile that
+// sit on the chain  MMAs done -> epilogue reads -> hand-back -> next MMAs of this set; matters for the convs with few K-blocks).  A/B it
+// with tools/ab_builds.py once a GPU is at hand.  Without the macro the preprocessed source -- and the SASS -- are those of the
+// validated kernel.
+#ifdef RSR_EARLY_HANDBACK
+#define RSR_HAND_BACK(bar_addr)                               \
+    do {                                                      \
+        tc_fence_before();                                    \
+        __syncwarp();                                         \
+        if (lane == 0) mbar_arrive_remote(bar_addr);          \
+        if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();          \
+    } while (0)
+#endif
 constexpr int EPI_WARP0 = 4;                  // first epilogue warp: warps 0..3 are the control warpgroup
 constexpr int NTHREADS = (EPI_WARP0 + NEPI) * 32;
 // epilogue staging per warp: CONV_STORE16 stages one 32-pixel row of its output as a dense, swizzled TMA-store source
@@ -416,6 +430,9 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                 tmem_ld32(taddr + 32, u);
                 tmem_ld32(taddr + 64, w);
                 tmem_ld_wait();
+#ifdef RSR_EARLY_HANDBACK
+                RSR_HAND_BACK(buf ? acc_empty1 : acc_empty0);
+#endif
 #pragma unroll
                 for (int j = 0; j < 32; j++)
                     f[j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
@@ -428,6 +445,9 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                     tmem_ld32(taddr + 64 + nb * 32, u);
                     tmem_ld32(taddr + 128 + nb * 32, w);
                     tmem_ld_wait();
+#ifdef RSR_EARLY_HANDBACK
+                    if (nb == 1) RSR_HAND_BACK(buf ? acc_empty1 : acc_empty0);
+#endif
 #pragma unroll
                     for (int j = 0; j < 32; j++)
                         f[nb * 32 + j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
@@ -436,10 +456,12 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
             }
             // Plain (CTA-scope release) remote arrive: only the TMEM reads have to be ordered (tcgen05 fence); a cluster-scope
             // release would also wait for this thread's global stores to drain.
+#ifndef RSR_EARLY_HANDBACK
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(buf ? acc_empty1 : acc_empty0);
             if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
+#endif
             if (a.act == 2) {
 #pragma unroll
                 for (int j = 0; j < NREAL; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * a.slope;
@@ -504,15 +526,20 @@ conv3x3_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs a, const in
                 tmem_ld32(taddr + 64 + nb * 32, u);
                 tmem_ld32(taddr + 128 + nb * 32, w);
                 tmem_ld_wait();
+#ifdef RSR_EARLY_HANDBACK
+                if (nb == 1) RSR_HAND_BACK(acc_empty_leader);
+#endif
 #pragma unroll
                 for (int j = 0; j < 32; j++)
                     t[nb * 32 + j] = __uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(u[j]), 1) +
                                      __shfl_down_sync(0xffffffffu, __uint_as_float(w[j]), 2);
             }
+#ifndef RSR_EARLY_HANDBACK
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(acc_empty_leader);  // early hand-back (CTA-scope release: only the TMEM reads have to be ordered)
             if (ts_on) a.dbg_ts[ti * 8 + 6] = clock64();
+#endif
             // one row of (fp16, int8) operands -> t = t * scale + operand, 8 channels per 16-B / 8-B chunk
             auto add_row = [&](const bool first) {
                 mbar_wait(ldbar, phl);

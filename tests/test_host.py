@@ -143,3 +143,19 @@ def test_options_and_tile_api_validate_without_gpu():
     assert e.tile_count(3840, 2160) == 220 and e.tile_count(1, 1) == 1
     img, out = np.zeros((40, 40, 3), np.uint8), np.zeros((160, 160, 3), np.uint8)
     assert e.process_tiles(img, out, 0, 1) != 0 and "no model" in e.last_error()
+
+
+def test_build_variant_compiles():
+    """-DRSR_EARLY_HANDBACK (csrc/conv3x3.cu, csrc/build.sh RSR_BUILD_VARIANTS): an A/B variant for hardware runs that is never the
+    default product -- it must at least keep compiling for sm_100a without spills"""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not installed")
+    src = os.path.join(ROOT, "realsr-ncnn-vulkan_b200", "csrc", "conv3x3.cu")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DRSR_EARLY_HANDBACK", "-Xptxas", "-v", "-c", src,
+                        "-o", os.devnull], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    spills = [int(x) for x in re.findall(r"(\d+) bytes spill stores", r.stderr)]
+    assert spills and max(spills) <= 64, r.stderr[-2000:]
