@@ -62,7 +62,8 @@ struct ConvArgs {
     // operand plus an int8 extension plane [px][64] that counts 1/256 of the fp16 value's ulp (res_ext_encode below): 8 more
     // mantissa bits for 64 B/px (an fp32 copy is 256 B/px; without the extension the README-crop golden has 3.2 % of its bytes off
     // by one, outside the 97 % contract).  res16/ext_in = this block's input x0; rr16/rr_ext = the input of the enclosing RRDB (read
-    // only when rrdb_end: t = 0.2*t + R, Eltwise x4.param:47); out16/ext_out = the next block's x0.
+    // only when rrdb_end: t = 0.2*t + R, Eltwise x4.param:47); out16/ext_out = the next block's x0.  The kernel reaches all of them
+    // through the row maps ConvMaps::rx / re / rrx / rre / o / reo (TMA); the pointers below name the same planes for the host side.
     const __half* res16;
     const uint8_t* ext_in;
     const __half* rr16;
