@@ -82,7 +82,8 @@ RSR_API int rsr_process_device(rsr_handle* h, const uint8_t* d_in, int w, int h_
 RSR_API int rsr_tile_count(const rsr_handle* h, int w, int h_);
 RSR_API int rsr_process_tiles(rsr_handle* h, const uint8_t* in, int w, int h_, int c, uint8_t* out, int tile_first, int tile_count);
 
-/* Last error message of this handle ("" if none).  The pointer stays valid until the next failing call. */
+/* Last error message of this handle ("" if none).  Thread-safe: the returned pointer is a per-thread copy, valid until this thread's
+ * next rsr_last_error() call. */
 RSR_API const char* rsr_last_error(const rsr_handle* h);
 
 /* ---- introspection used by the tests and the benchmark (no reference counterpart) ------------------------------ */
@@ -99,7 +100,8 @@ RSR_API long long rsr_last_conv_launches(const rsr_handle* h);
 /* Engine options: "max_batch" (tiles per job, 0 = auto), "merge_shapes" (1 default: one launch per layer over all shape groups of a
  * frame; 0: one job per shape group), "serpentine" (1 default: every second conv walks its tiles backwards, L2 reuse),
  * "time_convs" (CUDA events around every conv launch), "debug_mask" (timing experiments only, results become garbage: 1 = skip MMAs, 2 = skip
- * activation loads, 4 = skip weight loads, 8 = skip epilogue stores).  Unknown keys return RSR_ERR_GENERIC. */
+ * activation loads, 4 = skip weight loads, 8 = skip epilogue stores).  Unknown keys return RSR_ERR_GENERIC.  Set options between calls:
+ * a rsr_process* call that is already running may or may not see the new value. */
 RSR_API int rsr_set_option(rsr_handle* h, const char* key, long long value);
 
 /* Test hook: runs ONE 3x3 convolution of the loaded model (index in file order, >= 1) on the tensor-core kernel.

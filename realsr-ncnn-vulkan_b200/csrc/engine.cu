@@ -814,8 +814,14 @@ int rsr_process_device(rsr_handle* h, const uint8_t* d_in, int w, int h_, int c,
 
 int rsr_tile_count(const rsr_handle* h, int w, int h_)
 {
-    if (!h || w <= 0 || h_ <= 0 || h->tilesize <= 0) return 0;
-    return ((w + h->tilesize - 1) / h->tilesize) * ((h_ + h->tilesize - 1) / h->tilesize);
+    if (!h || w <= 0 || h_ <= 0) return 0;
+    int T;
+    {
+        std::lock_guard<std::mutex> g(const_cast<rsr_handle*>(h)->mu);
+        T = h->tilesize;
+    }
+    if (T <= 0) return 0;
+    return ((w + T - 1) / T) * ((h_ + T - 1) / T);
 }
 
 int rsr_process_tiles(rsr_handle* h, const uint8_t* in, int w, int h_, int c, uint8_t* out, int tile_first, int tile_count)
@@ -824,21 +830,39 @@ int rsr_process_tiles(rsr_handle* h, const uint8_t* in, int w, int h_, int c, ui
     return process_impl(h, in, w, h_, c, out, true, tile_first, tile_count);
 }
 
-const char* rsr_last_error(const rsr_handle* h) { return h ? h->err.c_str() : "null handle"; }
-long long rsr_kernel_launches(const rsr_handle* h) { return h ? h->launches : 0; }
-double rsr_last_ms(const rsr_handle* h, int what) { return !h ? 0.0 : (what == 1 ? h->last_conv_ms : h->last_ms); }
-long long rsr_last_padded_pixels(const rsr_handle* h) { return h ? h->last_padded : 0; }
-long long rsr_last_conv_launches(const rsr_handle* h) { return h ? h->last_conv_launches : 0; }
+const char* rsr_last_error(const rsr_handle* h)
+{
+    if (!h) return "null handle";
+    // several proc threads share one handle (main.cpp:811-828): hand out a per-thread copy taken under the lock, so that another thread's
+    // failure cannot reallocate the string this caller is still reading (valid until this thread's next rsr_last_error call)
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> g(const_cast<rsr_handle*>(h)->mu);
+    copy = h->err;
+    return copy.c_str();
+}
+// statistics: written by every finishing call under the handle mutex, so the getters take it too (proc threads share a handle)
+#define RSR_LOCKED_GET(h, expr, none)                                   \
+    do {                                                                \
+        if (!(h)) return (none);                                        \
+        std::lock_guard<std::mutex> g(const_cast<rsr_handle*>(h)->mu);  \
+        return (expr);                                                  \
+    } while (0)
+long long rsr_kernel_launches(const rsr_handle* h) { RSR_LOCKED_GET(h, h->launches, 0LL); }
+double rsr_last_ms(const rsr_handle* h, int what) { RSR_LOCKED_GET(h, what == 1 ? h->last_conv_ms : h->last_ms, 0.0); }
+long long rsr_last_padded_pixels(const rsr_handle* h) { RSR_LOCKED_GET(h, h->last_padded, 0LL); }
+long long rsr_last_conv_launches(const rsr_handle* h) { RSR_LOCKED_GET(h, h->last_conv_launches, 0LL); }
 
 int rsr_set_option(rsr_handle* h, const char* key, long long value)
 {
     if (!h || !key) return RSR_ERR_GENERIC;
+    if (strcmp(key, "max_batch") && strcmp(key, "serpentine") && strcmp(key, "merge_shapes") && strcmp(key, "debug_mask") && strcmp(key, "time_convs"))
+        return set_err(h, RSR_ERR_GENERIC, std::string("unknown option ") + key);
+    std::lock_guard<std::mutex> g(h->mu);  // (calls already running keep reading their options unlocked: set options between calls)
     if (!strcmp(key, "max_batch")) h->max_batch = value;
     else if (!strcmp(key, "serpentine")) h->serpentine = value ? 1 : 0;
     else if (!strcmp(key, "merge_shapes")) h->merge_shapes = value ? 1 : 0;
     else if (!strcmp(key, "debug_mask")) h->debug_mask = (int)value;
     else if (!strcmp(key, "time_convs")) h->time_convs = (int)value;
-    else return set_err(h, RSR_ERR_GENERIC, std::string("unknown option ") + key);
     return 0;
 }
 
