@@ -41,8 +41,39 @@ static void run(rsr_handle* h, int w, int hh, int c, int tile)
 
 int main(int argc, char** argv)
 {
-    if (argc != 3) return 64;
+    if (argc < 3) return 64;
     const std::string models = argv[1], mode = argv[2];
+    if (mode == "image" && argc == 11) {  // engine_host_test <models> image <model> <in.raw> w h c tile tta <out.raw>   (functional build)
+        const int w = atoi(argv[5]), hh = atoi(argv[6]), c = atoi(argv[7]), tile = atoi(argv[8]), tta = atoi(argv[9]);
+        rsr_handle* h = make(models, argv[3], 0, tta);
+        REQUIRE(rsr_set(h, 4, tile, 10) == 0);
+        if (const char* o = getenv("RSR_TWIN_OPTS")) {  // key=value[,key=value...]
+            std::string s = o;
+            for (size_t p = 0; p < s.size();) {
+                const size_t e = s.find(',', p), q = s.find('=', p);
+                REQUIRE(q != std::string::npos);
+                REQUIRE(rsr_set_option(h, s.substr(p, q - p).c_str(), atoll(s.c_str() + q + 1)) == 0);
+                p = e == std::string::npos ? s.size() : e + 1;
+            }
+        }
+        std::vector<uint8_t> in((size_t)w * hh * c), out((size_t)w * hh * c * 16, 0);
+        FILE* fp = fopen(argv[4], "rb");
+        REQUIRE(fp && fread(in.data(), 1, in.size(), fp) == in.size());
+        fclose(fp);
+        if (getenv("RSR_TWIN_SHARDS")) {  // the image in tile ranges, as sharded.process_sharded does with one handle per GPU
+            const int n = rsr_tile_count(h, w, hh), parts = atoi(getenv("RSR_TWIN_SHARDS"));
+            for (int k = 0; k < parts; k++) {
+                const int first = (int)((long long)n * k / parts), last = (int)((long long)n * (k + 1) / parts);
+                if (last > first && rsr_process_tiles(h, in.data(), w, hh, c, out.data(), first, last - first)) { fprintf(stderr, "process_tiles: %s\n", rsr_last_error(h)); return 1; }
+            }
+        } else if (rsr_process(h, in.data(), w, hh, c, out.data())) { fprintf(stderr, "process: %s\n", rsr_last_error(h)); return 1; }
+        fp = fopen(argv[10], "wb");
+        REQUIRE(fp && fwrite(out.data(), 1, out.size(), fp) == out.size());
+        fclose(fp);
+        printf("image ok: %lld launches\n", rsr_kernel_launches(h));
+        rsr_destroy(h);
+        return 0;
+    }
     if (mode == "sweep") {
         for (int tta = 0; tta < 2; tta++) {
             rsr_handle* h = make(models, tta ? "models-DF2K" : "models-DF2K_JPEG", tta, tta);

@@ -14,6 +14,7 @@
 #include <map>
 #include <mutex>
 
+#include "fake_map.h"
 #include "kernels.h"
 
 namespace {
@@ -36,16 +37,11 @@ void check(const void* p, size_t n, const char* what)
     --it;
     if (a < it->first || a + n > it->first + it->second) die(what, p, n);
 }
-struct FakeMap {  // what the fake encode stores inside the opaque CUtensorMap
-    uint64_t magic;
-    const void* base;
-    uint64_t extent;  // bytes from base to the end of the tensor
-};
 void check_map(const CUtensorMap* m, const char* what)
 {
     FakeMap f;
     memcpy(&f, m, sizeof f);
-    if (f.magic != 0x54454e534d4150ull) { fprintf(stderr, "fake_cuda: %s: tensor map was never encoded\n", what); abort(); }
+    if (f.magic != FAKE_MAP_MAGIC) { fprintf(stderr, "fake_cuda: %s: tensor map was never encoded\n", what); abort(); }
     check(f.base, f.extent, what);
 }
 }  // namespace
@@ -118,7 +114,6 @@ static CUresult fake_encode(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t r
         if (dims[i] == 0 || dims[i] > (1ull << 32) || box[i] == 0 || box[i] > 256 || estr[i] < 1 || estr[i] > 8) return CUDA_ERROR_INVALID_VALUE;
         if (i > 0) {
             if ((strides[i - 1] & 15) || strides[i - 1] >= (1ull << 40)) return CUDA_ERROR_INVALID_VALUE;
-            extent = extent > (dims[i] - 1) * strides[i - 1] + (i == 1 ? dims[0] * es : 0) ? extent : (dims[i] - 1) * strides[i - 1];
         }
     }
     // bytes from base to the last element: sum over dimensions of (dim - 1) * stride + one innermost row
@@ -128,7 +123,9 @@ static CUresult fake_encode(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t r
     const size_t span = sw == CU_TENSOR_MAP_SWIZZLE_32B ? 32 : sw == CU_TENSOR_MAP_SWIZZLE_64B ? 64 : sw == CU_TENSOR_MAP_SWIZZLE_128B ? 128 : (size_t)1 << 30;
     if ((inner & 15) || inner > span) return CUDA_ERROR_INVALID_VALUE;
     check(base, extent, "cuTensorMapEncodeTiled tensor");
-    FakeMap f{0x54454e534d4150ull, base, extent};
+    FakeMap f{};
+    f.magic = FAKE_MAP_MAGIC; f.base = base; f.extent = extent; f.elem_bytes = (uint32_t)es; f.rank = rank;
+    for (cuuint32_t i = 0; i < rank; i++) { f.dims[i] = dims[i]; if (i) f.strides[i - 1] = strides[i - 1]; }
     memset(m, 0, sizeof *m);
     memcpy(m, &f, sizeof f);
     std::lock_guard<std::mutex> g(g_mu);
@@ -147,7 +144,12 @@ long long fake_cuda_maps() { std::lock_guard<std::mutex> g(g_mu); return g_maps;
 long long fake_cuda_live_allocations() { std::lock_guard<std::mutex> g(g_mu); return (long long)g_alloc.size(); }
 }  // extern "C"
 
+void fake_cuda_check(const void* p, size_t n, const char* what) { check(p, n, what); }
+
 // ---- the kernel launchers (csrc/kernels.h): argument checks instead of kernels --------------------------------------------------------
+// (with -DFAKE_CUDA_FUNCTIONAL the launchers come from fake_kernels.cpp instead: the CUDA-core kernels run under the host emulation and
+// the conv kernel is replaced by a CPU model of its contract, so that whole images go through the engine)
+#ifndef FAKE_CUDA_FUNCTIONAL
 namespace rsr {
 
 static void count_launch() { std::lock_guard<std::mutex> g(g_mu); g_launches++; }
@@ -240,3 +242,4 @@ cudaError_t launch_alpha_bicubic4x(const AlphaArgs& a, cudaStream_t)
 }
 
 }  // namespace rsr
+#endif  // FAKE_CUDA_FUNCTIONAL
