@@ -84,6 +84,15 @@ int main(int argc, char** argv)
                         if (tta && (long long)s[0] * s[1] > 300 * 300) continue;
                         run(h, s[0], s[1], c, tile);
                     }
+            if (!tta) {  // the BASELINE configurations themselves (workspace up to the 16 GB job budget: virtual memory only, nothing touches it)
+                run(h, 1920, 1080, 3, 400);
+                REQUIRE(rsr_last_padded_pixels(h) == 2302800 && rsr_last_conv_launches(h) == 350);
+                run(h, 3840, 2160, 3, 200);
+                REQUIRE(rsr_last_padded_pixels(h) == 10091200);
+            } else {
+                run(h, 1280, 720, 3, 200);
+                REQUIRE(rsr_last_padded_pixels(h) == 9088000);
+            }
             // options that change the packing, a device-resident call, tile ranges of the sharded path, a model reload
             REQUIRE(rsr_set_option(h, "merge_shapes", 0) == 0);
             run(h, 333, 222, 3, 100);
