@@ -64,7 +64,10 @@ RSR_API int rsr_set(rsr_handle* h, int scale, int tilesize, int prepadding);
  *   out : (4w)*(4h)*c bytes, tightly packed HWC, allocated by the caller before the call (src/main.cpp:276) and
  *         written in place.
  *   c   : 3 (RGB) or 4 (RGBA: the alpha plane is up-scaled bicubically per tile like realsr.cpp:431-442, not by the network).
- * Host pointers.  Blocks until `out` is complete. */
+ * Host pointers.  Blocks until `out` is complete.
+ * Images with w or h <= prepadding (10): the reference's reflect-101 border (ncnn copy_make_border, one fold) then indexes outside
+ * the image -- its result is undefined; this library clamps the folded coordinate instead, so such images are processed without error
+ * but are outside the parity contract (the smallest well-defined sizes, 12x11, are golden-tested). */
 RSR_API int rsr_process(rsr_handle* h, const uint8_t* in, int w, int h_, int c, uint8_t* out);
 
 /* Same computation with `in` / `out` already resident in device memory of the handle's GPU (no H2D/D2H copies).
