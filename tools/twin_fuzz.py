@@ -15,9 +15,10 @@ shim = ["-include", FAKE + "/shim.h"]
 for cmd in (["g++", "-O2", "-std=c++17", "-w", *inc, *shim, "-c", "-x", "c++", CSRC + "/engine.cu", "-o", B + "/engine.o"],
             ["g++", "-O2", "-std=c++17", "-w", "-c", CSRC + "/model.cpp", "-o", B + "/model.o"],
             ["g++", "-O2", "-std=c++17", "-w", "-DFAKE_CUDA_FUNCTIONAL", *inc, *shim, "-c", FAKE + "/fake_cuda.cpp", "-o", B + "/fake_cuda.o"],
-            ["g++", "-O3", "-march=native", "-std=c++17", "-w", "-ffp-contract=off", *inc, "-c", FAKE + "/fake_kernels.cpp", "-o", B + "/fake_kernels.o"],
+            ["g++", "-O2", "-std=c++17", "-w", "-ffp-contract=off", *inc, "-c", FAKE + "/fake_kernels.cpp", "-o", B + "/fake_kernels.o"],
+            ["g++", "-O3", "-march=native", "-std=c++17", "-w", *inc, *shim, "-c", FAKE + "/fake_conv.cpp", "-o", B + "/fake_conv.o"],
             ["g++", "-O2", "-std=c++17", "-w", "-c", FAKE + "/engine_host_test.cpp", "-o", B + "/test.o"],
-            ["g++", "-o", B + "/engine_twin"] + [B + "/" + o for o in ("engine.o", "model.o", "fake_cuda.o", "fake_kernels.o", "test.o")] + ["-lpthread"]):
+            ["g++", "-o", B + "/engine_twin"] + [B + "/" + o for o in ("engine.o", "model.o", "fake_cuda.o", "fake_kernels.o", "fake_conv.o", "test.o")] + ["-lpthread"]):
     subprocess.check_call(cmd)
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 20
